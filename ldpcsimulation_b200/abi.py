@@ -1,0 +1,126 @@
+"""ctypes mirror of include/ldpc_gpu.h (structs and constants only; no library is loaded here)."""
+import ctypes as C
+
+OK = 0
+ERR_INVALID_ARG, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_COMM, ERR_IO, ERR_BAD_CODE = -1, -2, -3, -4, -5, -6, -7
+
+KIND_MINSUM, KIND_BP, KIND_GDBF, KIND_NGDBF_HW, KIND_DDBMP = 0, 1, 2, 3, 4
+
+F_QUANTIZE_SAMPLES = 1 << 0
+F_SATURATE_SAMPLES = 1 << 1
+F_NORMALIZED_MS = 1 << 2
+F_OFFSET_MS = 1 << 3
+F_SEQUENTIALMODE = 1 << 4
+F_MODESWITCHING = 1 << 5
+F_ADDNOISE = 1 << 6
+F_WEIGHTSYNDROMES = 1 << 7
+F_OUTPUTSMOOTHING = 1 << 8
+F_THRESHOLDADAPTATION = 1 << 9
+F_UNIFORMNOISE = 1 << 10
+F_NOISESHAPING = 1 << 11
+F_QUANTIZEPROBABILITIES = 1 << 12
+F_REDECODE = 1 << 13
+
+# reference -D macro name -> flag bit (C_implementations/Makefile:24-71)
+MACRO_FLAGS = {
+    "quantizeSamples": F_QUANTIZE_SAMPLES, "saturateSamples": F_SATURATE_SAMPLES,
+    "normalizedMS": F_NORMALIZED_MS, "offsetMS": F_OFFSET_MS,
+    "sequentialmode": F_SEQUENTIALMODE, "modeswitching": F_MODESWITCHING, "addNoise": F_ADDNOISE,
+    "weightSyndromes": F_WEIGHTSYNDROMES, "outputSmoothing": F_OUTPUTSMOOTHING,
+    "thresholdAdaptation": F_THRESHOLDADAPTATION, "uniformNoise": F_UNIFORMNOISE,
+    "noiseShaping": F_NOISESHAPING, "quantizeProbabilities": F_QUANTIZEPROBABILITIES, "redecode": F_REDECODE,
+}
+
+PREC_F64, PREC_F32 = 0, 1
+MEM_HOST, MEM_DEVICE = 0, 1
+DT_F64, DT_F32 = 0, 1
+HW_QBUF = 2648
+
+
+class DecoderCfg(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("flags", C.c_uint32), ("precision", C.c_int32), ("num_iterations", C.c_int32),
+        ("Ymax", C.c_double), ("Q", C.c_int32), ("NQ", C.c_int32),
+        ("alpha", C.c_double), ("delta", C.c_double), ("theta", C.c_double), ("lambda_", C.c_double),
+        ("noiseScale", C.c_double), ("windowsize", C.c_int32), ("maxphase", C.c_int32),
+        ("Tswitch", C.c_int32), ("reserved0", C.c_int32),
+        ("w", C.c_double), ("theta0", C.c_double), ("MAXLLR", C.c_double),
+    ]
+
+
+class Channel(C.Structure):
+    _fields_ = [("snr_db", C.c_double), ("R", C.c_double)]
+
+
+class Counters(C.Structure):
+    _fields_ = [
+        ("errors", C.c_int64), ("uncodedErrors", C.c_int64), ("totalBits", C.c_int64), ("totalWords", C.c_int64),
+        ("wordErrors", C.c_int64), ("totalIterations", C.c_int64), ("smoothingUsed", C.c_int64),
+        ("undetectedWords", C.c_int64),
+        ("error_weight_hist", C.POINTER(C.c_int64)), ("iter_hist", C.POINTER(C.c_int64)),
+        ("phase_hist", C.POINTER(C.c_int64)),
+    ]
+    SCALARS = ("errors", "uncodedErrors", "totalBits", "totalWords", "wordErrors", "totalIterations",
+               "smoothingUsed", "undetectedWords")
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k in self.SCALARS}
+
+
+class Batch(C.Structure):
+    _fields_ = [
+        ("n_frames", C.c_int64), ("mem", C.c_int32), ("y_dtype", C.c_int32),
+        ("y", C.c_void_p), ("noise", C.c_void_p), ("noise_rows", C.c_int64),
+        ("codeword", C.c_void_p), ("qpointer0", C.c_void_p),
+        ("out_bits", C.c_void_p), ("out_iters", C.c_void_p), ("out_soft", C.c_void_p),
+        ("out_errors", C.c_void_p), ("out_flags", C.c_void_p),
+    ]
+
+
+class SimArgs(C.Structure):
+    _fields_ = [
+        ("seed", C.c_uint64), ("frame_begin", C.c_int64), ("n_frames", C.c_int64),
+        ("stop_errors", C.c_int64), ("stop_word_errors", C.c_int64), ("poll_frames", C.c_int64),
+    ]
+
+
+def default_cfg(kind, **kw):
+    """Defaults = the reference's initial values of its parameter globals
+    (src/decodeGDBF.cpp:48-56, src/NGDBFhw.cpp:48-57, src/decodeBP.cpp:58)."""
+    c = DecoderCfg()
+    c.kind = kind
+    c.precision = PREC_F64
+    c.num_iterations = 10
+    c.Ymax, c.Q, c.NQ = 2.25, 5, 16
+    c.alpha, c.delta, c.theta, c.lambda_ = 2.25, 0.0, -0.6, 0.991
+    c.noiseScale, c.windowsize, c.maxphase, c.Tswitch = 1.0, 64, 7, 0
+    c.w, c.theta0, c.MAXLLR = 0.185, -0.525, 20.0
+    if kind == KIND_NGDBF_HW:
+        c.num_iterations, c.Ymax, c.noiseScale, c.maxphase, c.NQ = 600, 1.625, 0.95, 1, 5
+    if kind == KIND_MINSUM:
+        c.alpha = 1.25
+    for k, v in kw.items():
+        if k == "lambda":
+            k = "lambda_"
+        if k == "flags" and not isinstance(v, int):
+            v = sum(MACRO_FLAGS[m] for m in v)
+        if not hasattr(c, k):
+            raise AttributeError(k)
+        setattr(c, k, v)
+    return c
+
+
+def gdbf_rows_per_step(flags):
+    return (1 if flags & F_ADDNOISE else 0) + (1 if flags & F_QUANTIZEPROBABILITIES else 0)
+
+
+def noise_rows_needed(cfg):
+    if cfg.kind != KIND_GDBF:
+        return 0
+    ph = max(1, cfg.maxphase) if cfg.flags & F_REDECODE else 1
+    return cfg.num_iterations * ph * gdbf_rows_per_step(cfg.flags)
+
+
+def iter_hist_len(cfg):
+    ph = cfg.maxphase if (cfg.flags & F_REDECODE and cfg.kind == KIND_GDBF and cfg.maxphase > 1) else 1
+    return cfg.num_iterations * ph + 1
