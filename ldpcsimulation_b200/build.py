@@ -1,0 +1,71 @@
+"""Build recipe of the product: libldpc_gpu.so (sm_100a) and the C++ host mains.
+
+nvcc cross-compiles without a GPU.  -fmad=false: the parity instantiations must round every
+multiply and add separately, as the reference's x86-64 build does.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT, "libldpc_gpu.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
+              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-Wno-deprecated-gpu-targets"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def sources():
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
+    srcs.append(os.path.join(ROOT, "include", "ldpc_gpu.h"))
+    return srcs
+
+
+def build_library(force=False, verbose=False):
+    os.makedirs(OUT, exist_ok=True)
+    if not force and _newer(LIB, sources()):
+        return LIB
+    cmd = [NVCC] + NVCC_FLAGS + [os.path.join(CSRC, "ldpc_gpu.cu"), "-o", LIB, "-ldl"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    with open(os.path.join(OUT, "ptxas.log"), "w") as f:
+        f.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed")
+    if verbose:
+        print(r.stderr)
+    return LIB
+
+
+def build_host(force=False):
+    """C++ host mains that keep the reference binaries' positional CLIs (ldpcsimulation_b200/host)."""
+    host = os.path.join(HERE, "host")
+    src = os.path.join(host, "ldpcsim_main.cpp")
+    if not os.path.exists(src):
+        return None
+    bindir = os.path.join(ROOT, "bin")
+    os.makedirs(bindir, exist_ok=True)
+    exe = os.path.join(bindir, "ldpcsim")
+    if force or not _newer(exe, [src, LIB, os.path.join(ROOT, "include", "ldpc_gpu.h")]):
+        cmd = ["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), src, "-o", exe,
+               "-L" + OUT, "-lldpc_gpu", "-Wl,-rpath,$ORIGIN/../ldpcsimulation_b200/_build", "-ldl", "-lpthread"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("host build failed")
+    return exe
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_host(force="--force" in sys.argv))

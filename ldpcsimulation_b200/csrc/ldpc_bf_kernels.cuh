@@ -1,0 +1,370 @@
+// ldpc_bf_kernels.cuh -- bit-flipping decoders: the GDBF / NGDBF family (src/decodeGDBF.cpp,
+// src/RNGDBF.cpp) and the all-integer NGDBFhw model (src/NGDBFhw.cpp).
+//
+// One CTA owns one frame at a time; per-frame state on chip:
+//     yq[N] (Real)  theta[N] (Real)  shape[N] (Real, noiseShaping)  emet[N] (Real, sequential+adaptation)
+//     dsum[N] (int, smoothing)   d[N], r[N] (int8 +-1)   c2s[M] (int8 +-1)   dbits[N/32]
+// Each thread handles four consecutive variables per step, which is one Philox block of
+// perturbation noise (or four consecutive entries of the caller's noise row).
+// The syndrome is frozen during a flip step (the reference flips d in place but reads only c2s,
+// src/decodeGDBF.cpp:536-621), so flipping all variables in parallel is equivalent.
+#pragma once
+#include "ldpc_common.cuh"
+
+namespace ldpc {
+
+template <typename Real>
+struct GdbfSmem {
+    FrameScratch *fs; Real *yq, *theta, *shape, *emet; int *dsum; signed char *d, *r, *c2s; uint32_t *dbits; double *red; int *redi;
+};
+
+template <typename Real>
+static inline size_t gdbf_smem_bytes(const CodeDev &c)
+{
+    size_t n = 16 + sizeof(Real) * 4 * (size_t)c.N + 4 * (size_t)c.N + 2 * (size_t)c.N + (size_t)c.M + 16;
+    n = (n + 15) & ~(size_t)15;
+    n += 4 * (size_t)((c.N + 31) / 32) + 16;
+    n = (n + 15) & ~(size_t)15;
+    n += 8 * 32 + 4 * 32;                 // per-warp reduction scratch
+    return (n + 15) & ~(size_t)15;
+}
+
+template <typename Real>
+LDPC_DEVINL GdbfSmem<Real> gdbf_carve(unsigned char *raw, const CodeDev &c)
+{
+    GdbfSmem<Real> s;
+    s.fs = reinterpret_cast<FrameScratch *>(raw);
+    s.yq = reinterpret_cast<Real *>(raw + 16);
+    s.theta = s.yq + c.N; s.shape = s.theta + c.N; s.emet = s.shape + c.N;
+    s.dsum = reinterpret_cast<int *>(s.emet + c.N);
+    s.d = reinterpret_cast<signed char *>(s.dsum + c.N);
+    s.r = s.d + c.N; s.c2s = s.r + c.N;
+    size_t off = (size_t)(reinterpret_cast<unsigned char *>(s.c2s + c.M) - raw);
+    off = (off + 15) & ~(size_t)15;
+    s.dbits = reinterpret_cast<uint32_t *>(raw + off);
+    off += 4 * (size_t)((c.N + 31) / 32) + 16; off = (off + 15) & ~(size_t)15;
+    s.red = reinterpret_cast<double *>(raw + off);
+    s.redi = reinterpret_cast<int *>(raw + off + 8 * 32);
+    return s;
+}
+
+// Pack d (+-1 bytes) into dbits (bit = 1 <-> d = -1).  Ends with a barrier.
+LDPC_DEVINL void pack_decisions(const CodeDev &c, const signed char *d, uint32_t *dbits)
+{
+    const int npad = (c.N + 31) & ~31, lane = threadIdx.x & 31;
+    for (int i0 = threadIdx.x; i0 < npad; i0 += blockDim.x) {
+        const unsigned bal = __ballot_sync(0xffffffffu, i0 < c.N && d[i0] < 0);
+        if (lane == 0) dbits[i0 >> 5] = bal;
+    }
+    __syncthreads();
+}
+
+// evaluateObjectiveFunction (src/decodeGDBF.cpp:624-633).  The reference accumulates N+M terms
+// front to back in one double; the comparison f1 >= f2 that follows is an exact floating-point
+// test, so the sum is kept sequential (thread 0) instead of a tree.  Mode switching is not on the
+// throughput path.  Ends with a barrier; result valid in every thread.
+template <typename Real>
+LDPC_DEVINL double gdbf_objective(const CodeDev &c, const GdbfSmem<Real> &s)
+{
+    if (threadIdx.x == 0) {
+        double f = 0;
+        for (int i = 0; i < c.N; i++) f += (double)((Real)s.d[i] * s.yq[i]);
+        for (int j = 0; j < c.M; j++) f += (double)s.c2s[j];
+        s.red[0] = f;
+    }
+    __syncthreads();
+    const double f = s.red[0];
+    __syncthreads();
+    return f;
+}
+
+template <typename Real>
+__global__ void gdbf_kernel(const CodeDev c, const DecParams p, const FrameIO io)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const GdbfSmem<Real> s = gdbf_carve<Real>(smem_raw, c);
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int N = c.N, M = c.M, nblk = (N + 3) >> 2, T = p.T, W = p.windowsize;
+    const uint32_t fl = p.flags;
+    const bool redecode = (fl & LDPC_GPU_F_REDECODE) != 0;
+    const int maxphase = redecode ? (p.maxphase > 0 ? p.maxphase : 1) : 1;
+    const Real theta0 = (Real)p.theta, lambda = (Real)p.lambda;
+    const Real INF = real_inf<Real>();
+    CtaTotals tot; tot.clear();
+
+    for (long long f = blockIdx.x; f < io.n_frames; f += gridDim.x) {
+        const uint8_t *cw = codeword_row(io, c, f);
+        const unsigned long long fid = (unsigned long long)(io.frame_begin + f);
+        if (tid == 0) { s.fs->uncoded = 0; s.fs->errors = 0; s.fs->flag = 0; }
+        __syncthreads();
+        // ---- channel front end: src/decodeGDBF.cpp:251-274 / src/RNGDBF.cpp:251-275
+        int unc = 0;
+        for (int b = tid; b < nblk; b += nt) {
+            double y4[4];
+            raw_samples4(io, p, c, f, cw, b, y4);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = 4 * b + q;
+                if (i >= N) break;
+                double v = y4[q];
+                if (fl & LDPC_GPU_F_SATURATE_SAMPLES) if (fabs(v) > p.Ymax) v *= p.Ymax / fabs(v);
+                const bool rneg = !(v > 0);
+                if (fl & LDPC_GPU_F_QUANTIZE_SAMPLES) v = quantize_gdbf(v, p);
+                s.yq[i] = (Real)v;
+                const int cb = cw ? cw[i] : 0;
+                unc += (int)(rneg != (cb != 0));
+                s.r[i] = rneg ? -1 : 1; s.d[i] = rneg ? -1 : 1;
+                s.dsum[i] = 0; s.shape[i] = (Real)0; s.theta[i] = theta0;
+            }
+        }
+        for (int o = 16; o; o >>= 1) unc += __shfl_xor_sync(0xffffffffu, unc, o);
+        if (lane == 0 && unc) atomicAdd(&s.fs->uncoded, unc);
+        __syncthreads();
+
+        const Real noiseSigma = (Real)p.noiseSigma;
+        int it = 0, total_it = 0, phase = 0, satisfied = 1, smoothed = 0, smoothing_used = 0;
+        long long row = 0;                                            // next row of the noise array / Philox row
+        while (phase < maxphase) {                                    // src/RNGDBF.cpp:280-400
+            if (redecode) { for (int i = tid; i < N; i += nt) { s.d[i] = s.r[i]; s.dsum[i] = 0; } }
+            if (fl & LDPC_GPU_F_THRESHOLDADAPTATION) for (int i = tid; i < N; i += nt) s.theta[i] = theta0;
+            int mu = (fl & LDPC_GPU_F_SEQUENTIALMODE) ? 0 : 1;
+            __syncthreads();
+            double f1 = 0, f2 = 0;
+            for (it = 0; it < T; it++) {
+                // checkNodeUpdates, src/decodeGDBF.cpp:517-534
+                int bad = 0;
+                for (int j = tid; j < M; j += nt) {
+                    const int deg = c.cn_deg[j];
+                    int ng = 0;
+                    for (int k = 0; k < deg; k++) ng ^= (s.d[c.cn_var[(size_t)k * M + j]] < 0);
+                    s.c2s[j] = ng ? -1 : 1;
+                    bad |= ng;
+                }
+                satisfied = (__syncthreads_or(bad) == 0);
+                if (satisfied) break;                                 // :305-306
+                if ((fl & LDPC_GPU_F_MODESWITCHING) && it > p.Tswitch) f1 = gdbf_objective<Real>(c, s);
+
+                const long long row_pert = (fl & LDPC_GPU_F_ADDNOISE) ? row++ : -1;
+                const long long row_unif = (fl & LDPC_GPU_F_QUANTIZEPROBABILITIES) ? row++ : -1;
+                // symNodeUpdates, src/decodeGDBF.cpp:536-621
+                Real best = INF; int besti = -1;
+                for (int b = tid; b < nblk; b += nt) {
+                    double pert4[4] = {0, 0, 0, 0}, unif4[4] = {0, 0, 0, 0};
+                    if (row_pert >= 0) {                              // :318-333
+                        if (io.noise) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) if (4 * b + q < N) pert4[q] = io.noise[((size_t)f * io.noise_rows + row_pert) * N + 4 * b + q];
+                        } else if (fl & LDPC_GPU_F_UNIFORMNOISE) uniform4(io.seed, fid, (uint32_t)b, (uint32_t)row_pert, STREAM_DECODER, pert4);
+                        else { float n4[4]; normal4(io.seed, fid, (uint32_t)b, (uint32_t)row_pert, STREAM_DECODER, n4);
+#pragma unroll
+                               for (int q = 0; q < 4; q++) pert4[q] = (double)n4[q]; }
+                    }
+                    if (row_unif >= 0) {
+                        if (io.noise) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) if (4 * b + q < N) unif4[q] = io.noise[((size_t)f * io.noise_rows + row_unif) * N + 4 * b + q];
+                        } else uniform4(io.seed, fid, (uint32_t)b, (uint32_t)row_unif, STREAM_DECODER, unif4);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int i = 4 * b + q;
+                        if (i >= N) break;
+                        const int deg = c.vn_deg[i];
+                        const signed char di = s.d[i];
+                        Real E = (di > 0) ? s.yq[i] : -s.yq[i];                    // d[i]*y[i]
+                        Real wgt = (Real)1;
+                        if (fl & LDPC_GPU_F_WEIGHTSYNDROMES)
+                            wgt = redecode ? (Real)(p.alpha * p.Ymax / (double)deg)   // src/RNGDBF.cpp:566
+                                           : (Real)p.alpha;                           // src/decodeGDBF.cpp:550
+                        for (int sl = 0; sl < deg; sl++) E += (s.c2s[c.vn_chk[(size_t)sl * N + i]] > 0) ? wgt : -wgt;
+                        if (row_pert >= 0) {
+                            Real smp = (fl & LDPC_GPU_F_UNIFORMNOISE) ? (Real)(p.uni_scale * (pert4[q] - 0.5))
+                                                                      : (Real)(p.noiseSigma * pert4[q]);
+                            if (fl & LDPC_GPU_F_NOISESHAPING) { const Real prev = s.shape[i]; s.shape[i] = smp; smp = smp - prev; }
+                            E += smp;
+                        }
+                        bool flip = false;
+                        if (fl & LDPC_GPU_F_QUANTIZEPROBABILITIES) {               // :561-597
+                            const double val = ((double)(-E + s.theta[i])) / (double)noiseSigma;
+                            const double pcdf = 0.5 * erfc(-val * 0.70710678118654752440);
+                            const double lv[8] = { 0, 0.0625, 0.125, 0.25, 0.34375, 0.4106, 0.68359, 1 };
+                            double md = 1; int mi = 0;
+#pragma unroll
+                            for (int l = 0; l < 8; l++) { double t = lv[l] - pcdf; t = t * t; if (t < md) { md = t; mi = l; } }
+                            if (unif4[q] < lv[mi]) { flip = true; s.d[i] = -di; }
+                        } else {
+                            if (mu == 1 && E < s.theta[i]) { flip = true; s.d[i] = -di; }
+                            if (mu == 0) { s.emet[i] = E; if (E < best) { best = E; besti = i; } }
+                        }
+                        if ((fl & LDPC_GPU_F_THRESHOLDADAPTATION) && !(mu == 0 && !(fl & LDPC_GPU_F_QUANTIZEPROBABILITIES)))
+                            if (!flip) s.theta[i] *= lambda;                      // :612-617
+                    }
+                }
+                if (mu == 0 && !(fl & LDPC_GPU_F_QUANTIZEPROBABILITIES)) {
+                    // sequential mode: flip the first strict minimum (:604-610, :619-620)
+                    for (int o = 16; o; o >>= 1) {
+                        const Real ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+                        if (oi >= 0 && (besti < 0 || ob < best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+                    }
+                    if (lane == 0) { s.red[warp] = (double)best; s.redi[warp] = besti; }
+                    __syncthreads();
+                    if (tid == 0) {
+                        double bb = s.red[0]; int bi = s.redi[0];
+                        for (int wv = 1; wv < nwarps; wv++) { const double ob = s.red[wv]; const int oi = s.redi[wv];
+                            if (oi >= 0 && (bi < 0 || ob < bb || (ob == bb && oi < bi))) { bb = ob; bi = oi; } }
+                        if (bi >= 0) s.d[bi] = -s.d[bi];
+                        if (fl & LDPC_GPU_F_THRESHOLDADAPTATION) {
+                            // `flip` is raised at every new running minimum of E (:604-610), so theta_i is left
+                            // alone exactly at the prefix minima and multiplied by lambda elsewhere
+                            Real run = INF;
+                            for (int i = 0; i < N; i++) { const Real e = s.emet[i]; if (e < run) run = e; else s.theta[i] *= lambda; }
+                        }
+                    }
+                }
+                __syncthreads();
+                if ((fl & LDPC_GPU_F_MODESWITCHING) && it > p.Tswitch) {          // :338-346
+                    f2 = gdbf_objective<Real>(c, s);
+                    if (f1 >= f2) mu = 0;
+                }
+                if ((fl & LDPC_GPU_F_OUTPUTSMOOTHING) && it > T - W)               // :348-354
+                    for (int i = tid; i < N; i += nt) s.dsum[i] += s.d[i];
+            }
+            if (fl & LDPC_GPU_F_OUTPUTSMOOTHING) {
+                __syncthreads();
+                if (!satisfied) { for (int i = tid; i < N; i += nt) s.d[i] = (s.dsum[i] > 0) ? 1 : -1; smoothed = 1; }   // :358-367
+                else smoothed = 0;
+                if (it > T - W) smoothing_used++;                                  // :371-374
+            }
+            total_it += it; phase++;
+            __syncthreads();
+            if (!redecode || satisfied) break;                                    // src/RNGDBF.cpp:398-399
+        }
+        pack_decisions(c, s.d, s.dbits);
+        finish_frame(c, p, io, f, cw, s.dbits, s.fs, total_it, satisfied, smoothed, smoothing_used, phase, -1, tot);
+    }
+    if (tid == 0) tot.flush(io.counters);
+}
+
+// ---------------------------------------------------------------------------------------------
+// NGDBFhw: src/NGDBFhw.cpp.  All-integer flip metric on 5-bit sign-magnitude samples; the 2648-entry
+// per-frame noise buffer is read through a window that slides by one entry per iteration.
+// ---------------------------------------------------------------------------------------------
+static inline size_t hw_smem_bytes(const CodeDev &c)
+{
+    size_t n = 16 + (size_t)c.N * 3 + LDPC_GPU_HW_QBUF + (size_t)c.M + 16;
+    n = (n + 15) & ~(size_t)15;
+    n += 4 * (size_t)((c.N + 31) / 32) + 16;
+    return (n + 15) & ~(size_t)15;
+}
+
+__global__ void hw_kernel(const CodeDev c, const DecParams p, const FrameIO io)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FrameScratch *fs = reinterpret_cast<FrameScratch *>(smem_raw);
+    unsigned char *yprime = smem_raw + 16;                // 5-bit codes
+    signed char *d = reinterpret_cast<signed char *>(yprime + c.N);     // stored as +-1 (d01 = (1-d)/2)
+    signed char *r = d + c.N;
+    unsigned char *qprime = reinterpret_cast<unsigned char *>(r + c.N);
+    unsigned char *syn = qprime + LDPC_GPU_HW_QBUF;       // 0/1
+    size_t off = (size_t)(syn + c.M - smem_raw); off = (off + 15) & ~(size_t)15;
+    uint32_t *dbits = reinterpret_cast<uint32_t *>(smem_raw + off);
+
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int N = c.N, M = c.M, nblk = (N + 3) >> 2, T = p.T, QB = LDPC_GPU_HW_QBUF;
+    const int maxPhases = p.maxphase > 0 ? p.maxphase : 1;
+    CtaTotals tot; tot.clear();
+
+    for (long long f = blockIdx.x; f < io.n_frames; f += gridDim.x) {
+        const uint8_t *cw = codeword_row(io, c, f);
+        const unsigned long long fid = (unsigned long long)(io.frame_begin + f);
+        if (tid == 0) { fs->uncoded = 0; fs->errors = 0; fs->flag = 0; }
+        __syncthreads();
+        int unc = 0;
+        for (int b = tid; b < nblk; b += nt) {                        // :218-237
+            double y4[4];
+            raw_samples4(io, p, c, f, cw, b, y4);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = 4 * b + q;
+                if (i >= N) break;
+                double v = y4[q];
+                if (fabs(v) > p.Ymax) v *= p.Ymax / fabs(v);
+                const bool rneg = !(v > 0);
+                const int cb = cw ? cw[i] : 0;
+                unc += (int)(rneg && cb);                             // r*c < 0 with c in {0,1} (:141,230)
+                r[i] = rneg ? -1 : 1;
+                yprime[i] = (unsigned char)hw_pack(v / p.hw_two_w, p);
+            }
+        }
+        for (int b = tid; b < (QB + 3) / 4; b += nt) {                // :239-252
+            double n4[4];
+            if (io.noise) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) n4[q] = (4 * b + q < QB) ? io.noise[(size_t)f * QB + 4 * b + q] : 0.0;
+            } else { float nf[4]; normal4(io.seed, fid, (uint32_t)b, 0u, STREAM_DECODER, nf);
+#pragma unroll
+                     for (int q = 0; q < 4; q++) n4[q] = (double)nf[q]; }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = 4 * b + q;
+                if (i >= QB) break;
+                const double qv = p.noiseSigma * n4[q];
+                double qm = ((qv - p.theta0) / p.hw_two_w - 1.0);
+                if (qm > p.hw_lmax) qm = p.hw_lmax; else if (qm < -p.hw_lmax) qm = -p.hw_lmax;
+                qprime[i] = (unsigned char)hw_pack(qm, p);
+            }
+        }
+        for (int o = 16; o; o >>= 1) unc += __shfl_xor_sync(0xffffffffu, unc, o);
+        if (lane == 0 && unc) atomicAdd(&fs->uncoded, unc);
+        __syncthreads();
+
+        int qpointer = io.qpointer0 ? io.qpointer0[f] : 0;
+        int leastIterations = T, leastErrors = N, satisfied = 1, it = 0;
+        for (int phase = 0; phase < maxPhases; phase++) {             // :280-373
+            for (int i = tid; i < N; i += nt) d[i] = r[i];
+            __syncthreads();
+            for (it = 0; it < T; it++) {
+                int bad = 0;
+                for (int j = tid; j < M; j += nt) {                   // checkNodeUpdates :546-563
+                    const int deg = c.cn_deg[j];
+                    int ng = 0;
+                    for (int k = 0; k < deg; k++) ng ^= (d[c.cn_var[(size_t)k * M + j]] < 0);
+                    syn[j] = (unsigned char)ng;
+                    bad |= ng;
+                }
+                satisfied = (__syncthreads_or(bad) == 0);
+                if (satisfied) break;
+                for (int i = tid; i < N; i += nt) {                   // symNodeUpdates :565-593
+                    const int deg = c.vn_deg[i];
+                    int E = (int)d[i] * hw_unpack(yprime[i]);         // (1-2d01) = d
+                    int SSum = 0;
+                    for (int sl = 0; sl < deg; sl++) SSum += 1 - (int)syn[c.vn_chk[(size_t)sl * N + i]];
+                    E += SSum * p.hw_Smult + hw_unpack(qprime[i + qpointer]);
+                    if (E <= p.hw_theta) d[i] = -d[i];
+                }
+                qpointer++;                                           // :356-358
+                if (qpointer >= QB - N) qpointer = 0;
+                __syncthreads();
+            }
+            // countDecisionErrors against c in {0,1} (:362-372)
+            if (tid == 0) fs->errors = 0;
+            __syncthreads();
+            int le = 0;
+            for (int i = tid; i < N; i += nt) le += (int)((d[i] < 0) != ((cw ? cw[i] : 0) != 0));
+            for (int o = 16; o; o >>= 1) le += __shfl_xor_sync(0xffffffffu, le, o);
+            if (lane == 0 && le) atomicAdd(&fs->errors, le);
+            __syncthreads();
+            const int newErrors = fs->errors;
+            if (newErrors < leastErrors) leastErrors = newErrors;
+            if (it < leastIterations) leastIterations = it;
+            __syncthreads();
+        }
+        pack_decisions(c, d, dbits);
+        if (tid == 0) fs->errors = 0;
+        __syncthreads();
+        finish_frame(c, p, io, f, cw, dbits, fs, leastIterations, satisfied, 0, 0, maxPhases, leastErrors, tot);
+    }
+    if (tid == 0) tot.flush(io.counters);
+}
+
+} // namespace ldpc

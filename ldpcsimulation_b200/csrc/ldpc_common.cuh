@@ -1,0 +1,168 @@
+// ldpc_common.cuh -- pieces every decode kernel shares: the channel front end (a2/a3), the
+// per-frame epilogue and the accounting of a19 (src/decodeMinSum.cpp:270-288).
+#pragma once
+#include <math.h>
+#include "ldpc_types.cuh"
+#include "ldpc_rng.cuh"
+
+namespace ldpc {
+
+#define LDPC_DEVINL __device__ __forceinline__
+
+// sgn(0) = +1: src/decodeMinSum.cpp:518-523 (MS, BP, DD-BMP)
+LDPC_DEVINL bool neg_ge(double x) { return !(x >= 0.0); }
+LDPC_DEVINL bool neg_ge(float x)  { return !(x >= 0.0f); }
+// sgn(0) = -1: src/decodeGDBF.cpp:495-501 (GDBF family, NGDBFhw)
+LDPC_DEVINL bool neg_gt(double x) { return !(x > 0.0); }
+
+LDPC_DEVINL double absr(double x) { return fabs(x); }
+LDPC_DEVINL float  absr(float x)  { return fabsf(x); }
+template <typename Real> LDPC_DEVINL Real real_inf();
+template <> LDPC_DEVINL double real_inf<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
+template <> LDPC_DEVINL float  real_inf<float>()  { return __int_as_float(0x7f800000); }
+
+// a3: MS / DD-BMP quantiser, src/decodeMinSum.cpp:480-489
+LDPC_DEVINL double quantize_ms(double x, const DecParams &p)
+{
+    const double s = neg_ge(x) ? -1.0 : 1.0;
+    if (fabs(x) > p.Ymax) return s * p.Ymax;
+    double q = s * (floor(fabs(x) * p.ms_Nq1 / p.ms_twoY) + 0.0) * p.ms_step;
+    if (q == 0.0) q = s * p.ms_step;
+    return q;
+}
+// a3: GDBF quantiser, src/decodeGDBF.cpp:488-493
+LDPC_DEVINL double quantize_gdbf(double x, const DecParams &p)
+{
+    const double s = neg_gt(x) ? -1.0 : 1.0;
+    return s * floor((fabs(x) * p.g_qmax) / p.g_twol + 0.5) * p.g_step;
+}
+// a3/a17: NGDBFhw quantize(double)+pack(), src/NGDBFhw.cpp:639-663 (NQ = 5)
+LDPC_DEVINL int hw_pack(double ymod, const DecParams &p)
+{
+    const bool neg = neg_gt(ymod);
+    const int k = (int)floor(fabs(ymod) * p.hw_NL / p.hw_two_lmax);
+    return (k & 31) | (neg ? 16 : 0);
+}
+// a17: unpack(), src/NGDBFhw.cpp:665-677
+LDPC_DEVINL int hw_unpack(int code)
+{
+    const int mag = ((code << 1) & 31) | 1;
+    return (code & 16) ? -mag : mag;
+}
+
+// Which codeword row does frame f carry?  decode_batch: row f of `codeword`; simulate: row
+// (frame id mod n_cw) of the table (data.enc is read cyclically, src/decodeMinSum.cpp:195-211).
+LDPC_DEVINL const uint8_t *codeword_row(const FrameIO &io, const CodeDev &c, long long f)
+{
+    if (io.codeword) return io.codeword + (size_t)f * c.N;
+    if (io.cw_table && io.n_cw > 0) return io.cw_table + (size_t)((unsigned long long)(io.frame_begin + f) % (unsigned long long)io.n_cw) * c.N;
+    return nullptr;
+}
+
+// a2: four raw channel samples y = x(1 + sigma n) of block b (src/decodeMinSum.cpp:216), from the
+// caller's array or from the Philox channel.
+LDPC_DEVINL void raw_samples4(const FrameIO &io, const DecParams &p, const CodeDev &c, long long f, const uint8_t *cw, int b, double y[4])
+{
+    const int i0 = 4 * b;
+    if (io.y) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = i0 + q;
+            if (i < c.N) y[q] = (io.y_dtype == LDPC_GPU_DT_F64) ? ((const double *)io.y)[(size_t)f * c.N + i]
+                                                                : (double)((const float *)io.y)[(size_t)f * c.N + i];
+            else y[q] = 1.0;
+        }
+    } else {
+        float n[4];
+        normal4(io.seed, (unsigned long long)(io.frame_begin + f), (uint32_t)b, 0u, STREAM_CHANNEL, n);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = i0 + q;
+            const double x = (cw && i < c.N && cw[i]) ? -1.0 : 1.0;
+            y[q] = __dmul_rn(x, __dadd_rn(1.0, __dmul_rn(p.sigma, (double)n[q])));
+        }
+    }
+}
+
+// Per-CTA running totals (thread 0's registers), flushed once per launch.
+struct CtaTotals {
+    unsigned long long v[CNT_N];
+    LDPC_DEVINL void clear() {
+#pragma unroll
+        for (int q = 0; q < CNT_N; q++) v[q] = 0ull;
+    }
+    LDPC_DEVINL void flush(unsigned long long *g) {
+        if (!g) return;
+#pragma unroll
+        for (int q = 0; q < CNT_N; q++) if (v[q]) atomicAdd(&g[q], v[q]);
+    }
+};
+
+// Shared scratch every kernel reserves at the front of its dynamic shared memory.
+struct FrameScratch {
+    int uncoded;      // increments of uncodedErrors for the current frame
+    int errors;       // Hamming distance to the codeword
+    int flag;         // block-wide boolean scratch
+    int pad;
+};
+
+// End of frame: count decision errors against the codeword (countDecisionErrors,
+// src/decodeMinSum.cpp:382-393), emit the per-frame outputs and do the accounting of
+// src/decodeMinSum.cpp:270-288.  `dbits` holds the hard decisions, bit i = 1 <-> d_i = -1.
+// Must be called by every thread of the CTA; ends with a barrier.
+LDPC_DEVINL void finish_frame(const CodeDev &c, const DecParams &p, const FrameIO &io, long long f, const uint8_t *cw,
+                              const uint32_t *dbits, FrameScratch *fs, int it, int satisfied, int smoothed,
+                              int smoothing_used, int phases, int errors_override, CtaTotals &tot)
+{
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int npad = (c.N + 31) & ~31;
+    const size_t bpf = (size_t)(c.N + 7) >> 3;
+    int local_err = 0;
+    for (int i0 = tid; i0 < npad; i0 += nt) {
+        const bool valid = i0 < c.N;
+        const uint32_t word = dbits[i0 >> 5];
+        const int bit = (word >> lane) & 1;
+        const int cb = (valid && cw) ? cw[i0] : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, valid && (bit != cb));
+        if (lane == 0) local_err += __popc(bal);
+        if (io.out_bits && valid && (lane & 7) == 0) io.out_bits[(size_t)f * bpf + (i0 >> 3)] = (uint8_t)((word >> lane) & 0xffu);
+    }
+    if (lane == 0 && local_err) atomicAdd(&fs->errors, local_err);
+    __syncthreads();
+    if (tid == 0) {
+        const int e = errors_override >= 0 ? errors_override : fs->errors;
+        if (io.out_iters)  io.out_iters[f] = it;
+        if (io.out_errors) io.out_errors[f] = e;
+        if (io.out_flags)  io.out_flags[f] = (uint8_t)((satisfied ? 1 : 0) | (smoothed ? 2 : 0) | ((phases & 15) << 4));
+        if (e > 0) {
+            tot.v[CNT_ERRORS] += (unsigned long long)e; tot.v[CNT_WORDERRS] += 1ull;
+            if (io.ew_hist) atomicAdd(&io.ew_hist[e - 1], 1ull);
+            if (satisfied) tot.v[CNT_UNDETECTED] += 1ull;
+        }
+        tot.v[CNT_UNCODED] += (unsigned long long)fs->uncoded;
+        tot.v[CNT_WORDS] += 1ull; tot.v[CNT_BITS] += (unsigned long long)c.N; tot.v[CNT_ITERS] += (unsigned long long)it;
+        tot.v[CNT_SMOOTH] += (unsigned long long)smoothing_used;
+        if (io.it_hist && it < p.iter_hist_len) atomicAdd(&io.it_hist[it], 1ull);
+        if (io.ph_hist && (p.flags & LDPC_GPU_F_REDECODE) && p.kind == LDPC_GPU_KIND_GDBF) atomicAdd(&io.ph_hist[phases - 1], 1ull);
+    }
+    __syncthreads();
+}
+
+// All parity checks satisfied by the decisions in dbits?  Every thread must call; returns the
+// same value in every thread.
+LDPC_DEVINL bool syndrome_ok(const CodeDev &c, const uint32_t *dbits)
+{
+    int bad = 0;
+    for (int j = threadIdx.x; j < c.M; j += blockDim.x) {
+        const int deg = c.cn_deg[j];
+        unsigned par = 0;
+        for (int k = 0; k < deg; k++) {
+            const uint32_t i = c.cn_var[(size_t)k * c.M + j];
+            par ^= dbits[i >> 5] >> (i & 31);
+        }
+        bad |= (int)(par & 1u);
+    }
+    return __syncthreads_or(bad) == 0;
+}
+
+} // namespace ldpc

