@@ -1,0 +1,325 @@
+#!/usr/bin/env python3
+"""bench.py -- coded Gbit/s decoded at fixed iterations, on N B200s, next to the host-CPU reference.
+
+Workload (BASELINE.json configs[1] / SURVEY.md 8(d) M1): IEEE 802.3an (2048,1723) RS-LDPC
+(codes/802_3/802_3_H.alist: N=2048, M=384, E=12288), normalised min-sum (the reference's
+decodeNormalizedMinSum: quantizeSamples + normalizedMS), T=10 fixed iterations (the reference has no
+early stop for min-sum), all-zero codeword, BPSK/AWGN at Eb/N0 = 4.0 dB, R = 0.8413.
+
+  step        one pass of the hot path over one batch: ldpc_gpu_simulate() = Philox channel ->
+              condition/quantise -> T iterations -> decisions -> error counting, all in one kernel
+  value       whole-job coded Gbit/s of that step (no input to stage: samples are generated in-kernel)
+  e2e         the same decoder through the reference-facing call ldpc_gpu_decode_batch() with HOST
+              buffers: pinned fp32 samples H2D, kernel, packed decisions + iteration counts D2H
+  roofline    algorithmic message bytes ((4E+N)*b per frame-iteration) over the kernel
+              time measured with CUDA events on the launching stream, against the measured HBM peak
+  cpu_baseline / --impl reference
+              the reference's own object code (oracle/_ref), one process per host core
+
+One process per GPU (torchrun for N>1); frames are sharded by frame-id range, the only collective is
+the final NCCL all-reduce of the counters (ldpc_gpu_allreduce_counters).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(code="802_3_H", variant="decodeNormalizedMinSum", snr_db=4.0, R=0.8413, T=10,
+                cfg=dict(Ymax=2.0, Q=6, alpha=1.25))
+N_BITS, M_CHK, E_EDGES = 2048, 384, 12288
+
+
+def cfg_of(abi, precision):
+    return abi.default_cfg(abi.KIND_MINSUM, flags=["quantizeSamples", "normalizedMS"], num_iterations=WORKLOAD["T"],
+                           precision=precision, **WORKLOAD["cfg"])
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference(frames_per_proc, reps=1, cores=None):
+    """The reference's CPU implementation of the path on the host cores: one process per core."""
+    cores = cores or os.cpu_count() or 1
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "cpu_worker.py"), "--variant", WORKLOAD["variant"],
+           "--code", WORKLOAD["code"], "--snr", str(WORKLOAD["snr_db"]), "--rate", str(WORKLOAD["R"]),
+           "--iters", str(WORKLOAD["T"]), "--frames", str(frames_per_proc), "--reps", str(reps),
+           "--cfg", json.dumps(WORKLOAD["cfg"])]
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen(cmd + ["--seed", str(100 + i)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for i in range(cores)]
+    outs = []
+    for p in procs:
+        o, e = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("cpu worker failed: " + e[-400:])
+        outs.append(json.loads(o.strip().splitlines()[-1]))
+    wall = time.perf_counter() - t0
+    fps = sum(o["frames_per_s"] for o in outs)
+    return {"value": fps * N_BITS / 1e9, "unit": "Gbit/s", "cores": cores, "kind": outs[0]["kind"],
+            "frames_per_s": fps, "wall_s": wall,
+            "sample": "%d frames x %d rep(s) per process, %d processes, frame loop only, %s built -O2" %
+                      (frames_per_proc, reps, cores, "oracle/_ref (reference object code)" if outs[0]["kind"] == "reference" else "oracle port")}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    frames = 96
+    for _ in range(args.warmup):
+        cpu_reference(8)
+    t0 = time.perf_counter()
+    res = [cpu_reference(frames) for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    val = statistics.mean(r["value"] for r in res)
+    line = {"impl": "reference", "metric": "coded Gbit/s decoded at fixed iters", "value": val, "unit": "Gbit/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_block("cpu"),
+            "cpu_baseline": {"value": val, "unit": "Gbit/s", "cores": res[0]["cores"], "kind": res[0]["kind"], "sample": res[0]["sample"]},
+            "e2e": {"value": val, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def config_block(where, frames_per_step=None, e2e_frames=None):
+    c = {"workload": "IEEE 802.3an (2048,1723) RS-LDPC 802_3_H.alist, normalised min-sum (decodeNormalizedMinSum: "
+                     "Ymax=2.0 Q=6 alpha=1.25), T=10 fixed iterations, all-zero codeword, BPSK/AWGN Eb/N0=4.0 dB R=0.8413",
+         "code": "802_3_H", "N": N_BITS, "M": M_CHK, "E": E_EDGES, "T": WORKLOAD["T"], "snr_db": WORKLOAD["snr_db"],
+         "decoder": WORKLOAD["variant"]}
+    if where == "gpu":
+        c.update({"frames_per_step_per_gpu": frames_per_step, "e2e_frames_per_step_per_gpu": e2e_frames,
+                  "parallelism": "frames sharded by frame-id range, one process per GPU, final NCCL all-reduce of counters",
+                  "l2": "value: no resident input to flush (channel samples are generated in-kernel by Philox); "
+                        "e2e: every step streams a fresh host batch far larger than L2"})
+    return c
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--frames", type=int, default=1 << 20, help="frames per step per GPU (value)")
+    ap.add_argument("--e2e-frames", type=int, default=1 << 17, help="frames per step per GPU (e2e, host buffers)")
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    from ldpcsimulation_b200 import abi, capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if capi.device_count() < 1:
+        raise RuntimeError("bench.py: no CUDA device visible (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # CPU baseline first (rank 0, N=1 only), before the GPU is busy
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_reference(160)
+
+    prec = abi.PREC_F32 if args.precision == "f32" else abi.PREC_F64
+    code = capi.Code(os.path.join(ROOT, "codes", "802_3", "802_3_H.alist"))
+    cfg = cfg_of(abi, prec)
+    dec = capi.Decoder(code, cfg, device=local)
+    geo = dec.geometry()
+    snr, R, F = WORKLOAD["snr_db"], WORKLOAD["R"], args.frames
+
+    # the path's one collective: library-owned NCCL communicator, id distributed over torch.distributed
+    if world > 1:
+        import ctypes as C
+        idbuf = (C.c_uint8 * 128)()
+        if rank == 0:
+            capi.check(capi.lib().ldpc_gpu_comm_unique_id(idbuf))
+        t = torch.tensor(list(idbuf), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        idbuf = (C.c_uint8 * 128)(*t.cpu().tolist())
+        capi.check(capi.lib().ldpc_gpu_comm_init(idbuf, rank, world, local))
+
+    def step(i):
+        # disjoint global frame-id ranges per (step, rank): the union over ranks is one Monte-Carlo run
+        return dec.simulate(snr, R, 1234, (i * world + rank) * F, F)
+
+    launches, kernel_ms = 0, 0.0
+    for i in range(args.warmup):
+        step(i)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    total = None
+    for i in range(args.steps):
+        r = step(args.warmup + i)
+        ms, nl = dec.last_timing()
+        kernel_ms += ms
+        launches += nl
+        if total is None:
+            total = dict(r.counters)
+        else:
+            for k in total:
+                total[k] += r.counters[k]
+        last = r
+    if world > 1:                                       # final all-reduce of the counters, inside the timed region
+        cnt = last["_cnt"]
+        for k in total:
+            setattr(cnt, k, total[k])
+        capi.check(capi.lib().ldpc_gpu_allreduce_counters(cnt, code.N, cfg.num_iterations, 1))
+        total = cnt.as_dict()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        tw = torch.tensor([wall, kernel_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        wall, kernel_ms = float(tw[0]), float(tw[1])
+    frames_total = F * args.steps * world
+    value = frames_total * N_BITS / wall / 1e9
+
+    # ---- e2e: reference-facing call with host buffers -------------------------------------------
+    Fe = args.e2e_frames
+    sigma = float(np.sqrt(10 ** (-snr / 10) / R / 2))
+    gen = torch.Generator(device="cuda").manual_seed(7 + rank)
+    y_host = torch.empty((Fe, N_BITS), dtype=torch.float32, pin_memory=True)
+    y_host.copy_(1.0 + sigma * torch.randn((Fe, N_BITS), generator=gen, device="cuda", dtype=torch.float32))
+    bits_host = torch.empty((Fe, N_BITS // 8), dtype=torch.uint8, pin_memory=True)
+    iters_host = torch.empty((Fe,), dtype=torch.int32, pin_memory=True)
+    torch.cuda.synchronize()
+    b = abi.Batch()
+    b.n_frames, b.mem, b.y_dtype = Fe, abi.MEM_HOST, abi.DT_F32
+    b.y, b.out_bits, b.out_iters = y_host.data_ptr(), bits_host.data_ptr(), iters_host.data_ptr()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        dec.decode_raw(snr, R, b)
+    barrier()
+    t1 = time.perf_counter()
+    e2e_launches = 0
+    for _ in range(e2e_steps):
+        dec.decode_raw(snr, R, b)
+        e2e_launches += dec.last_timing()[1]
+    barrier()
+    e2e_wall = time.perf_counter() - t1
+    if dist is not None:
+        tw = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        e2e_wall = float(tw[0])
+    e2e_value = Fe * e2e_steps * world * N_BITS / e2e_wall / 1e9
+    ber_e2e = float(np.unpackbits(bits_host.numpy()).mean())
+
+    if world > 1:
+        capi.lib().ldpc_gpu_comm_destroy()
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+
+    b_msg = 4 if prec == abi.PREC_F32 else 8
+    bytes_per_frame = WORKLOAD["T"] * (4 * E_EDGES + N_BITS) * b_msg           # B_iter * T, B_io = 0 (fused channel)
+    peak, peak_src = measured_peak()
+    achieved = F * args.steps * bytes_per_frame / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+    line = {
+        "metric": "coded Gbit/s decoded at fixed iters", "value": value, "unit": "Gbit/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": config_block("gpu", F, Fe),
+        "e2e": {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": Fe * N_BITS * 4,
+                "d2h_bytes_per_step": Fe * (N_BITS // 8 + 4), "steps": e2e_steps, "api": "ldpc_gpu_decode_batch(mem=HOST, fp32 samples)",
+                "decoded_ber": ber_e2e},
+        "gpu_launches": int(launches), "e2e_gpu_launches": int(e2e_launches),
+        "kernel_ms_per_step": kernel_ms / args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_frame": bytes_per_frame,
+                     "note": "messages never leave the SM (shared memory), so algorithmic message bytes over kernel time can "
+                             "exceed the HBM copy peak; see DESIGN.md for the shared-memory / issue-slot view"},
+        "geometry": geo, "counters": total, "ber": total["errors"] / max(1, total["totalBits"]),
+        "fer": total["wordErrors"] / max(1, total["totalWords"]),
+        "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
