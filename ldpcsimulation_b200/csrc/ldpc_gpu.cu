@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "ldpc_mp_kernels.cuh"
+#include "ldpc_ms_fast.cuh"
 #include "ldpc_bf_kernels.cuh"
 
 using namespace ldpc;
@@ -263,7 +264,9 @@ static int build_device_code(ldpc_gpu_decoder *d, const ldpc_gpu_code *c)
     std::vector<uint32_t> cn_var((size_t)dcm * M, 0), vn_chk((size_t)dvm * N, 0);
     for (int j = 0; j < M; j++) for (int k = 0; k < c->row_deg[j]; k++) cn_var[(size_t)k * M + j] = (uint32_t)c->mlist[(size_t)j * dcm + k];
     for (int i = 0; i < N; i++) for (int s = 0; s < c->col_deg[i]; s++) vn_chk[(size_t)s * N + i] = (uint32_t)c->nlist[(size_t)i * dvm + s];
-    const int VPL = v.idx16 ? 8 : 4, groups = (dcm + VPL - 1) / VPL;
+    const int VPL = v.idx16 ? 8 : 4;
+    int groups = (dcm + VPL - 1) / VPL;
+    if (v.idx16 && dcm > 8 && dcm <= 32) groups = 4;             // ms_fast_kernel<.., DC=32, ..> loads four vectors per row
     int rc;
     if (v.idx16) {
         std::vector<uint16_t> pos((size_t)groups * M * VPL, 0);
@@ -299,6 +302,26 @@ static int pick_kernel(ldpc_gpu_decoder *d)
 #undef MP_PICK
         smem = f64 ? mp_smem_bytes<double>(v, algo) : mp_smem_bytes<float>(v, algo);
         block = std::min(1024, std::max(128, round32(v.M)));
+        if (algo == ALGO_MS && v.idx16 && !getenv("LDPC_GPU_GENERIC_MS")) {
+            // degree-specialised min-sum kernel where an instantiation covers the code
+            const bool rc = v.regular_dc > 0, rv = v.regular_dv > 0;
+            KernelFn fast = nullptr;
+#define MS_FAST(DC, DV, RC, RV) (f64 ? (KernelFn)ms_fast_kernel<double, DC, DV, RC, RV, 1024, 1> : (KernelFn)ms_fast_kernel<float, DC, DV, RC, RV, 1024, 1>)
+            const char *mb = getenv("LDPC_GPU_MINB");
+            if (v.regular_dc == 32 && v.regular_dv == 6 && v.M <= 384 && !f64)          // the 802.3an H: 384 check threads per frame
+                fast = (mb && atoi(mb) == 3) ? (KernelFn)ms_fast_kernel<float, 32, 6, true, true, 384, 3>
+                     : (mb && atoi(mb) == 1) ? (KernelFn)ms_fast_kernel<float, 32, 6, true, true, 384, 1>
+                                             : (KernelFn)ms_fast_kernel<float, 32, 6, true, true, 384, 2>;   // measured best (profiles/r1_tuning.md)
+            else if (v.regular_dc == 32 && v.regular_dv == 6) fast = MS_FAST(32, 6, true, true);
+            else if (v.regular_dc == 32 && v.dv_max <= 6) fast = MS_FAST(32, 6, true, false);
+            else if (v.dc_max <= 8 && v.regular_dv == 3) fast = MS_FAST(8, 3, false, true);
+            else if (v.regular_dc == 8 && v.regular_dv == 4) fast = MS_FAST(8, 4, true, true);
+            else if (v.dc_max <= 8 && v.dv_max <= 8) fast = MS_FAST(8, 8, false, false);
+            else if (v.dc_max <= 32 && v.dv_max <= 8) fast = MS_FAST(32, 8, false, false);
+#undef MS_FAST
+            (void)rc; (void)rv;
+            if (fast) d->fn = fast;
+        }
     } else if (kind == LDPC_GPU_KIND_GDBF) {
         d->fn = f64 ? (KernelFn)gdbf_kernel<double> : (KernelFn)gdbf_kernel<float>;
         smem = f64 ? gdbf_smem_bytes<double>(v) : gdbf_smem_bytes<float>(v);

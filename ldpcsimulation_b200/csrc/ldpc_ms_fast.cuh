@@ -1,0 +1,179 @@
+// ldpc_ms_fast.cuh -- min-sum family, degree-specialised kernel (the headline path).
+//
+// Same data flow, same arithmetic order and the same on-chip layout as mp_kernel<.., ALGO_MS>
+// (ldpc_mp_kernels.cuh), with everything the profiler showed to be wasted removed
+// (profiles/r1a_*: 82 issued lane-instructions per edge-iteration in the generic loop):
+//   * row / column weights are template parameters: loops fully unroll, a check thread keeps the
+//     row's DC incoming messages in registers between its two passes;
+//   * the argmin index is not tracked: c2v_k = (|v_k| == min1) ? min2 : min1 gives the reference's
+//     result for every tie pattern (when the minimum is attained twice min2 == min1);
+//   * normalisation / offset act on min1 and min2 once per row, not once per edge (the division is
+//     sign-symmetric, so the value per edge is the reference's bit for bit);
+//   * fp32: the sign product is an XOR of raw bit patterns and is applied with one LOP3 per edge.
+//     (-0.0 then counts as negative where the reference's sgn() says +1; it can only occur when a
+//     caller passes y = -0.0 exactly.  The fp64 parity instantiation keeps sgn()'s comparison.)
+#pragma once
+#include "ldpc_mp_kernels.cuh"
+
+namespace ldpc {
+
+template <typename Real> struct SignOps;
+template <> struct SignOps<float> {
+    typedef uint32_t acc_t;
+    static LDPC_DEVINL acc_t zero() { return 0u; }
+    static LDPC_DEVINL void fold(acc_t &a, float v) { a ^= __float_as_uint(v); }
+    // magnitude (>= 0) carrying the row's sign product
+    static LDPC_DEVINL float presign(float mag, acc_t a) { return __uint_as_float(__float_as_uint(mag) ^ (a & 0x80000000u)); }
+    // times sgn(v_k)
+    static LDPC_DEVINL float apply(float presigned, float v) { return __uint_as_float(__float_as_uint(presigned) ^ (__float_as_uint(v) & 0x80000000u)); }
+};
+template <> struct SignOps<double> {
+    typedef bool acc_t;
+    static LDPC_DEVINL acc_t zero() { return false; }
+    static LDPC_DEVINL void fold(acc_t &a, double v) { a ^= neg_ge(v); }
+    static LDPC_DEVINL double presign(double mag, acc_t a) { return a ? -mag : mag; }
+    static LDPC_DEVINL double apply(double presigned, double v) { return neg_ge(v) ? -presigned : presigned; }
+};
+
+template <typename Real> LDPC_DEVINL Real rmin(Real a, Real b);
+template <> LDPC_DEVINL float rmin<float>(float a, float b) { return fminf(a, b); }
+template <> LDPC_DEVINL double rmin<double>(double a, double b) { return fmin(a, b); }
+template <typename Real> LDPC_DEVINL Real rmax(Real a, Real b);
+template <> LDPC_DEVINL float rmax<float>(float a, float b) { return fmaxf(a, b); }
+template <> LDPC_DEVINL double rmax<double>(double a, double b) { return fmax(a, b); }
+
+// DC / DV: compile-time bounds of the row / column weight.  REGC / REGV: every row / column has
+// exactly that weight (no per-slot predicate).
+// NT_MAX / MINB: launch bounds (threads per CTA, CTAs per SM the register allocation must allow).
+template <typename Real, int DC, int DV, bool REGC, bool REGV, int NT_MAX, int MINB>
+__global__ void __launch_bounds__(NT_MAX, MINB) ms_fast_kernel(const CodeDev c, const DecParams p, const FrameIO io)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FrameScratch *fs = reinterpret_cast<FrameScratch *>(smem_raw);
+    Real *msg = reinterpret_cast<Real *>(smem_raw + 16);
+    Real *yq = msg + c.dvN;
+    uint32_t *dbits = reinterpret_cast<uint32_t *>(yq + c.N);
+
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int N = c.N, M = c.M;
+    const int nwords = (N + 31) >> 5, npad = nwords << 5, nblk = (N + 3) >> 2;
+    constexpr int VPL = 8, NG = (DC + VPL - 1) / VPL;
+    const uint4 *cnv = reinterpret_cast<const uint4 *>(c.cn_pos);
+    const Real INF = real_inf<Real>();
+    const Real alpha = (Real)p.alpha, delta = (Real)p.delta;
+    const bool normalized = (p.flags & LDPC_GPU_F_NORMALIZED_MS) != 0, offset = (p.flags & LDPC_GPU_F_OFFSET_MS) != 0;
+    const uint32_t qflags = p.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES);
+
+    CtaTotals tot; tot.clear();
+
+    for (long long f = blockIdx.x; f < io.n_frames; f += gridDim.x) {
+        const uint8_t *cw = codeword_row(io, c, f);
+        if (tid == 0) { fs->uncoded = 0; fs->errors = 0; fs->flag = 0; }
+        for (int w = tid; w < nwords; w += nt) dbits[w] = 0u;
+        __syncthreads();
+
+        // ---- channel front end (src/decodeMinSum.cpp:214-240) --------------------------------
+        int unc = 0;
+        for (int b = tid; b < nblk; b += nt) {
+            double y4[4];
+            raw_samples4(io, p, c, f, cw, b, y4);
+            uint32_t nib = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = 4 * b + q;
+                if (i >= N) break;
+                double v = y4[q];
+                if (qflags & LDPC_GPU_F_QUANTIZE_SAMPLES) v = quantize_ms(v, p);
+                if (qflags & LDPC_GPU_F_SATURATE_SAMPLES) { if (v > p.Ymax) v = p.Ymax; if (v < -p.Ymax) v = -p.Ymax; }
+                const bool rneg = !(v > 0);
+                const Real vr = (Real)v;
+                yq[i] = vr;
+                const int cb = cw ? cw[i] : 0;
+                unc += (int)(rneg != (cb != 0));
+                nib |= (uint32_t)rneg << q;
+                const int deg = REGV ? DV : (int)c.vn_deg[i];
+#pragma unroll
+                for (int s = 0; s < DV; s++) if (REGV || s < deg) msg[s * N + i] = vr;
+                if (io.out_soft && p.T == 0) {
+                    if (io.y_dtype == LDPC_GPU_DT_F64) ((double *)io.out_soft)[(size_t)f * N + i] = (double)vr;
+                    else ((float *)io.out_soft)[(size_t)f * N + i] = (float)vr;
+                }
+            }
+            if (nib) atomicOr(&dbits[(4 * b) >> 5], nib << ((4 * b) & 31));
+        }
+        for (int o = 16; o; o >>= 1) unc += __shfl_xor_sync(0xffffffffu, unc, o);
+        if (lane == 0 && unc) atomicAdd(&fs->uncoded, unc);
+        __syncthreads();
+
+        for (int it = 0; it < p.T; it++) {
+            // ---- check-node phase: src/decodeMinSum.cpp:410-450 (+ :494-515) --------------------
+            for (int j = tid; j < M; j += nt) {
+                const int deg = REGC ? DC : (int)c.cn_deg[j];
+                Real v[DC];
+                Real m1 = INF, m2 = INF;
+                typename SignOps<Real>::acc_t sg = SignOps<Real>::zero();
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+                    const uint4 w = __ldg(&cnv[(size_t)g * M + j]);
+#pragma unroll
+                    for (int q = 0; q < VPL; q++) {
+                        const int k = g * VPL + q;
+                        if (k < DC && (REGC || k < deg)) {
+                            v[k] = msg[IdxVec<uint16_t>::get(w, q)];
+                            const Real a = absr(v[k]);
+                            m2 = rmin(m2, rmax(m1, a));
+                            m1 = rmin(m1, a);
+                            SignOps<Real>::fold(sg, v[k]);
+                        }
+                    }
+                }
+                Real o1 = m1, o2 = m2;
+                if (normalized) {
+                    if (sizeof(Real) == 8) { o1 = o1 / alpha; o2 = o2 / alpha; }
+                    else { o1 = o1 * (Real)p.inv_alpha_f; o2 = o2 * (Real)p.inv_alpha_f; }
+                }
+                if (offset) { o1 = o1 - delta; o1 = (o1 > 0) ? o1 : (Real)0; o2 = o2 - delta; o2 = (o2 > 0) ? o2 : (Real)0; }
+                const Real s1 = SignOps<Real>::presign(o1, sg), s2 = SignOps<Real>::presign(o2, sg);
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+                    const uint4 w = __ldg(&cnv[(size_t)g * M + j]);
+#pragma unroll
+                    for (int q = 0; q < VPL; q++) {
+                        const int k = g * VPL + q;
+                        if (k < DC && (REGC || k < deg)) {
+                            const Real sel = (absr(v[k]) == m1) ? s2 : s1;
+                            msg[IdxVec<uint16_t>::get(w, q)] = SignOps<Real>::apply(sel, v[k]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- variable-node phase: src/decodeMinSum.cpp:452-476 ----------------------------
+            const bool last = (it == p.T - 1);
+            for (int i0 = tid; i0 < npad; i0 += nt) {
+                bool dneg = false;
+                if (i0 < N) {
+                    const int deg = REGV ? DV : (int)c.vn_deg[i0];
+                    Real cm[DV];
+                    Real sum = yq[i0];
+#pragma unroll
+                    for (int s = 0; s < DV; s++) if (REGV || s < deg) { cm[s] = msg[s * N + i0]; sum += cm[s]; }
+#pragma unroll
+                    for (int s = 0; s < DV; s++) if (REGV || s < deg) msg[s * N + i0] = sum - cm[s];
+                    dneg = !(sum > 0);
+                    if (last && io.out_soft) {
+                        if (io.y_dtype == LDPC_GPU_DT_F64) ((double *)io.out_soft)[(size_t)f * N + i0] = (double)sum;
+                        else ((float *)io.out_soft)[(size_t)f * N + i0] = (float)sum;
+                    }
+                }
+                if (last) { const unsigned bal = __ballot_sync(0xffffffffu, dneg); if (lane == 0) dbits[i0 >> 5] = bal; }
+            }
+            __syncthreads();
+        }
+        const int satisfied = syndrome_ok(c, dbits);
+        finish_frame(c, p, io, f, cw, dbits, fs, p.T, satisfied, 0, 0, 1, -1, tot);
+    }
+    if (tid == 0) tot.flush(io.counters);
+}
+
+} // namespace ldpc
