@@ -18,33 +18,41 @@ struct GdbfSmem {
     FrameScratch *fs; Real *yq, *theta, *shape, *emet; int *dsum; signed char *d, *r, *c2s; uint32_t *dbits; double *red; int *redi;
 };
 
+// per-frame arrays (shared memory, or a per-CTA slice of the HBM workspace when GSTATE)
 template <typename Real>
-static inline size_t gdbf_smem_bytes(const CodeDev &c)
+static inline size_t gdbf_state_bytes(const CodeDev &c)
 {
-    size_t n = 16 + sizeof(Real) * 4 * (size_t)c.N + 4 * (size_t)c.N + 2 * (size_t)c.N + (size_t)c.M + 16;
-    n = (n + 15) & ~(size_t)15;
-    n += 4 * (size_t)((c.N + 31) / 32) + 16;
+    size_t n = sizeof(Real) * 4 * (size_t)c.N + 4 * (size_t)c.N + 2 * (size_t)c.N + (size_t)c.M + 16;
+    return (n + 15) & ~(size_t)15;
+}
+template <typename Real>
+static inline size_t gdbf_smem_bytes(const CodeDev &c, bool gstate = false)
+{
+    size_t n = 16 + 4 * (size_t)((c.N + 31) / 32) + 16;
     n = (n + 15) & ~(size_t)15;
     n += 8 * 32 + 4 * 32;                 // per-warp reduction scratch
-    return (n + 15) & ~(size_t)15;
+    n = (n + 15) & ~(size_t)15;
+    if (!gstate) n += gdbf_state_bytes<Real>(c);
+    return n;
 }
 
 template <typename Real>
-LDPC_DEVINL GdbfSmem<Real> gdbf_carve(unsigned char *raw, const CodeDev &c)
+LDPC_DEVINL GdbfSmem<Real> gdbf_carve(unsigned char *raw, unsigned char *state, const CodeDev &c)
 {
     GdbfSmem<Real> s;
     s.fs = reinterpret_cast<FrameScratch *>(raw);
-    s.yq = reinterpret_cast<Real *>(raw + 16);
-    s.theta = s.yq + c.N; s.shape = s.theta + c.N; s.emet = s.shape + c.N;
-    s.dsum = reinterpret_cast<int *>(s.emet + c.N);
-    s.d = reinterpret_cast<signed char *>(s.dsum + c.N);
-    s.r = s.d + c.N; s.c2s = s.r + c.N;
-    size_t off = (size_t)(reinterpret_cast<unsigned char *>(s.c2s + c.M) - raw);
-    off = (off + 15) & ~(size_t)15;
+    size_t off = 16;
     s.dbits = reinterpret_cast<uint32_t *>(raw + off);
     off += 4 * (size_t)((c.N + 31) / 32) + 16; off = (off + 15) & ~(size_t)15;
     s.red = reinterpret_cast<double *>(raw + off);
     s.redi = reinterpret_cast<int *>(raw + off + 8 * 32);
+    off += 8 * 32 + 4 * 32; off = (off + 15) & ~(size_t)15;
+    if (!state) state = raw + off;
+    s.yq = reinterpret_cast<Real *>(state);
+    s.theta = s.yq + c.N; s.shape = s.theta + c.N; s.emet = s.shape + c.N;
+    s.dsum = reinterpret_cast<int *>(s.emet + c.N);
+    s.d = reinterpret_cast<signed char *>(s.dsum + c.N);
+    s.r = s.d + c.N; s.c2s = s.r + c.N;
     return s;
 }
 
@@ -78,11 +86,11 @@ LDPC_DEVINL double gdbf_objective(const CodeDev &c, const GdbfSmem<Real> &s)
     return f;
 }
 
-template <typename Real>
+template <typename Real, bool GSTATE>
 __global__ void gdbf_kernel(const CodeDev c, const DecParams p, const FrameIO io)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const GdbfSmem<Real> s = gdbf_carve<Real>(smem_raw, c);
+    const GdbfSmem<Real> s = gdbf_carve<Real>(smem_raw, GSTATE ? io.workspace + (size_t)blockIdx.x * io.ws_stride : nullptr, c);
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int N = c.N, M = c.M, nblk = (N + 3) >> 2, T = p.T, W = p.windowsize;
     const uint32_t fl = p.flags;

@@ -211,6 +211,7 @@ struct ldpc_gpu_decoder {
     std::vector<void *> owned;
     KernelFn fn = nullptr;
     int block = 0, smem = 0, ctas_per_sm = 0, grid_full = 0;
+    bool gstate = false; size_t ws_stride = 0; unsigned char *d_ws = nullptr;   // HBM-resident frame state
     DecParams base;
     Slot slot[2];
     unsigned long long *d_counters = nullptr, *d_ew = nullptr, *d_it = nullptr, *d_ph = nullptr;
@@ -292,17 +293,26 @@ static int pick_kernel(ldpc_gpu_decoder *d)
 {
     const CodeDev &v = d->dev; const int kind = d->cfg.kind; const bool f64 = d->cfg.precision == LDPC_GPU_PREC_F64;
     size_t smem = 0; int block = 128;
+    int max_optin = 0;
+    CU_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d->device));
     if (kind == LDPC_GPU_KIND_MINSUM || kind == LDPC_GPU_KIND_BP || kind == LDPC_GPU_KIND_DDBMP) {
         if (v.dc_max > 64) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "message-passing kernels hold a row's signs in 64 bits: dc_max > 64");
         const int algo = kind == LDPC_GPU_KIND_MINSUM ? ALGO_MS : kind == LDPC_GPU_KIND_BP ? ALGO_BP : ALGO_DDBMP;
-#define MP_PICK(A)                                                                                                   \
-    d->fn = f64 ? (v.idx16 ? (KernelFn)mp_kernel<double, uint16_t, A> : (KernelFn)mp_kernel<double, uint32_t, A>)   \
-                : (v.idx16 ? (KernelFn)mp_kernel<float, uint16_t, A> : (KernelFn)mp_kernel<float, uint32_t, A>)
+        smem = f64 ? mp_smem_bytes<double>(v, algo) : mp_smem_bytes<float>(v, algo);
+        if (smem > (size_t)max_optin || getenv("LDPC_GPU_FORCE_HBM_STATE")) {
+            d->gstate = true;
+            d->ws_stride = f64 ? mp_state_bytes<double>(v, algo) : mp_state_bytes<float>(v, algo);
+            smem = f64 ? mp_smem_bytes<double>(v, algo, true) : mp_smem_bytes<float>(v, algo, true);
+        }
+#define MP_PICK2(A, G)                                                                                                     \
+    d->fn = f64 ? (v.idx16 ? (KernelFn)mp_kernel<double, uint16_t, A, G> : (KernelFn)mp_kernel<double, uint32_t, A, G>)   \
+                : (v.idx16 ? (KernelFn)mp_kernel<float, uint16_t, A, G> : (KernelFn)mp_kernel<float, uint32_t, A, G>)
+#define MP_PICK(A) do { if (d->gstate) MP_PICK2(A, true); else MP_PICK2(A, false); } while (0)
         if (algo == ALGO_MS) MP_PICK(ALGO_MS); else if (algo == ALGO_BP) MP_PICK(ALGO_BP); else MP_PICK(ALGO_DDBMP);
 #undef MP_PICK
-        smem = f64 ? mp_smem_bytes<double>(v, algo) : mp_smem_bytes<float>(v, algo);
+#undef MP_PICK2
         block = std::min(1024, std::max(128, round32(v.M)));
-        if (algo == ALGO_MS && v.idx16 && !getenv("LDPC_GPU_GENERIC_MS")) {
+        if (algo == ALGO_MS && v.idx16 && !d->gstate && !getenv("LDPC_GPU_GENERIC_MS")) {
             // degree-specialised min-sum kernel where an instantiation covers the code
             const bool rc = v.regular_dc > 0, rv = v.regular_dv > 0;
             KernelFn fast = nullptr;
@@ -323,8 +333,14 @@ static int pick_kernel(ldpc_gpu_decoder *d)
             if (fast) d->fn = fast;
         }
     } else if (kind == LDPC_GPU_KIND_GDBF) {
-        d->fn = f64 ? (KernelFn)gdbf_kernel<double> : (KernelFn)gdbf_kernel<float>;
         smem = f64 ? gdbf_smem_bytes<double>(v) : gdbf_smem_bytes<float>(v);
+        if (smem > (size_t)max_optin || getenv("LDPC_GPU_FORCE_HBM_STATE")) {
+            d->gstate = true;
+            d->ws_stride = f64 ? gdbf_state_bytes<double>(v) : gdbf_state_bytes<float>(v);
+            smem = f64 ? gdbf_smem_bytes<double>(v, true) : gdbf_smem_bytes<float>(v, true);
+        }
+        d->fn = d->gstate ? (f64 ? (KernelFn)gdbf_kernel<double, true> : (KernelFn)gdbf_kernel<float, true>)
+                          : (f64 ? (KernelFn)gdbf_kernel<double, false> : (KernelFn)gdbf_kernel<float, false>);
         block = std::min(1024, std::max(128, round32(std::max(v.M, (v.N + 3) / 4))));
     } else if (kind == LDPC_GPU_KIND_NGDBF_HW) {
         if (v.N >= LDPC_GPU_HW_QBUF) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "NGDBFhw's 2648-entry noise window needs N < 2648 (src/NGDBFhw.cpp:151)");
@@ -332,11 +348,8 @@ static int pick_kernel(ldpc_gpu_decoder *d)
         smem = hw_smem_bytes(v);
         block = std::min(1024, std::max(128, round32(std::max(v.M, v.N / 2))));
     } else return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown decoder kind");
-    int max_optin = 0;
-    CU_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d->device));
     if (smem > (size_t)max_optin)
-        return set_err(LDPC_GPU_ERR_UNSUPPORTED, "per-frame state (" + std::to_string(smem) + " B) exceeds one SM's shared memory; "
-                                                 "the HBM-resident path for this code size is not built yet");
+        return set_err(LDPC_GPU_ERR_UNSUPPORTED, "shared-memory scratch (" + std::to_string(smem) + " B) exceeds one SM");
     CU_TRY(cudaFuncSetAttribute((const void *)d->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes fa;
     CU_TRY(cudaFuncGetAttributes(&fa, (const void *)d->fn));
@@ -346,6 +359,13 @@ static int pick_kernel(ldpc_gpu_decoder *d)
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)d->fn, block, smem));
     if (nb < 1) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "kernel does not fit on an SM");
     d->block = block; d->smem = (int)smem; d->ctas_per_sm = nb; d->grid_full = nb * d->n_sm;
+    if (d->gstate) {
+        // HBM-resident state: enough CTAs to fill the SMs, bounded so the workspace stays modest
+        d->ws_stride = (d->ws_stride + 255) & ~(size_t)255;
+        const size_t budget = (size_t)8 << 30;
+        while (d->grid_full > d->n_sm && (size_t)d->grid_full * d->ws_stride > budget) d->grid_full -= d->n_sm;
+        CU_TRY(cudaMalloc(&d->d_ws, (size_t)d->grid_full * d->ws_stride));
+    }
     return LDPC_GPU_OK;
 }
 
@@ -381,6 +401,7 @@ extern "C" int ldpc_gpu_decoder_destroy(ldpc_gpu_decoder *d)
         if (s.st) cudaStreamDestroy(s.st);
     }
     if (d->d_counters) cudaFree(d->d_counters);
+    if (d->d_ws) cudaFree(d->d_ws);
     if (d->d_cwtab) cudaFree(d->d_cwtab);
     delete d;
     return LDPC_GPU_OK;
@@ -496,7 +517,8 @@ static int launch(ldpc_gpu_decoder *d, const DecParams &p, const FrameIO &io, cu
 {
     const long long want = std::min<long long>(io.n_frames, d->grid_full);
     if (want <= 0) return LDPC_GPU_OK;
-    d->fn<<<(unsigned)want, d->block, d->smem, st>>>(d->dev, p, io);
+    FrameIO io2 = io; io2.workspace = d->d_ws; io2.ws_stride = d->ws_stride;
+    d->fn<<<(unsigned)want, d->block, d->smem, st>>>(d->dev, p, io2);
     CU_TRY(cudaGetLastError());
     d->last_launches++;
     return LDPC_GPU_OK;

@@ -33,15 +33,20 @@ template <typename Real> LDPC_DEVINL Real bp_phi(Real x);
 template <> LDPC_DEVINL float bp_phi<float>(float x) { return log1pf(2.0f / expm1f(x)); }
 template <> LDPC_DEVINL double bp_phi<double>(double x) { return log1p(2.0 / expm1(x)); }
 
-template <typename Real, typename IdxT, int ALGO>
+// GSTATE: the message / sample arrays live in a per-CTA slice of an HBM workspace instead of shared
+// memory (same code, same arithmetic): the path for codes such as DVB-S2 (N=64800, E=226799) whose
+// messages exceed one SM.  Decisions and scratch stay in shared memory.
+template <typename Real, typename IdxT, int ALGO, bool GSTATE>
 __global__ void mp_kernel(const CodeDev c, const DecParams p, const FrameIO io)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrameScratch *fs = reinterpret_cast<FrameScratch *>(smem_raw);
-    Real *msg = reinterpret_cast<Real *>(smem_raw + 16);
+    unsigned char *state = GSTATE ? io.workspace + (size_t)blockIdx.x * io.ws_stride : smem_raw + 16;
+    Real *msg = reinterpret_cast<Real *>(state);
     Real *yq = msg + c.dvN;
     Real *mem = yq + c.N;                                             // DD-BMP only
-    uint32_t *dbits = reinterpret_cast<uint32_t *>(ALGO == ALGO_DDBMP ? mem + c.dvN : mem);
+    uint32_t *dbits = GSTATE ? reinterpret_cast<uint32_t *>(smem_raw + 16)
+                             : reinterpret_cast<uint32_t *>(ALGO == ALGO_DDBMP ? mem + c.dvN : mem);
 
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const int N = c.N, M = c.M;
@@ -251,12 +256,18 @@ __global__ void mp_kernel(const CodeDev c, const DecParams p, const FrameIO io)
     if (tid == 0) tot.flush(io.counters);
 }
 
-// Dynamic shared memory of mp_kernel.
+// Bytes of per-frame message / sample state, and the dynamic shared memory of mp_kernel.
 template <typename Real>
-static inline size_t mp_smem_bytes(const CodeDev &c, int algo)
+static inline size_t mp_state_bytes(const CodeDev &c, int algo)
 {
-    size_t n = 16 + sizeof(Real) * ((size_t)c.dvN + c.N) + 4 * (size_t)((c.N + 31) / 32);
+    size_t n = sizeof(Real) * ((size_t)c.dvN + c.N);
     if (algo == ALGO_DDBMP) n += sizeof(Real) * (size_t)c.dvN;
+    return (n + 15) & ~(size_t)15;
+}
+template <typename Real>
+static inline size_t mp_smem_bytes(const CodeDev &c, int algo, bool gstate = false)
+{
+    size_t n = 16 + 4 * (size_t)((c.N + 31) / 32) + (gstate ? 0 : mp_state_bytes<Real>(c, algo));
     return (n + 15) & ~(size_t)15;
 }
 

@@ -70,6 +70,8 @@ struct FrameIO {
     unsigned long long *it_hist;  // device [iter_hist_len] or NULL
     unsigned long long *ph_hist;  // device [maxphase] or NULL
     unsigned long long seed;
+    unsigned char *workspace;     // device, gridDim.x * ws_stride bytes: per-CTA frame state of the HBM-resident
+    size_t         ws_stride;     //   instantiations (codes whose state exceeds one SM's shared memory)
     // channel_dump outputs
     double       *dump_y;
     double       *dump_noise;

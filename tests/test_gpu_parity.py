@@ -127,3 +127,43 @@ def test_f32_within_tolerance(variant, code):
     # f32 samples in, f32 sums out (the host mains' fast path) decode the same way
     c = dec.decode(snr, R, y.astype(np.float32), y_dtype=abi.DT_F32)
     assert np.array_equal(b.bits[conv], c.bits[conv]) or np.mean(b.bits[conv] != c.bits[conv]) < 1e-3
+
+
+# ---- config 4: codes whose per-frame state exceeds one SM -> HBM-resident instantiations ----------
+@pytest.mark.parametrize("variant,prec", [("decodeMinSum", abi.PREC_F64), ("decodeNormalizedMinSum", abi.PREC_F64),
+                                          ("decodeSMNGDBF", abi.PREC_F64), ("decodeMinSum", abi.PREC_F32)])
+def test_dvbs2_hbm_resident(variant, prec):
+    """DVB-S2 rate-1/2 (N=64800, E=226799): messages live in an HBM workspace; same results as the oracle."""
+    cfg = cases.cfg_for(variant, num_iterations=12, precision=prec, alpha=(1.25 if "MinSum" in variant else 0.7))
+    orc = Oracle("dvbs2")
+    dec = capi.Decoder(capi.Code(code_path("dvbs2")), cfg)
+    assert dec.geometry()["smem_bytes"] < 64 * 1024            # state is not in shared memory
+    snr = 1.6 if cfg.kind == abi.KIND_MINSUM else 3.5
+    y, noise, rows, cw = cases.make_inputs(orc.N, cfg, snr, 0.5, 3, 17)
+    cfg64 = cases.cfg_for(variant, num_iterations=12, alpha=(1.25 if "MinSum" in variant else 0.7))
+    a = orc.decode(cfg64, snr, 0.5, y, noise, rows, cw)
+    b = dec.decode(snr, 0.5, y, noise, rows, cw)
+    if prec == abi.PREC_F64:
+        _same(a, b, soft="exact" if cfg.kind == abi.KIND_MINSUM else None)
+    else:
+        assert np.array_equal(a.iters, b.iters)
+        scale = np.abs(a.soft).max(axis=1, keepdims=True)
+        assert (np.abs(a.soft - b.soft) / scale).max() < 1e-4
+        assert np.mean(a.d != b.d) < 1e-3
+
+
+@pytest.mark.parametrize("variant", ["decodeMinSum", "decodeBP", "decodeDDBMP", "decodeSMNGDBF", "decodeSGDBF"])
+def test_forced_hbm_state_matches_shared_memory_path(variant, monkeypatch):
+    """The HBM-resident instantiation is the same code over a different address space."""
+    cfg = cases.cfg_for(variant)
+    R, snr = cases.operating_point(variant, "PEG")
+    orc = Oracle("PEG")
+    y, noise, rows, cw = cases.make_inputs(orc.N, cfg, snr, R, 9, 23)
+    code = capi.Code(code_path("PEG"))
+    a = capi.Decoder(code, cfg).decode(snr, R, y, noise, rows, cw)
+    monkeypatch.setenv("LDPC_GPU_FORCE_HBM_STATE", "1")
+    dec = capi.Decoder(code, cfg)
+    b = dec.decode(snr, R, y, noise, rows, cw)
+    _same(a, b, soft="exact" if cfg.kind != abi.KIND_GDBF else None)
+    _same(orc.decode(cfg, snr, R, y, noise, rows, cw), b,
+          soft=("exact" if cfg.kind in (abi.KIND_MINSUM, abi.KIND_DDBMP) else (1e-9 if cfg.kind == abi.KIND_BP else None)))
