@@ -47,6 +47,11 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
+HOST_BINARIES = ["decodeMinSum", "decodeOffsetMinSum", "decodeNormalizedMinSum", "decodeBP", "decodeDDBMP", "decodeGDBF",
+                 "decodeMGDBF", "decodeSGDBF", "decodeStochasticNGDBF", "decodeMNGDBF", "decodeSMNGDBF", "decodeUniformSMNGDBF",
+                 "decodeRSMNGDBF", "decodeSMGDBF", "decodeSATGDBF", "decodeATGDBF", "NGDBFhw"]
+
+
 def build_host(force=False):
     """C++ host mains that keep the reference binaries' positional CLIs (ldpcsimulation_b200/host)."""
     host = os.path.join(HERE, "host")
@@ -63,6 +68,12 @@ def build_host(force=False):
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("host build failed")
+    for name in HOST_BINARIES:                      # one entry point per reference binary (argv[0] dispatch)
+        link = os.path.join(bindir, name)
+        if not os.path.islink(link):
+            if os.path.exists(link):
+                os.remove(link)
+            os.symlink("ldpcsim", link)
     return exe
 
 

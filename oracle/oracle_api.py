@@ -224,7 +224,7 @@ class Reference:
             L.ref_decode_batch.argtypes = [C.c_char_p, C.POINTER(abi.DecoderCfg), C.POINTER(abi.Channel),
                                            C.POINTER(abi.Batch), C.POINTER(abi.Counters), C.c_void_p]
             L.ref_compiled_flags.restype = C.c_uint
-            L.ref_run_main.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_ulonglong]
+            L.ref_run_main.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_ulonglong, C.c_char_p]
             self._libs[variant] = L
         self.L = self._libs[variant]
         self.flags = int(self.L.ref_compiled_flags())
@@ -247,7 +247,7 @@ class Reference:
         out["qpointer_trace"] = qtrace
         return out
 
-    def run_main(self, argv, stream_seed):
+    def run_main(self, argv, stream_seed=1, stdout_path=None):
         """Run the variant's unmodified main() on the harness's deterministic random() stream."""
         arr = (C.c_char_p * (len(argv) + 1))(*[a.encode() for a in argv], None)
-        return self.L.ref_run_main(len(argv), arr, stream_seed)
+        return self.L.ref_run_main(len(argv), arr, stream_seed, None if stdout_path is None else os.fsencode(stdout_path))

@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <iostream>
 #include <unistd.h>
 using namespace std;
 
@@ -474,18 +475,17 @@ extern "C" int ref_decode_batch(const char *alist_path, const ldpc_gpu_decoder_c
 // ---- whole-program run of the reference's main() on the shim's deterministic stream -------
 // argv is the variant's own positional command line.  stdout is silenced; the TSV line the
 // reference appends to its log file is the observable.
-extern "C" int ref_run_main(int argc, char **argv, unsigned long long stream_seed)
+extern "C" int ref_run_main(int argc, char **argv, unsigned long long stream_seed, const char *stdout_path)
 {
     g_uq = 0; g_xs = stream_seed ? stream_seed : 88172645463325252ULL;
-    fflush(stdout);
-    FILE *saved = stdout;
-    FILE *devnull = fopen("/dev/null", "w");
-    (void)saved;
-    // cout shares the C stdout buffer only through fd 1; redirect the descriptor itself.
+    fflush(stdout); cout.flush();
+    // cout reaches the terminal through fd 1: redirect the descriptor itself
+    FILE *sink = fopen(stdout_path ? stdout_path : "/dev/null", "w");
+    if (!sink) return -100;
     int fd_saved = dup(1);
-    dup2(fileno(devnull), 1);
+    dup2(fileno(sink), 1);
     int rc = ref_main(argc, argv);
-    fflush(stdout);
-    dup2(fd_saved, 1); close(fd_saved); fclose(devnull);
+    fflush(stdout); cout.flush();
+    dup2(fd_saved, 1); close(fd_saved); fclose(sink);
     return rc;
 }
