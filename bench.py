@@ -174,7 +174,7 @@ def main():
 
     import numpy as np
     import torch
-    from ldpcsimulation_b200 import abi, capi
+    from ldpcsimulation_b200 import abi, capi, shard
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -217,7 +217,8 @@ def main():
 
     def step(i):
         # disjoint global frame-id ranges per (step, rank): the union over ranks is one Monte-Carlo run
-        return dec.simulate(snr, R, 1234, (i * world + rank) * F, F)
+        begin, n = shard.step_range(i, rank, world, F)
+        return dec.simulate(snr, R, 1234, begin, n)
 
     launches, kernel_ms = 0, 0.0
     for i in range(args.warmup):
