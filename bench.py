@@ -222,7 +222,9 @@ def main():
 
     launches, kernel_ms = 0, 0.0
     for i in range(args.warmup):
-        step(i)
+        r = step(i)
+    if world > 1:                                       # first collective on a fresh communicator sets up its channels
+        capi.check(capi.lib().ldpc_gpu_allreduce_counters(r["_cnt"], code.N, cfg.num_iterations, 1))
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
