@@ -20,6 +20,7 @@
 
 #include "ldpc_mp_kernels.cuh"
 #include "ldpc_ms_fast.cuh"
+#include "ldpc_schedule.h"
 #include "ldpc_bf_kernels.cuh"
 
 using namespace ldpc;
@@ -251,6 +252,32 @@ template <typename T> static int upload(ldpc_gpu_decoder *d, const std::vector<T
     return LDPC_GPU_OK;
 }
 
+// Regular codes: conflict-free check schedule + variable relabelling (ldpc_schedule.h).
+static int build_schedule(ldpc_gpu_decoder *d, const ldpc_gpu_code *c, size_t real_bytes)
+{
+    CodeDev &v = d->dev;
+    v.sched = nullptr; v.col_of_var = nullptr; v.var_of_col = nullptr;
+    if (v.regular_dc <= 0 || v.regular_dv <= 0 || v.regular_dc % 4 || v.N > 65535 || getenv("LDPC_GPU_NO_SCHED")) return LDPC_GPU_OK;
+    const int N = v.N, M = v.M, dc = v.regular_dc, dvm = c->dv_max, dcm = c->dc_max;
+    std::vector<int> ml((size_t)M * dc);
+    for (int j = 0; j < M; j++) for (int k = 0; k < dc; k++) ml[(size_t)j * dc + k] = c->mlist[(size_t)j * dcm + k];
+    RowSchedule rs = build_row_schedule(N, M, dc, ml);
+    if (!rs.ok) return LDPC_GPU_OK;                               // no perfect schedule: the unscheduled kernel is used
+    std::vector<uint32_t> tab((size_t)(dc / 4) * M * 4, 0);
+    for (int j = 0; j < M; j++) for (int t = 0; t < dc; t++) {
+        const int k = rs.order[(size_t)j * dc + t];
+        const int i = c->mlist[(size_t)j * dcm + k], s = c->vn_slot[(size_t)j * dcm + k];
+        tab[((size_t)(t / 4) * M + j) * 4 + (t % 4)] = (uint32_t)(((size_t)s * N + rs.col[i]) * real_bytes);
+    }
+    (void)dvm;
+    std::vector<uint16_t> cov(N), voc(N);
+    for (int i = 0; i < N; i++) { cov[i] = (uint16_t)rs.col[i]; voc[i] = (uint16_t)rs.var_of_col[i]; }
+    const uint32_t *pt; const uint16_t *p1, *p2; int rc;
+    if ((rc = upload(d, tab, &pt)) || (rc = upload(d, cov, &p1)) || (rc = upload(d, voc, &p2))) return rc;
+    v.sched = reinterpret_cast<const uint4 *>(pt); v.col_of_var = p1; v.var_of_col = p2;
+    return LDPC_GPU_OK;
+}
+
 static int build_device_code(ldpc_gpu_decoder *d, const ldpc_gpu_code *c)
 {
     CodeDev &v = d->dev;
@@ -318,7 +345,12 @@ static int pick_kernel(ldpc_gpu_decoder *d)
             KernelFn fast = nullptr;
 #define MS_FAST(DC, DV, RC, RV) (f64 ? (KernelFn)ms_fast_kernel<double, DC, DV, RC, RV, 1024, 1> : (KernelFn)ms_fast_kernel<float, DC, DV, RC, RV, 1024, 1>)
             const char *mb = getenv("LDPC_GPU_MINB");
-            if (v.regular_dc == 32 && v.regular_dv == 6 && v.M <= 384 && !f64)          // the 802.3an H: 384 check threads per frame
+            if (v.sched && v.regular_dc == 32 && v.regular_dv == 6 && v.N == 2048 && v.M <= 384)   // the 802.3an H, scheduled
+                fast = f64 ? (KernelFn)ms_sched_kernel<double, 32, 6, 2048, 384, 1>
+                           : ((mb && atoi(mb) == 3) ? (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 3>
+                              : (mb && atoi(mb) == 1) ? (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 1>
+                                                      : (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 2>);
+            else if (v.regular_dc == 32 && v.regular_dv == 6 && v.M <= 384 && !f64)     // the 802.3an H: 384 check threads per frame
                 fast = (mb && atoi(mb) == 3) ? (KernelFn)ms_fast_kernel<float, 32, 6, true, true, 384, 3>
                      : (mb && atoi(mb) == 1) ? (KernelFn)ms_fast_kernel<float, 32, 6, true, true, 384, 1>
                                              : (KernelFn)ms_fast_kernel<float, 32, 6, true, true, 384, 2>;   // measured best (profiles/r1_tuning.md)
@@ -418,7 +450,9 @@ extern "C" int ldpc_gpu_decoder_create(const ldpc_gpu_code *code, const ldpc_gpu
     ldpc_gpu_decoder *d = new ldpc_gpu_decoder;
     d->device = device; d->cfg = *cfg; d->N = code->N; d->M = code->M;
     cudaDeviceGetAttribute(&d->n_sm, cudaDevAttrMultiProcessorCount, device);
-    if ((rc = build_device_code(d, code)) || (rc = pick_kernel(d))) { ldpc_gpu_decoder_destroy(d); return rc; }
+    if ((rc = build_device_code(d, code)) ||
+        (cfg->kind == LDPC_GPU_KIND_MINSUM && (rc = build_schedule(d, code, cfg->precision == LDPC_GPU_PREC_F64 ? 8 : 4))) ||
+        (rc = pick_kernel(d))) { ldpc_gpu_decoder_destroy(d); return rc; }
     for (Slot &s : d->slot) {
         if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&s.k0) != cudaSuccess ||
             cudaEventCreate(&s.k1) != cudaSuccess) { ldpc_gpu_decoder_destroy(d); return set_err(LDPC_GPU_ERR_CUDA, "stream/event creation failed"); }

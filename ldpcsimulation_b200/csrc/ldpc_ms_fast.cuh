@@ -177,3 +177,144 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_fast_kernel(const CodeDev c, 
 }
 
 } // namespace ldpc
+
+namespace ldpc {
+
+// ---------------------------------------------------------------------------------------------
+// Scheduled variant for regular codes whose size is known at compile time (the 802.3an H):
+// identical arithmetic, but
+//   * the check phase walks each row in the bank-conflict-free order of ldpc_schedule.h, reading
+//     pre-multiplied BYTE offsets four at a time (no index unpacking, no address arithmetic);
+//   * variables live at storage column col(i); the variable phase walks columns at stride 1 with
+//     compile-time slot strides (immediate offsets);
+//   * decisions are scattered back to true variable order once, in the last iteration.
+// ---------------------------------------------------------------------------------------------
+template <typename Real, int DC, int DV, int NFIX, int NT_MAX, int MINB>
+__global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c, const DecParams p, const FrameIO io)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FrameScratch *fs = reinterpret_cast<FrameScratch *>(smem_raw);
+    Real *msg = reinterpret_cast<Real *>(smem_raw + 16);
+    constexpr int N = NFIX;
+    Real *yq = msg + DV * N;
+    uint32_t *dbits = reinterpret_cast<uint32_t *>(yq + N);
+    unsigned char *msgb = reinterpret_cast<unsigned char *>(msg);
+
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int M = c.M;
+    constexpr int nwords = (N + 31) >> 5, nblk = (N + 3) >> 2;
+    constexpr int NG = DC / 4;
+    static_assert(DC % 4 == 0 && N % 32 == 0, "scheduled kernel needs dc % 4 == 0 and N % 32 == 0");
+    const Real INF = real_inf<Real>();
+    const Real alpha = (Real)p.alpha, delta = (Real)p.delta;
+    const bool normalized = (p.flags & LDPC_GPU_F_NORMALIZED_MS) != 0, offset = (p.flags & LDPC_GPU_F_OFFSET_MS) != 0;
+    const uint32_t qflags = p.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES);
+
+    CtaTotals tot; tot.clear();
+
+    for (long long f = blockIdx.x; f < io.n_frames; f += gridDim.x) {
+        const uint8_t *cw = codeword_row(io, c, f);
+        if (tid == 0) { fs->uncoded = 0; fs->errors = 0; fs->flag = 0; }
+        for (int w = tid; w < nwords; w += nt) dbits[w] = 0u;
+        __syncthreads();
+
+        int unc = 0;
+        for (int b = tid; b < nblk; b += nt) {
+            double y4[4];
+            raw_samples4(io, p, c, f, cw, b, y4);
+            const uint2 cc = __ldg(reinterpret_cast<const uint2 *>(c.col_of_var) + b);      // four uint16 columns
+            uint32_t nib = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = 4 * b + q;
+                double v = y4[q];
+                if (qflags & LDPC_GPU_F_QUANTIZE_SAMPLES) v = quantize_ms(v, p);
+                if (qflags & LDPC_GPU_F_SATURATE_SAMPLES) { if (v > p.Ymax) v = p.Ymax; if (v < -p.Ymax) v = -p.Ymax; }
+                const bool rneg = !(v > 0);
+                const Real vr = (Real)v;
+                const int col = (int)(((q < 2 ? cc.x : cc.y) >> (16 * (q & 1))) & 0xffffu);
+                yq[col] = vr;
+                const int cb = cw ? cw[i] : 0;
+                unc += (int)(rneg != (cb != 0));
+                nib |= (uint32_t)rneg << q;
+#pragma unroll
+                for (int s = 0; s < DV; s++) msg[s * N + col] = vr;
+                if (io.out_soft && p.T == 0) {
+                    if (io.y_dtype == LDPC_GPU_DT_F64) ((double *)io.out_soft)[(size_t)f * N + i] = (double)vr;
+                    else ((float *)io.out_soft)[(size_t)f * N + i] = (float)vr;
+                }
+            }
+            if (nib) atomicOr(&dbits[(4 * b) >> 5], nib << ((4 * b) & 31));
+        }
+        for (int o = 16; o; o >>= 1) unc += __shfl_xor_sync(0xffffffffu, unc, o);
+        if (lane == 0 && unc) atomicAdd(&fs->uncoded, unc);
+        __syncthreads();
+
+        for (int it = 0; it < p.T; it++) {
+            const bool last = (it == p.T - 1);
+            if (last) for (int w = tid; w < nwords; w += nt) dbits[w] = 0u;          // re-filled below, in true variable order
+            // ---- check-node phase ----------------------------------------------------------------
+            for (int j = tid; j < M; j += nt) {
+                Real v[DC];
+                Real m1 = INF, m2 = INF;
+                typename SignOps<Real>::acc_t sg = SignOps<Real>::zero();
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+                    const uint4 w = __ldg(&c.sched[(size_t)g * M + j]);
+                    const uint32_t off[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int k = g * 4 + q;
+                        v[k] = *reinterpret_cast<const Real *>(msgb + off[q]);
+                        const Real a = absr(v[k]);
+                        m2 = rmin(m2, rmax(m1, a));
+                        m1 = rmin(m1, a);
+                        SignOps<Real>::fold(sg, v[k]);
+                    }
+                }
+                Real o1 = m1, o2 = m2;
+                if (normalized) {
+                    if (sizeof(Real) == 8) { o1 = o1 / alpha; o2 = o2 / alpha; }
+                    else { o1 = o1 * (Real)p.inv_alpha_f; o2 = o2 * (Real)p.inv_alpha_f; }
+                }
+                if (offset) { o1 = o1 - delta; o1 = (o1 > 0) ? o1 : (Real)0; o2 = o2 - delta; o2 = (o2 > 0) ? o2 : (Real)0; }
+                const Real s1 = SignOps<Real>::presign(o1, sg), s2 = SignOps<Real>::presign(o2, sg);
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+                    const uint4 w = __ldg(&c.sched[(size_t)g * M + j]);
+                    const uint32_t off[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int k = g * 4 + q;
+                        const Real sel = (absr(v[k]) == m1) ? s2 : s1;
+                        *reinterpret_cast<Real *>(msgb + off[q]) = SignOps<Real>::apply(sel, v[k]);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- variable-node phase (storage columns) --------------------------------------------
+            for (int col = tid; col < N; col += nt) {
+                Real cm[DV];
+                Real sum = yq[col];
+#pragma unroll
+                for (int s = 0; s < DV; s++) { cm[s] = msg[s * N + col]; sum += cm[s]; }
+#pragma unroll
+                for (int s = 0; s < DV; s++) msg[s * N + col] = sum - cm[s];
+                if (last) {
+                    const int i = (int)__ldg(&c.var_of_col[col]);
+                    if (!(sum > 0)) atomicOr(&dbits[i >> 5], 1u << (i & 31));
+                    if (io.out_soft) {
+                        if (io.y_dtype == LDPC_GPU_DT_F64) ((double *)io.out_soft)[(size_t)f * N + i] = (double)sum;
+                        else ((float *)io.out_soft)[(size_t)f * N + i] = (float)sum;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const int satisfied = syndrome_ok(c, dbits);
+        finish_frame(c, p, io, f, cw, dbits, fs, p.T, satisfied, 0, 0, 1, -1, tot);
+    }
+    if (tid == 0) tot.flush(io.counters);
+}
+
+} // namespace ldpc

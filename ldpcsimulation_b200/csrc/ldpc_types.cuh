@@ -1,6 +1,7 @@
 // ldpc_types.cuh -- device-side views shared by the kernels and the C-ABI host code.
 #pragma once
 #include <stdint.h>
+#include <cuda_runtime.h>
 #include "../../include/ldpc_gpu.h"
 
 namespace ldpc {
@@ -26,6 +27,10 @@ struct CodeDev {
     const uint8_t *vn_deg;   // [N]
     const uint32_t*cn_var;   // [k*M + j]  variable of slot k of check j (bit-flipping kernels), padded with 0
     const uint32_t*vn_chk;   // [s*N + i]  check of slot s of variable i, padded with 0
+    // bank-conflict-free check schedule of a regular code (ldpc_schedule.h), or NULL
+    const uint4   *sched;    // [(t/4)][j]  four BYTE offsets (s*N + col(i))*sizeof(Real) of steps 4(t/4)..+3 of row j
+    const uint16_t*col_of_var; // [N] storage column of variable i
+    const uint16_t*var_of_col; // [N] inverse
 };
 
 // Decoder configuration + per-call channel constants, all derived on the host in double with the
