@@ -12,7 +12,7 @@ import numpy as np
 from . import abi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_build", "libldpc_gpu.so")
+LIB_PATH = os.environ.get("LDPC_GPU_LIB", os.path.join(HERE, "_build", "libldpc_gpu.so"))
 
 # every symbol include/ldpc_gpu.h declares
 EXPORTS = [

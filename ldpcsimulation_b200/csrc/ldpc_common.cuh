@@ -26,10 +26,31 @@ LDPC_DEVINL double quantize_ms(double x, const DecParams &p)
 {
     const double s = neg_ge(x) ? -1.0 : 1.0;
     if (fabs(x) > p.Ymax) return s * p.Ymax;
-    double q = s * (floor(fabs(x) * p.ms_Nq1 / p.ms_twoY) + 0.0) * p.ms_step;
+    // dividing by a power of two is exact, so it may be a multiplication by the (exact) reciprocal
+    const double t = fabs(x) * p.ms_Nq1;
+    double q = s * (floor(p.ms_inv_twoY != 0.0 ? t * p.ms_inv_twoY : t / p.ms_twoY) + 0.0) * p.ms_step;
     if (q == 0.0) q = s * p.ms_step;
     return q;
 }
+// fp32 front end of the min-sum family, used by the fp32 instantiation when its samples are fp32
+// anyway (Philox channel or LDPC_GPU_DT_F32 input): the same clip / floor / no-zero-level rule as
+// quantize_ms (src/decodeMinSum.cpp:480-489, :224-229), evaluated in fp32.  A sample within one fp32
+// ulp of a level boundary may land one level away from the fp64 rule; the fp64 instantiation, and
+// the fp32 one on fp64 input, keep the double arithmetic.
+LDPC_DEVINL float condition_ms_f32(float y, const DecParams &p, uint32_t qflags)
+{
+    float v = y;
+    if (qflags & LDPC_GPU_F_QUANTIZE_SAMPLES) {
+        const float a = fabsf(y);
+        float q = floorf(a * p.ms_scale_f) * p.ms_step_f;
+        q = (q == 0.0f) ? p.ms_step_f : q;
+        q = (a > p.Ymax_f) ? p.Ymax_f : q;
+        v = (y >= 0.0f) ? q : -q;
+    }
+    if (qflags & LDPC_GPU_F_SATURATE_SAMPLES) v = fminf(fmaxf(v, -p.Ymax_f), p.Ymax_f);
+    return v;
+}
+
 // a3: GDBF quantiser, src/decodeGDBF.cpp:488-493
 LDPC_DEVINL double quantize_gdbf(double x, const DecParams &p)
 {
@@ -109,6 +130,10 @@ struct FrameScratch {
 // End of frame: count decision errors against the codeword (countDecisionErrors,
 // src/decodeMinSum.cpp:382-393), emit the per-frame outputs and do the accounting of
 // src/decodeMinSum.cpp:270-288.  `dbits` holds the hard decisions, bit i = 1 <-> d_i = -1.
+LDPC_DEVINL bool syndrome_ok(const CodeDev &c, const uint32_t *dbits);
+
+// `satisfied` < 0 means "not computed": the syndrome of the decisions is then evaluated here, and only
+// when somebody consumes it (a flags output, or a frame in error for the undetected-error counter).
 // Must be called by every thread of the CTA; ends with a barrier.
 LDPC_DEVINL void finish_frame(const CodeDev &c, const DecParams &p, const FrameIO &io, long long f, const uint8_t *cw,
                               const uint32_t *dbits, FrameScratch *fs, int it, int satisfied, int smoothed,
@@ -129,6 +154,10 @@ LDPC_DEVINL void finish_frame(const CodeDev &c, const DecParams &p, const FrameI
     }
     if (lane == 0 && local_err) atomicAdd(&fs->errors, local_err);
     __syncthreads();
+    if (satisfied < 0) {
+        const int e_all = errors_override >= 0 ? errors_override : fs->errors;       // same value in every thread
+        satisfied = (io.out_flags || e_all > 0) ? (int)syndrome_ok(c, dbits) : 0;
+    }
     if (tid == 0) {
         const int e = errors_override >= 0 ? errors_override : fs->errors;
         if (io.out_iters)  io.out_iters[f] = it;

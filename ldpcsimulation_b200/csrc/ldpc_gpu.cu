@@ -256,7 +256,7 @@ template <typename T> static int upload(ldpc_gpu_decoder *d, const std::vector<T
 static int build_schedule(ldpc_gpu_decoder *d, const ldpc_gpu_code *c, size_t real_bytes)
 {
     CodeDev &v = d->dev;
-    v.sched = nullptr; v.col_of_var = nullptr; v.var_of_col = nullptr;
+    v.sched = nullptr; v.sched16 = nullptr; v.col_of_var = nullptr; v.var_of_col = nullptr;
     if (v.regular_dc <= 0 || v.regular_dv <= 0 || v.regular_dc % 4 || v.N > 65535 || getenv("LDPC_GPU_NO_SCHED")) return LDPC_GPU_OK;
     const int N = v.N, M = v.M, dc = v.regular_dc, dvm = c->dv_max, dcm = c->dc_max;
     std::vector<int> ml((size_t)M * dc);
@@ -275,6 +275,14 @@ static int build_schedule(ldpc_gpu_decoder *d, const ldpc_gpu_code *c, size_t re
     const uint32_t *pt; const uint16_t *p1, *p2; int rc;
     if ((rc = upload(d, tab, &pt)) || (rc = upload(d, cov, &p1)) || (rc = upload(d, voc, &p2))) return rc;
     v.sched = reinterpret_cast<const uint4 *>(pt); v.col_of_var = p1; v.var_of_col = p2;
+    if ((size_t)v.dvN * real_bytes <= 65536 && dc % 8 == 0) {     // uint16 byte offsets: the row fits dc/2 registers
+        std::vector<uint16_t> t16((size_t)(dc / 8) * M * 8, 0);
+        for (int j = 0; j < M; j++) for (int t = 0; t < dc; t++)
+            t16[((size_t)(t / 8) * M + j) * 8 + (t % 8)] = (uint16_t)tab[((size_t)(t / 4) * M + j) * 4 + (t % 4)];
+        const uint16_t *p16;
+        if ((rc = upload(d, t16, &p16))) return rc;
+        v.sched16 = reinterpret_cast<const uint4 *>(p16);
+    }
     return LDPC_GPU_OK;
 }
 
@@ -468,6 +476,7 @@ extern "C" int ldpc_gpu_decoder_create(const ldpc_gpu_code *code, const ldpc_gpu
     p.noiseScale = cfg->noiseScale; p.w = cfg->w; p.theta0 = cfg->theta0; p.MAXLLR = cfg->MAXLLR;
     const double Nq = pow(2.0, cfg->Q);                            // decodeMinSum.cpp:125
     p.ms_Nq1 = Nq - 1; p.ms_twoY = 2.0 * cfg->Ymax; p.ms_step = 2 * cfg->Ymax / (Nq - 1);
+    { int ex; p.ms_inv_twoY = (p.ms_twoY > 0 && frexp(p.ms_twoY, &ex) == 0.5) ? 1.0 / p.ms_twoY : 0.0; }
     const double gq = pow(2, (cfg->NQ - 1)), gl = cfg->Ymax / 2.0; // decodeGDBF.cpp:490-491
     p.g_qmax = gq; p.g_twol = 2 * gl; p.g_step = 2.0 * gl / gq;
     if (cfg->kind == LDPC_GPU_KIND_NGDBF_HW) {                    // NGDBFhw.cpp:171-176
@@ -480,6 +489,7 @@ extern "C" int ldpc_gpu_decoder_create(const ldpc_gpu_code *code, const ldpc_gpu
         p.hw_Smult = (int)round(NL / lmax);
     }
     p.inv_alpha_f = (float)(1.0 / cfg->alpha);
+    p.ms_scale_f = (float)((Nq - 1) / (2.0 * cfg->Ymax)); p.ms_step_f = (float)p.ms_step; p.Ymax_f = (float)cfg->Ymax;
     p.iter_hist_len = iter_hist_len(*cfg);
     p.rows_per_step = rows_per_step(cfg->flags);
     *out = d;

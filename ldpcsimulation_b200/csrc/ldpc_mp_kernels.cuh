@@ -110,7 +110,7 @@ __global__ void mp_kernel(const CodeDev c, const DecParams p, const FrameIO io)
         if (lane == 0 && unc) atomicAdd(&fs->uncoded, unc);
         __syncthreads();
 
-        int it = 0, satisfied = 0;
+        int it = 0, satisfied = -1;
         for (it = 0; it < p.T; it++) {
             // ---- check-node phase ------------------------------------------------------------
             for (int j = tid; j < M; j += nt) {
@@ -250,7 +250,8 @@ __global__ void mp_kernel(const CodeDev c, const DecParams p, const FrameIO io)
                 if (satisfied) break;                                 // `it` is not incremented on this exit (:203-204)
             }
         }
-        if (ALGO != ALGO_DDBMP || p.T == 0) satisfied = syndrome_ok(c, dbits);   // extension: the reference keeps no syndrome here
+        if (ALGO == ALGO_DDBMP && p.T == 0) satisfied = syndrome_ok(c, dbits);
+        // MS / BP: the reference keeps no syndrome; finish_frame evaluates it on demand (satisfied == -1)
         finish_frame(c, p, io, f, cw, dbits, fs, it, satisfied, 0, 0, 1, -1, tot);
     }
     if (tid == 0) tot.flush(io.counters);

@@ -19,11 +19,17 @@ namespace ldpc {
 
 template <typename Real> struct SignOps;
 template <> struct SignOps<float> {
-    typedef uint32_t acc_t;
+    typedef uint32_t acc_t;                     // number of negative messages seen (parity = sign product)
     static LDPC_DEVINL acc_t zero() { return 0u; }
-    static LDPC_DEVINL void fold(acc_t &a, float v) { a ^= __float_as_uint(v); }
+    // acc += sign bit, as hi32(bits * 2) + acc: one IMAD.HI on the FMA pipe (the ALU pipe is the busy one here)
+#ifndef LDPC_SIGN_XOR
+    static LDPC_DEVINL void fold(acc_t &a, float v) { a = __umulhi(__float_as_uint(v), 2u) + a; }
+#else
+    static LDPC_DEVINL void fold(acc_t &a, float v) { a ^= __float_as_uint(v) >> 31; }
+#endif
+    static LDPC_DEVINL acc_t merge(acc_t a, acc_t b) { return a + b; }
     // magnitude (>= 0) carrying the row's sign product
-    static LDPC_DEVINL float presign(float mag, acc_t a) { return __uint_as_float(__float_as_uint(mag) ^ (a & 0x80000000u)); }
+    static LDPC_DEVINL float presign(float mag, acc_t a) { return __uint_as_float(__float_as_uint(mag) ^ (a << 31)); }
     // times sgn(v_k)
     static LDPC_DEVINL float apply(float presigned, float v) { return __uint_as_float(__float_as_uint(presigned) ^ (__float_as_uint(v) & 0x80000000u)); }
 };
@@ -31,6 +37,7 @@ template <> struct SignOps<double> {
     typedef bool acc_t;
     static LDPC_DEVINL acc_t zero() { return false; }
     static LDPC_DEVINL void fold(acc_t &a, double v) { a ^= neg_ge(v); }
+    static LDPC_DEVINL acc_t merge(acc_t a, acc_t b) { return a ^ b; }
     static LDPC_DEVINL double presign(double mag, acc_t a) { return a ? -mag : mag; }
     static LDPC_DEVINL double apply(double presigned, double v) { return neg_ge(v) ? -presigned : presigned; }
 };
@@ -63,6 +70,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_fast_kernel(const CodeDev c, 
     const Real alpha = (Real)p.alpha, delta = (Real)p.delta;
     const bool normalized = (p.flags & LDPC_GPU_F_NORMALIZED_MS) != 0, offset = (p.flags & LDPC_GPU_F_OFFSET_MS) != 0;
     const uint32_t qflags = p.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES);
+    const bool fcond = !io.y || io.y_dtype == LDPC_GPU_DT_F32;      // fp32 instantiation: fp32 front end on fp32 samples
 
     CtaTotals tot; tot.clear();
 
@@ -82,11 +90,17 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_fast_kernel(const CodeDev c, 
             for (int q = 0; q < 4; q++) {
                 const int i = 4 * b + q;
                 if (i >= N) break;
-                double v = y4[q];
-                if (qflags & LDPC_GPU_F_QUANTIZE_SAMPLES) v = quantize_ms(v, p);
-                if (qflags & LDPC_GPU_F_SATURATE_SAMPLES) { if (v > p.Ymax) v = p.Ymax; if (v < -p.Ymax) v = -p.Ymax; }
-                const bool rneg = !(v > 0);
-                const Real vr = (Real)v;
+                Real vr; bool rneg;
+                if (sizeof(Real) == 4 && fcond) {
+                    const float vf = condition_ms_f32((float)y4[q], p, qflags);
+                    vr = (Real)vf; rneg = !(vf > 0.0f);
+                } else {
+                    double v = y4[q];
+                    if (qflags & LDPC_GPU_F_QUANTIZE_SAMPLES) v = quantize_ms(v, p);
+                    if (qflags & LDPC_GPU_F_SATURATE_SAMPLES) { if (v > p.Ymax) v = p.Ymax; if (v < -p.Ymax) v = -p.Ymax; }
+                    rneg = !(v > 0);
+                    vr = (Real)v;
+                }
                 yq[i] = vr;
                 const int cb = cw ? cw[i] : 0;
                 unc += (int)(rneg != (cb != 0));
@@ -170,8 +184,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_fast_kernel(const CodeDev c, 
             }
             __syncthreads();
         }
-        const int satisfied = syndrome_ok(c, dbits);
-        finish_frame(c, p, io, f, cw, dbits, fs, p.T, satisfied, 0, 0, 1, -1, tot);
+        finish_frame(c, p, io, f, cw, dbits, fs, p.T, /*satisfied: evaluated on demand*/ -1, 0, 0, 1, -1, tot);
     }
     if (tid == 0) tot.flush(io.counters);
 }
@@ -189,6 +202,19 @@ namespace ldpc {
 //     compile-time slot strides (immediate offsets);
 //   * decisions are scattered back to true variable order once, in the last iteration.
 // ---------------------------------------------------------------------------------------------
+// Step k's byte offset out of the thread's register-resident row schedule (two uint16 per word),
+// unpacked on the FMA pipe (IMAD.HI / IMAD): the ALU pipe is the busy one in the check phase.
+template <int NW>
+LDPC_DEVINL uint32_t row_off(const uint32_t (&offp)[NW], int k)
+{
+    const uint32_t x = offp[k >> 1];
+    uint32_t hi, lo;
+    asm("mul.hi.u32 %0, %1, 65536;" : "=r"(hi) : "r"(x));
+    if (k & 1) return hi;
+    asm("mad.lo.u32 %0, %1, 0xFFFF0000, %2;" : "=r"(lo) : "r"(hi), "r"(x));
+    return lo;
+}
+
 template <typename Real, int DC, int DV, int NFIX, int NT_MAX, int MINB>
 __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c, const DecParams p, const FrameIO io)
 {
@@ -209,8 +235,21 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
     const Real alpha = (Real)p.alpha, delta = (Real)p.delta;
     const bool normalized = (p.flags & LDPC_GPU_F_NORMALIZED_MS) != 0, offset = (p.flags & LDPC_GPU_F_OFFSET_MS) != 0;
     const uint32_t qflags = p.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES);
+    const bool fcond = !io.y || io.y_dtype == LDPC_GPU_DT_F32;      // fp32 instantiation: fp32 front end on fp32 samples
 
     CtaTotals tot; tot.clear();
+#ifdef LDPC_REG_OFFSETS
+    // thread j owns row j for every frame of the launch: its schedule stays in registers
+    uint32_t offp[DC / 2];
+    {
+        const int j = tid < M ? tid : 0;
+#pragma unroll
+        for (int g = 0; g < DC / 8; g++) {
+            const uint4 w = __ldg(&c.sched16[(size_t)g * M + j]);
+            offp[4 * g + 0] = w.x; offp[4 * g + 1] = w.y; offp[4 * g + 2] = w.z; offp[4 * g + 3] = w.w;
+        }
+    }
+#endif
 
     for (long long f = blockIdx.x; f < io.n_frames; f += gridDim.x) {
         const uint8_t *cw = codeword_row(io, c, f);
@@ -227,11 +266,17 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int i = 4 * b + q;
-                double v = y4[q];
-                if (qflags & LDPC_GPU_F_QUANTIZE_SAMPLES) v = quantize_ms(v, p);
-                if (qflags & LDPC_GPU_F_SATURATE_SAMPLES) { if (v > p.Ymax) v = p.Ymax; if (v < -p.Ymax) v = -p.Ymax; }
-                const bool rneg = !(v > 0);
-                const Real vr = (Real)v;
+                Real vr; bool rneg;
+                if (sizeof(Real) == 4 && fcond) {
+                    const float vf = condition_ms_f32((float)y4[q], p, qflags);
+                    vr = (Real)vf; rneg = !(vf > 0.0f);
+                } else {
+                    double v = y4[q];
+                    if (qflags & LDPC_GPU_F_QUANTIZE_SAMPLES) v = quantize_ms(v, p);
+                    if (qflags & LDPC_GPU_F_SATURATE_SAMPLES) { if (v > p.Ymax) v = p.Ymax; if (v < -p.Ymax) v = -p.Ymax; }
+                    rneg = !(v > 0);
+                    vr = (Real)v;
+                }
                 const int col = (int)(((q < 2 ? cc.x : cc.y) >> (16 * (q & 1))) & 0xffffu);
                 yq[col] = vr;
                 const int cb = cw ? cw[i] : 0;
@@ -254,10 +299,28 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
             const bool last = (it == p.T - 1);
             if (last) for (int w = tid; w < nwords; w += nt) dbits[w] = 0u;          // re-filled below, in true variable order
             // ---- check-node phase ----------------------------------------------------------------
+#ifndef LDPC_EXPERIMENT_SKIP_CN
             for (int j = tid; j < M; j += nt) {
                 Real v[DC];
-                Real m1 = INF, m2 = INF;
-                typename SignOps<Real>::acc_t sg = SignOps<Real>::zero();
+#ifndef LDPC_NACC
+#define LDPC_NACC 1
+#endif
+                // LDPC_NACC independent partial reductions (exact: min / max / sign parity are associative)
+                constexpr int NA = LDPC_NACC;
+                Real pm1[NA], pm2[NA];
+                typename SignOps<Real>::acc_t psg[NA];
+#pragma unroll
+                for (int q = 0; q < NA; q++) { pm1[q] = INF; pm2[q] = INF; psg[q] = SignOps<Real>::zero(); }
+#ifdef LDPC_REG_OFFSETS
+#pragma unroll
+                for (int k = 0; k < DC; k++) {
+                    v[k] = *reinterpret_cast<const Real *>(msgb + row_off(offp, k));
+                    const Real a = absr(v[k]);
+                    pm2[k % NA] = rmin(pm2[k % NA], rmax(pm1[k % NA], a));
+                    pm1[k % NA] = rmin(pm1[k % NA], a);
+                    SignOps<Real>::fold(psg[k % NA], v[k]);
+                }
+#else
 #pragma unroll
                 for (int g = 0; g < NG; g++) {
                     const uint4 w = __ldg(&c.sched[(size_t)g * M + j]);
@@ -267,11 +330,24 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
                         const int k = g * 4 + q;
                         v[k] = *reinterpret_cast<const Real *>(msgb + off[q]);
                         const Real a = absr(v[k]);
-                        m2 = rmin(m2, rmax(m1, a));
-                        m1 = rmin(m1, a);
-                        SignOps<Real>::fold(sg, v[k]);
+                        pm2[k % NA] = rmin(pm2[k % NA], rmax(pm1[k % NA], a));
+                        pm1[k % NA] = rmin(pm1[k % NA], a);
+                        SignOps<Real>::fold(psg[k % NA], v[k]);
                     }
                 }
+#endif
+                // merge (a1<=a2) with (b1<=b2): min1 = min(a1,b1), min2 = min(max(a1,b1), a2, b2)
+#pragma unroll
+                for (int st = 1; st < NA; st *= 2)
+#pragma unroll
+                    for (int q = 0; q + st < NA; q += 2 * st) {
+                        const Real a1 = pm1[q], b1 = pm1[q + st];
+                        pm2[q] = rmin(rmax(a1, b1), rmin(pm2[q], pm2[q + st]));
+                        pm1[q] = rmin(a1, b1);
+                        psg[q] = SignOps<Real>::merge(psg[q], psg[q + st]);
+                    }
+                const Real m1 = pm1[0], m2 = pm2[0];
+                const typename SignOps<Real>::acc_t sg = psg[0];
                 Real o1 = m1, o2 = m2;
                 if (normalized) {
                     if (sizeof(Real) == 8) { o1 = o1 / alpha; o2 = o2 / alpha; }
@@ -279,6 +355,13 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
                 }
                 if (offset) { o1 = o1 - delta; o1 = (o1 > 0) ? o1 : (Real)0; o2 = o2 - delta; o2 = (o2 > 0) ? o2 : (Real)0; }
                 const Real s1 = SignOps<Real>::presign(o1, sg), s2 = SignOps<Real>::presign(o2, sg);
+#ifdef LDPC_REG_OFFSETS
+#pragma unroll
+                for (int k = 0; k < DC; k++) {
+                    const Real sel = (absr(v[k]) == m1) ? s2 : s1;
+                    *reinterpret_cast<Real *>(msgb + row_off(offp, k)) = SignOps<Real>::apply(sel, v[k]);
+                }
+#else
 #pragma unroll
                 for (int g = 0; g < NG; g++) {
                     const uint4 w = __ldg(&c.sched[(size_t)g * M + j]);
@@ -290,9 +373,12 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
                         *reinterpret_cast<Real *>(msgb + off[q]) = SignOps<Real>::apply(sel, v[k]);
                     }
                 }
+#endif
             }
+#endif
             __syncthreads();
             // ---- variable-node phase (storage columns) --------------------------------------------
+#ifndef LDPC_EXPERIMENT_SKIP_VN
             for (int col = tid; col < N; col += nt) {
                 Real cm[DV];
                 Real sum = yq[col];
@@ -309,10 +395,10 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
                     }
                 }
             }
+#endif
             __syncthreads();
         }
-        const int satisfied = syndrome_ok(c, dbits);
-        finish_frame(c, p, io, f, cw, dbits, fs, p.T, satisfied, 0, 0, 1, -1, tot);
+        finish_frame(c, p, io, f, cw, dbits, fs, p.T, /*satisfied: evaluated on demand*/ -1, 0, 0, 1, -1, tot);
     }
     if (tid == 0) tot.flush(io.counters);
 }

@@ -29,6 +29,7 @@ struct CodeDev {
     const uint32_t*vn_chk;   // [s*N + i]  check of slot s of variable i, padded with 0
     // bank-conflict-free check schedule of a regular code (ldpc_schedule.h), or NULL
     const uint4   *sched;    // [(t/4)][j]  four BYTE offsets (s*N + col(i))*sizeof(Real) of steps 4(t/4)..+3 of row j
+    const uint4   *sched16;  // [(t/8)][j]  the same as eight uint16 byte offsets per vector (when they fit 16 bits), or NULL
     const uint16_t*col_of_var; // [N] storage column of variable i
     const uint16_t*var_of_col; // [N] inverse
 };
@@ -40,6 +41,7 @@ struct DecParams {
     double   Ymax, alpha, delta, theta, lambda, noiseScale, w, theta0, MAXLLR;
     double   ms_Nq1;        // Nq - 1,             Nq = pow(2,Q)          decodeMinSum.cpp:125
     double   ms_twoY;       // 2.0 * Ymax
+    double   ms_inv_twoY;   // 1/(2*Ymax) when 2*Ymax is a power of two (the division is then exact), else 0
     double   ms_step;       // 2*Ymax/(Nq-1)                              :485
     double   g_qmax;        // pow(2, NQ-1)                               decodeGDBF.cpp:490
     double   g_twol;        // 2 * (Ymax/2.0)
@@ -49,6 +51,7 @@ struct DecParams {
     double   sigma, N0, noiseSigma;                   // decodeMinSum.cpp:146-147, decodeGDBF.cpp:296
     double   uni_scale;     // (sqrt(3)*noiseSigma)*2.0                   decodeGDBF.cpp:322
     float    inv_alpha_f;   // fp32 instantiation: multiply instead of divide
+    float    ms_scale_f, ms_step_f, Ymax_f;   // fp32 front end (fp32 instantiation fed by the Philox channel or fp32 samples)
     int      iter_hist_len;
     int      rows_per_step; // GDBF noise rows consumed per flip step
 };
