@@ -21,6 +21,7 @@
 #include "ldpc_mp_kernels.cuh"
 #include "ldpc_ms_fast.cuh"
 #include "ldpc_schedule.h"
+#include "ldpc_ms_tile.cuh"
 #include "ldpc_bf_kernels.cuh"
 
 using namespace ldpc;
@@ -213,6 +214,7 @@ struct ldpc_gpu_decoder {
     KernelFn fn = nullptr;
     int block = 0, smem = 0, ctas_per_sm = 0, grid_full = 0;
     bool gstate = false; size_t ws_stride = 0; unsigned char *d_ws = nullptr;   // HBM-resident frame state
+    int frames_per_cta = 1;                                                      // > 1: frame-interleaved tile kernel
     DecParams base;
     Slot slot[2];
     unsigned long long *d_counters = nullptr, *d_ew = nullptr, *d_it = nullptr, *d_ph = nullptr;
@@ -347,6 +349,18 @@ static int pick_kernel(ldpc_gpu_decoder *d)
 #undef MP_PICK
 #undef MP_PICK2
         block = std::min(1024, std::max(128, round32(v.M)));
+        if (algo == ALGO_MS && d->gstate && v.dv_max <= 8 && v.dc_max <= 64 && !getenv("LDPC_GPU_NO_TILE")) {
+            // HBM-bound codes: frame-interleaved tile kernel (ldpc_ms_tile.cuh)
+#define TILE_PICK(DC, NT) (f64 ? (v.idx16 ? (KernelFn)ms_tile_kernel<double, uint16_t, DC, 8, NT> : (KernelFn)ms_tile_kernel<double, uint32_t, DC, 8, NT>) \
+                               : (v.idx16 ? (KernelFn)ms_tile_kernel<float, uint16_t, DC, 8, NT> : (KernelFn)ms_tile_kernel<float, uint32_t, DC, 8, NT>))
+            if (v.dc_max <= 8) { d->fn = TILE_PICK(8, 1024); block = 1024; }      // measured: 1024 > 512 threads per tile
+            else if (v.dc_max <= 32) { d->fn = TILE_PICK(32, 512); block = 512; }
+            else { d->fn = TILE_PICK(64, 256); block = 256; }
+#undef TILE_PICK
+            d->frames_per_cta = f64 ? TileFI<double>::value : TileFI<float>::value;
+            d->ws_stride = f64 ? ms_tile_state_bytes<double>(v) : ms_tile_state_bytes<float>(v);
+            smem = f64 ? ms_tile_smem_bytes<double>(v) : ms_tile_smem_bytes<float>(v);
+        }
         if (algo == ALGO_MS && v.idx16 && !d->gstate && !getenv("LDPC_GPU_GENERIC_MS")) {
             // degree-specialised min-sum kernel where an instantiation covers the code
             const bool rc = v.regular_dc > 0, rv = v.regular_dv > 0;
@@ -512,7 +526,7 @@ extern "C" int ldpc_gpu_decoder_set_codewords(ldpc_gpu_decoder *d, const uint8_t
 extern "C" int ldpc_gpu_decoder_geometry(const ldpc_gpu_decoder *d, int *grid, int *block, int *smem, int *fpc)
 {
     if (!d) return set_err(LDPC_GPU_ERR_INVALID_ARG, "decoder is NULL");
-    if (grid) *grid = d->grid_full; if (block) *block = d->block; if (smem) *smem = d->smem; if (fpc) *fpc = d->ctas_per_sm;
+    if (grid) *grid = d->grid_full; if (block) *block = d->block; if (smem) *smem = d->smem; if (fpc) *fpc = d->ctas_per_sm * d->frames_per_cta;
     return LDPC_GPU_OK;
 }
 extern "C" int ldpc_gpu_last_timing(const ldpc_gpu_decoder *d, double *ms, int64_t *launches)
@@ -559,7 +573,7 @@ static int fetch_counters(ldpc_gpu_decoder *d, ldpc_gpu_counters *out, cudaStrea
 
 static int launch(ldpc_gpu_decoder *d, const DecParams &p, const FrameIO &io, cudaStream_t st)
 {
-    const long long want = std::min<long long>(io.n_frames, d->grid_full);
+    const long long want = std::min<long long>((io.n_frames + d->frames_per_cta - 1) / d->frames_per_cta, d->grid_full);
     if (want <= 0) return LDPC_GPU_OK;
     FrameIO io2 = io; io2.workspace = d->d_ws; io2.ws_stride = d->ws_stride;
     d->fn<<<(unsigned)want, d->block, d->smem, st>>>(d->dev, p, io2);

@@ -1,0 +1,167 @@
+// ldpc_ms_tile.cuh -- min-sum family for codes whose messages do not fit one SM (DVB-S2 N=64800,
+// E=226799: 3.9 MB of fp32 message traffic per frame-iteration).  This path is HBM-bound, so the
+// layout is chosen for the memory system rather than for shared memory:
+//
+//   one CTA owns a TILE of FI frames (FI * sizeof(Real) = 32 bytes, one DRAM sector) and keeps
+//       msg[(s*N + i) * FI + fl]     yq[i * FI + fl]          fl = frame lane inside the tile
+//   in its slice of an HBM workspace.  A thread is (node, fl); a warp is 32/FI consecutive nodes x FI
+//   frames.  A variable warp therefore touches 128 contiguous bytes per slot, and a check warp's
+//   gather touches whole 32-byte sectors (the one-frame-per-CTA GSTATE kernel used 4 bytes of every
+//   sector it fetched: profiles/r1_summary.md).  Algorithmic traffic per frame-iteration is the
+//   minimum (4E + N) * sizeof(Real) bytes: every message read once and written once
+//   per phase.  The row's indices are loaded once per thread as 16-byte vectors and are shared by the
+//   FI lanes of the row (same address -> one transaction).
+//
+// Arithmetic and order are those of ms_fast_kernel / mp_kernel (the reference's); decisions, counters
+// and a-posteriori sums are bit-identical to the single-frame kernels in both precisions.
+#pragma once
+#include "ldpc_ms_fast.cuh"
+
+namespace ldpc {
+
+template <typename Real> struct TileFI { enum { value = 32 / sizeof(Real) }; };
+
+template <typename Real>
+static inline size_t ms_tile_state_bytes(const CodeDev &c)
+{
+    return (((size_t)c.dvN + c.N) * sizeof(Real) * TileFI<Real>::value + 255) & ~(size_t)255;
+}
+template <typename Real>
+static inline size_t ms_tile_smem_bytes(const CodeDev &c)
+{
+    const size_t FI = TileFI<Real>::value;
+    return ((16 * FI + 4 * FI * (size_t)((c.N + 31) / 32)) + 15) & ~(size_t)15;
+}
+
+// DCMAX / DVMAX: compile-time bounds of the row / column weights (register arrays).
+template <typename Real, typename IdxT, int DCMAX, int DVMAX, int NT_MAX>
+__global__ void __launch_bounds__(NT_MAX, 1) ms_tile_kernel(const CodeDev c, const DecParams p, const FrameIO io)
+{
+    constexpr int FI = TileFI<Real>::value;
+    constexpr int VPL = IdxVec<IdxT>::VPL, NG = (DCMAX + VPL - 1) / VPL;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FrameScratch *fs = reinterpret_cast<FrameScratch *>(smem_raw);                       // [FI]
+    const int N = c.N, M = c.M, nwords = (N + 31) >> 5, nblk = (N + 3) >> 2;
+    uint32_t *dbits = reinterpret_cast<uint32_t *>(smem_raw + 16 * FI);                // [FI][nwords]
+    Real *msg = reinterpret_cast<Real *>(io.workspace + (size_t)blockIdx.x * io.ws_stride);
+    Real *yq = msg + (size_t)c.dvN * FI;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const uint4 *cnv = reinterpret_cast<const uint4 *>(c.cn_pos);
+    const Real INF = real_inf<Real>();
+    const Real alpha = (Real)p.alpha, delta = (Real)p.delta;
+    const bool normalized = (p.flags & LDPC_GPU_F_NORMALIZED_MS) != 0, offset = (p.flags & LDPC_GPU_F_OFFSET_MS) != 0;
+    const uint32_t qflags = p.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES);
+    const bool fcond = !io.y || io.y_dtype == LDPC_GPU_DT_F32;
+    const long long ntiles = (io.n_frames + FI - 1) / FI;
+    CtaTotals tot; tot.clear();
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long f0 = tile * FI;
+        if (tid < FI) { fs[tid].uncoded = 0; fs[tid].errors = 0; fs[tid].flag = 0; }
+        for (int w = tid; w < FI * nwords; w += nt) dbits[w] = 0u;
+        __syncthreads();
+        // ---- channel front end, (block of 4 samples, frame lane) per thread ---------------------
+        for (int t = tid; t < nblk * FI; t += nt) {
+            const int b = t / FI, fl = t % FI;
+            const long long f = (f0 + fl < io.n_frames) ? f0 + fl : io.n_frames - 1;     // dead lanes replay the last frame, unreported
+            const uint8_t *cw = codeword_row(io, c, f);
+            double y4[4];
+            raw_samples4(io, p, c, f, cw, b, y4);
+            uint32_t nib = 0; int unc = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = 4 * b + q;
+                if (i >= N) break;
+                Real vr; bool rneg;
+                if (sizeof(Real) == 4 && fcond) {
+                    const float vf = condition_ms_f32((float)y4[q], p, qflags);
+                    vr = (Real)vf; rneg = !(vf > 0.0f);
+                } else {
+                    double v = y4[q];
+                    if (qflags & LDPC_GPU_F_QUANTIZE_SAMPLES) v = quantize_ms(v, p);
+                    if (qflags & LDPC_GPU_F_SATURATE_SAMPLES) { if (v > p.Ymax) v = p.Ymax; if (v < -p.Ymax) v = -p.Ymax; }
+                    rneg = !(v > 0); vr = (Real)v;
+                }
+                yq[(size_t)i * FI + fl] = vr;
+                const int cb = cw ? cw[i] : 0;
+                unc += (int)(rneg != (cb != 0));
+                nib |= (uint32_t)rneg << q;
+                const int deg = c.vn_deg[i];
+                for (int s = 0; s < deg; s++) msg[((size_t)s * N + i) * FI + fl] = vr;
+                if (io.out_soft && p.T == 0 && f0 + fl < io.n_frames) {
+                    if (io.y_dtype == LDPC_GPU_DT_F64) ((double *)io.out_soft)[(size_t)f * N + i] = (double)vr;
+                    else ((float *)io.out_soft)[(size_t)f * N + i] = (float)vr;
+                }
+            }
+            if (nib) atomicOr(&dbits[fl * nwords + ((4 * b) >> 5)], nib << ((4 * b) & 31));
+            if (unc) atomicAdd(&fs[fl].uncoded, unc);
+        }
+        __syncthreads();
+
+        for (int it = 0; it < p.T; it++) {
+            const bool last = (it == p.T - 1);
+            if (last) for (int w = tid; w < FI * nwords; w += nt) dbits[w] = 0u;
+            // ---- check-node phase: (row, frame lane) per thread -------------------------------------
+            for (int t = tid; t < M * FI; t += nt) {
+                const int j = t / FI, fl = t % FI;
+                const int deg = c.cn_deg[j];
+                uint4 w[NG];
+#pragma unroll
+                for (int g = 0; g < NG; g++) if (g * VPL < deg) w[g] = __ldg(&cnv[(size_t)g * M + j]);
+                Real v[DCMAX];
+                Real m1 = INF, m2 = INF;
+                typename SignOps<Real>::acc_t sg = SignOps<Real>::zero();
+#pragma unroll
+                for (int k = 0; k < DCMAX; k++) if (k < deg) v[k] = msg[(size_t)IdxVec<IdxT>::get(w[k / VPL], k % VPL) * FI + fl];
+#pragma unroll
+                for (int k = 0; k < DCMAX; k++) if (k < deg) {
+                    const Real a = absr(v[k]);
+                    m2 = rmin(m2, rmax(m1, a)); m1 = rmin(m1, a);
+                    SignOps<Real>::fold(sg, v[k]);
+                }
+                Real o1 = m1, o2 = m2;
+                if (normalized) {
+                    if (sizeof(Real) == 8) { o1 = o1 / alpha; o2 = o2 / alpha; }
+                    else { o1 = o1 * (Real)p.inv_alpha_f; o2 = o2 * (Real)p.inv_alpha_f; }
+                }
+                if (offset) { o1 = o1 - delta; o1 = (o1 > 0) ? o1 : (Real)0; o2 = o2 - delta; o2 = (o2 > 0) ? o2 : (Real)0; }
+                const Real s1 = SignOps<Real>::presign(o1, sg), s2 = SignOps<Real>::presign(o2, sg);
+#pragma unroll
+                for (int k = 0; k < DCMAX; k++) if (k < deg) {
+                    const Real sel = (absr(v[k]) == m1) ? s2 : s1;
+                    msg[(size_t)IdxVec<IdxT>::get(w[k / VPL], k % VPL) * FI + fl] = SignOps<Real>::apply(sel, v[k]);
+                }
+            }
+            __syncthreads();
+            // ---- variable-node phase: (variable, frame lane) per thread ------------------------------
+            for (int t = tid; t < N * FI; t += nt) {
+                const int i = t / FI, fl = t % FI;
+                const int deg = c.vn_deg[i];
+                Real cm[DVMAX];
+                Real sum = yq[(size_t)i * FI + fl];
+#pragma unroll
+                for (int s = 0; s < DVMAX; s++) if (s < deg) cm[s] = msg[((size_t)s * N + i) * FI + fl];
+#pragma unroll
+                for (int s = 0; s < DVMAX; s++) if (s < deg) sum += cm[s];                // nlist order
+#pragma unroll
+                for (int s = 0; s < DVMAX; s++) if (s < deg) msg[((size_t)s * N + i) * FI + fl] = sum - cm[s];
+                if (last) {
+                    if (!(sum > 0)) atomicOr(&dbits[fl * nwords + (i >> 5)], 1u << (i & 31));
+                    if (io.out_soft && f0 + fl < io.n_frames) {
+                        if (io.y_dtype == LDPC_GPU_DT_F64) ((double *)io.out_soft)[(size_t)(f0 + fl) * N + i] = (double)sum;
+                        else ((float *)io.out_soft)[(size_t)(f0 + fl) * N + i] = (float)sum;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        for (int fl = 0; fl < FI; fl++) {
+            if (f0 + fl >= io.n_frames) break;                       // uniform: dead lanes are not reported
+            const uint8_t *cw = codeword_row(io, c, f0 + fl);
+            finish_frame(c, p, io, f0 + fl, cw, dbits + fl * nwords, &fs[fl], p.T, -1, 0, 0, 1, -1, tot);
+        }
+    }
+    if (tid == 0) tot.flush(io.counters);
+}
+
+} // namespace ldpc
