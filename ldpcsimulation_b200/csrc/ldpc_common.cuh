@@ -105,16 +105,19 @@ LDPC_DEVINL void raw_samples4(const FrameIO &io, const DecParams &p, const CodeD
     }
 }
 
-// Per-CTA running totals (thread 0's registers), flushed once per launch.
+// Per-CTA running totals, flushed once per launch.  They live in (static) shared memory and are
+// touched by thread 0 only: as a register struct they cost 16 registers in every thread of the CTA
+// for the whole kernel (profiles/r1_summary.md).
 struct CtaTotals {
-    unsigned long long v[CNT_N];
+    unsigned long long *v;
     LDPC_DEVINL void clear() {
-#pragma unroll
-        for (int q = 0; q < CNT_N; q++) v[q] = 0ull;
+        __shared__ unsigned long long s_totals[CNT_N];
+        v = s_totals;
+        if (threadIdx.x < CNT_N) s_totals[threadIdx.x] = 0ull;
+        __syncthreads();
     }
     LDPC_DEVINL void flush(unsigned long long *g) {
         if (!g) return;
-#pragma unroll
         for (int q = 0; q < CNT_N; q++) if (v[q]) atomicAdd(&g[q], v[q]);
     }
 };

@@ -214,6 +214,7 @@ struct ldpc_gpu_decoder {
     KernelFn fn = nullptr;
     int block = 0, smem = 0, ctas_per_sm = 0, grid_full = 0;
     bool gstate = false; size_t ws_stride = 0; unsigned char *d_ws = nullptr;   // HBM-resident frame state
+    long long stagger_cycles = 0;
     int frames_per_cta = 1;                                                      // > 1: frame-interleaved tile kernel
     DecParams base;
     Slot slot[2];
@@ -369,7 +370,9 @@ static int pick_kernel(ldpc_gpu_decoder *d)
             const char *mb = getenv("LDPC_GPU_MINB");
             if (v.sched && v.regular_dc == 32 && v.regular_dv == 6 && v.N == 2048 && v.M <= 384)   // the 802.3an H, scheduled
                 fast = f64 ? (KernelFn)ms_sched_kernel<double, 32, 6, 2048, 384, 1>
-                           : ((mb && atoi(mb) == 3) ? (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 3>
+                           : ((mb && atoi(mb) == 13) ? (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 3, true>
+                              : (mb && atoi(mb) == 12) ? (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 2, true>
+                              : (mb && atoi(mb) == 3) ? (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 3>
                               : (mb && atoi(mb) == 1) ? (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 1>
                                                       : (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 2>);
             else if (v.regular_dc == 32 && v.regular_dv == 6 && v.M <= 384 && !f64)     // the 802.3an H: 384 check threads per frame
@@ -576,6 +579,7 @@ static int launch(ldpc_gpu_decoder *d, const DecParams &p, const FrameIO &io, cu
     const long long want = std::min<long long>((io.n_frames + d->frames_per_cta - 1) / d->frames_per_cta, d->grid_full);
     if (want <= 0) return LDPC_GPU_OK;
     FrameIO io2 = io; io2.workspace = d->d_ws; io2.ws_stride = d->ws_stride;
+    { const char *sg = getenv("LDPC_GPU_STAGGER"); io2.stagger_cycles = sg ? atoll(sg) : d->stagger_cycles; }
     d->fn<<<(unsigned)want, d->block, d->smem, st>>>(d->dev, p, io2);
     CU_TRY(cudaGetLastError());
     d->last_launches++;

@@ -215,7 +215,10 @@ LDPC_DEVINL uint32_t row_off(const uint32_t (&offp)[NW], int k)
     return lo;
 }
 
-template <typename Real, int DC, int DV, int NFIX, int NT_MAX, int MINB>
+// HALF: a check thread keeps only the second half of its row in registers and gathers the first half
+// again in its write pass (the gathers are conflict-free, so this trades 16 extra LDS per row for 16
+// registers per thread, which is what allows a third CTA per SM).
+template <typename Real, int DC, int DV, int NFIX, int NT_MAX, int MINB, bool HALF = false>
 __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c, const DecParams p, const FrameIO io)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -238,6 +241,13 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
     const bool fcond = !io.y || io.y_dtype == LDPC_GPU_DT_F32;      // fp32 instantiation: fp32 front end on fp32 samples
 
     CtaTotals tot; tot.clear();
+    // Co-resident CTAs start together and do identical work, so they stay in lock step: both in the
+    // ALU-bound check phase, then both in the LSU-bound variable phase.  Starting the second CTA of
+    // every SM a fraction of an iteration late lets the two phases overlap (profiles/r1_summary.md).
+    if (io.stagger_cycles > 0 && blockIdx.x >= gridDim.x / 2) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < io.stagger_cycles) { }
+    }
 #ifdef LDPC_REG_OFFSETS
     // thread j owns row j for every frame of the launch: its schedule stays in registers
     uint32_t offp[DC / 2];
@@ -301,26 +311,10 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
             // ---- check-node phase ----------------------------------------------------------------
 #ifndef LDPC_EXPERIMENT_SKIP_CN
             for (int j = tid; j < M; j += nt) {
-                Real v[DC];
-#ifndef LDPC_NACC
-#define LDPC_NACC 1
-#endif
-                // LDPC_NACC independent partial reductions (exact: min / max / sign parity are associative)
-                constexpr int NA = LDPC_NACC;
-                Real pm1[NA], pm2[NA];
-                typename SignOps<Real>::acc_t psg[NA];
-#pragma unroll
-                for (int q = 0; q < NA; q++) { pm1[q] = INF; pm2[q] = INF; psg[q] = SignOps<Real>::zero(); }
-#ifdef LDPC_REG_OFFSETS
-#pragma unroll
-                for (int k = 0; k < DC; k++) {
-                    v[k] = *reinterpret_cast<const Real *>(msgb + row_off(offp, k));
-                    const Real a = absr(v[k]);
-                    pm2[k % NA] = rmin(pm2[k % NA], rmax(pm1[k % NA], a));
-                    pm1[k % NA] = rmin(pm1[k % NA], a);
-                    SignOps<Real>::fold(psg[k % NA], v[k]);
-                }
-#else
+                constexpr int KEEP0 = HALF ? DC / 2 : 0;              // steps [KEEP0, DC) stay in registers
+                Real v[DC - KEEP0];
+                Real m1 = INF, m2 = INF;
+                typename SignOps<Real>::acc_t sg = SignOps<Real>::zero();
 #pragma unroll
                 for (int g = 0; g < NG; g++) {
                     const uint4 w = __ldg(&c.sched[(size_t)g * M + j]);
@@ -328,26 +322,14 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const int k = g * 4 + q;
-                        v[k] = *reinterpret_cast<const Real *>(msgb + off[q]);
-                        const Real a = absr(v[k]);
-                        pm2[k % NA] = rmin(pm2[k % NA], rmax(pm1[k % NA], a));
-                        pm1[k % NA] = rmin(pm1[k % NA], a);
-                        SignOps<Real>::fold(psg[k % NA], v[k]);
+                        const Real x = *reinterpret_cast<const Real *>(msgb + off[q]);
+                        if (k >= KEEP0) v[k - KEEP0] = x;
+                        const Real a = absr(x);
+                        m2 = rmin(m2, rmax(m1, a));
+                        m1 = rmin(m1, a);
+                        SignOps<Real>::fold(sg, x);
                     }
                 }
-#endif
-                // merge (a1<=a2) with (b1<=b2): min1 = min(a1,b1), min2 = min(max(a1,b1), a2, b2)
-#pragma unroll
-                for (int st = 1; st < NA; st *= 2)
-#pragma unroll
-                    for (int q = 0; q + st < NA; q += 2 * st) {
-                        const Real a1 = pm1[q], b1 = pm1[q + st];
-                        pm2[q] = rmin(rmax(a1, b1), rmin(pm2[q], pm2[q + st]));
-                        pm1[q] = rmin(a1, b1);
-                        psg[q] = SignOps<Real>::merge(psg[q], psg[q + st]);
-                    }
-                const Real m1 = pm1[0], m2 = pm2[0];
-                const typename SignOps<Real>::acc_t sg = psg[0];
                 Real o1 = m1, o2 = m2;
                 if (normalized) {
                     if (sizeof(Real) == 8) { o1 = o1 / alpha; o2 = o2 / alpha; }
@@ -355,25 +337,19 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
                 }
                 if (offset) { o1 = o1 - delta; o1 = (o1 > 0) ? o1 : (Real)0; o2 = o2 - delta; o2 = (o2 > 0) ? o2 : (Real)0; }
                 const Real s1 = SignOps<Real>::presign(o1, sg), s2 = SignOps<Real>::presign(o2, sg);
-#ifdef LDPC_REG_OFFSETS
 #pragma unroll
-                for (int k = 0; k < DC; k++) {
-                    const Real sel = (absr(v[k]) == m1) ? s2 : s1;
-                    *reinterpret_cast<Real *>(msgb + row_off(offp, k)) = SignOps<Real>::apply(sel, v[k]);
-                }
-#else
-#pragma unroll
-                for (int g = 0; g < NG; g++) {
+                for (int g = NG - 1; g >= 0; g--) {                   // register-resident half first
                     const uint4 w = __ldg(&c.sched[(size_t)g * M + j]);
                     const uint32_t off[4] = { w.x, w.y, w.z, w.w };
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const int k = g * 4 + q;
-                        const Real sel = (absr(v[k]) == m1) ? s2 : s1;
-                        *reinterpret_cast<Real *>(msgb + off[q]) = SignOps<Real>::apply(sel, v[k]);
+                        Real *slot = reinterpret_cast<Real *>(msgb + off[q]);
+                        const Real x = (k >= KEEP0) ? v[k >= KEEP0 ? k - KEEP0 : 0] : *slot;
+                        const Real sel = (absr(x) == m1) ? s2 : s1;
+                        *slot = SignOps<Real>::apply(sel, x);
                     }
                 }
-#endif
             }
 #endif
             __syncthreads();

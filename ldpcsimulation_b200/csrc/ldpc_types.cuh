@@ -78,6 +78,7 @@ struct FrameIO {
     unsigned long long *it_hist;  // device [iter_hist_len] or NULL
     unsigned long long *ph_hist;  // device [maxphase] or NULL
     unsigned long long seed;
+    long long stagger_cycles;     // start delay of the second CTA of each SM (phase offset), 0 = none
     unsigned char *workspace;     // device, gridDim.x * ws_stride bytes: per-CTA frame state of the HBM-resident
     size_t         ws_stride;     //   instantiations (codes whose state exceeds one SM's shared memory)
     // channel_dump outputs
