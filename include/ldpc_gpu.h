@@ -85,6 +85,7 @@ extern "C" {
 /* ---- element type of caller sample / soft buffers ---------------------- */
 #define LDPC_GPU_DT_F64  0
 #define LDPC_GPU_DT_F32  1
+#define LDPC_GPU_DT_F16  2   /* IEEE binary16 samples in (halves the host->device bytes); out_soft is then fp32 */
 
 /* Length of NGDBFhw's per-frame noise buffer (src/NGDBFhw.cpp:151-152). */
 #define LDPC_GPU_HW_QBUF  2648
@@ -145,7 +146,7 @@ typedef struct ldpc_gpu_counters {
 typedef struct ldpc_gpu_batch {
     int64_t      n_frames;
     int32_t      mem;           /* LDPC_GPU_MEM_*: where ALL pointers below live        */
-    int32_t      y_dtype;       /* LDPC_GPU_DT_*: element type of y and out_soft        */
+    int32_t      y_dtype;       /* LDPC_GPU_DT_*: element type of y and out_soft (F16 in -> F32 soft out) */
     const void  *y;             /* [F][N] raw channel samples y = x(1+sigma n), before clip/quantise */
     const double*noise;         /* optional raw RNG outputs consumed in reference order:
                                    GDBF addNoise: rann() values, [F][noise_rows][N], one row per executed

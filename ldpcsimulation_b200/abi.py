@@ -33,7 +33,7 @@ MACRO_FLAGS = {
 
 PREC_F64, PREC_F32 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
-DT_F64, DT_F32 = 0, 1
+DT_F64, DT_F32, DT_F16 = 0, 1, 2
 HW_QBUF = 2648
 
 

@@ -150,11 +150,11 @@ class Decoder:
                want_soft=True, y_dtype=abi.DT_F64, outputs=True):
         """Host-memory parity entry.  y: [F][N] raw channel samples."""
         N = self.N
-        y = np.ascontiguousarray(y, dtype=np.float64 if y_dtype == abi.DT_F64 else np.float32)
+        y = np.ascontiguousarray(y, dtype={abi.DT_F64: np.float64, abi.DT_F32: np.float32, abi.DT_F16: np.float16}[y_dtype])
         F = y.shape[0]
         out = Result(bits=np.zeros((F, (N + 7) // 8), np.uint8) if outputs else None,
                      iters=np.zeros(F, np.int32) if outputs else None,
-                     soft=np.zeros((F, N), y.dtype) if (want_soft and outputs) else None,
+                     soft=np.zeros((F, N), np.float64 if y_dtype == abi.DT_F64 else np.float32) if (want_soft and outputs) else None,
                      errors=np.zeros(F, np.int32) if outputs else None,
                      flags=np.zeros(F, np.uint8) if outputs else None)
         b = abi.Batch()

@@ -2,6 +2,7 @@
 // per-frame epilogue and the accounting of a19 (src/decodeMinSum.cpp:270-288).
 #pragma once
 #include <math.h>
+#include <cuda_fp16.h>
 #include "ldpc_types.cuh"
 #include "ldpc_rng.cuh"
 
@@ -90,7 +91,8 @@ LDPC_DEVINL void raw_samples4(const FrameIO &io, const DecParams &p, const CodeD
         for (int q = 0; q < 4; q++) {
             const int i = i0 + q;
             if (i < c.N) y[q] = (io.y_dtype == LDPC_GPU_DT_F64) ? ((const double *)io.y)[(size_t)f * c.N + i]
-                                                                : (double)((const float *)io.y)[(size_t)f * c.N + i];
+                              : (io.y_dtype == LDPC_GPU_DT_F32) ? (double)((const float *)io.y)[(size_t)f * c.N + i]
+                                                                : (double)__half2float(((const __half *)io.y)[(size_t)f * c.N + i]);
             else y[q] = 1.0;
         }
     } else {

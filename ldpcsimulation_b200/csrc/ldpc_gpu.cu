@@ -594,7 +594,7 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
     if (!d || !b) return set_err(LDPC_GPU_ERR_INVALID_ARG, "decoder or batch is NULL");
     if (b->n_frames < 0) return set_err(LDPC_GPU_ERR_INVALID_ARG, "n_frames < 0");
     if (b->n_frames > 0 && !b->y) return set_err(LDPC_GPU_ERR_INVALID_ARG, "batch.y is NULL");
-    if (b->y_dtype != LDPC_GPU_DT_F64 && b->y_dtype != LDPC_GPU_DT_F32) return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown y_dtype");
+    if (b->y_dtype != LDPC_GPU_DT_F64 && b->y_dtype != LDPC_GPU_DT_F32 && b->y_dtype != LDPC_GPU_DT_F16) return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown y_dtype");
     const int N = d->N, kind = d->cfg.kind;
     const int rps = rows_per_step(d->cfg.flags);
     if (kind == LDPC_GPU_KIND_GDBF && rps > 0) {
@@ -609,7 +609,8 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
     cudaStream_t st0 = d->slot[0].st;
     if (cnt) { if ((rc = zero_counters(d, st0))) return rc; CU_TRY(cudaStreamSynchronize(st0)); }
 
-    const size_t esz = b->y_dtype == LDPC_GPU_DT_F64 ? 8 : 4, bpf = (size_t)(N + 7) / 8;
+    const size_t esz = b->y_dtype == LDPC_GPU_DT_F64 ? 8 : b->y_dtype == LDPC_GPU_DT_F32 ? 4 : 2, bpf = (size_t)(N + 7) / 8;
+    const size_t ssz = b->y_dtype == LDPC_GPU_DT_F64 ? 8 : 4;     // out_soft element size
     const size_t noise_pf = kind == LDPC_GPU_KIND_NGDBF_HW ? (size_t)LDPC_GPU_HW_QBUF : (kind == LDPC_GPU_KIND_GDBF && b->noise ? (size_t)b->noise_rows * N : 0);
     FrameIO io; memset(&io, 0, sizeof io);
     io.y_dtype = b->y_dtype; io.noise_rows = b->noise_rows;
@@ -625,8 +626,13 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
         float ms = 0; cudaEventElapsedTime(&ms, d->slot[0].k0, d->slot[0].k1); d->last_kernel_ms = ms;
     } else if (b->mem == LDPC_GPU_MEM_HOST) {
         // two-slot pipeline: H2D / kernel / D2H of consecutive chunks overlap on two streams
-        const size_t per_frame = esz * N * (b->out_soft ? 2 : 1) + 8 * noise_pf + (b->codeword ? N : 0) + bpf + 16;
-        long long chunk = (long long)std::max<size_t>(1, ((size_t)192 << 20) / per_frame);
+        const size_t per_frame = esz * N + (b->out_soft ? ssz * N : 0) + 8 * noise_pf + (b->codeword ? N : 0) + bpf + 16;
+        // chunks small enough that the first H2D and the last D2H (the parts no kernel hides) are a few percent
+        // of the batch, large enough to give every CTA tens of frames
+        const char *cb = getenv("LDPC_GPU_CHUNK_MB");
+        const size_t chunk_bytes = (size_t)(cb ? atoi(cb) : 16) << 20;
+        long long chunk = (long long)std::max<size_t>(1, chunk_bytes / per_frame);
+        chunk = std::max<long long>(chunk, 16ll * d->grid_full * d->frames_per_cta);
         chunk = std::min<long long>(chunk, std::max<long long>(1, (b->n_frames + 1) / 2));
         if (b->n_frames <= 2 * (long long)d->grid_full) chunk = std::max<long long>(1, b->n_frames);
         std::vector<std::pair<int, bool>> pending;       // slots with a timing pair outstanding
@@ -661,7 +667,7 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
             io.out_bits = nullptr; io.out_iters = nullptr; io.out_soft = nullptr; io.out_errors = nullptr; io.out_flags = nullptr;
             if (b->out_bits)   { if ((rc = s.bits.reserve(bpf * nf))) return rc;  io.out_bits = (uint8_t *)s.bits.p; }
             if (b->out_iters)  { if ((rc = s.iters.reserve(4 * (size_t)nf))) return rc; io.out_iters = (int *)s.iters.p; }
-            if (b->out_soft)   { if ((rc = s.soft.reserve(esz * N * nf))) return rc; io.out_soft = s.soft.p; }
+            if (b->out_soft)   { if ((rc = s.soft.reserve(ssz * N * nf))) return rc; io.out_soft = s.soft.p; }
             if (b->out_errors) { if ((rc = s.errs.reserve(4 * (size_t)nf))) return rc; io.out_errors = (int *)s.errs.p; }
             if (b->out_flags)  { if ((rc = s.flags.reserve((size_t)nf))) return rc; io.out_flags = (uint8_t *)s.flags.p; }
             CU_TRY(cudaEventRecord(s.k0, s.st));
@@ -669,7 +675,7 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
             CU_TRY(cudaEventRecord(s.k1, s.st));
             if (b->out_bits)   CU_TRY(cudaMemcpyAsync(b->out_bits + (size_t)f0 * bpf, s.bits.p, bpf * nf, cudaMemcpyDeviceToHost, s.st));
             if (b->out_iters)  CU_TRY(cudaMemcpyAsync(b->out_iters + f0, s.iters.p, 4 * (size_t)nf, cudaMemcpyDeviceToHost, s.st));
-            if (b->out_soft)   CU_TRY(cudaMemcpyAsync((char *)b->out_soft + (size_t)f0 * N * esz, s.soft.p, esz * N * nf, cudaMemcpyDeviceToHost, s.st));
+            if (b->out_soft)   CU_TRY(cudaMemcpyAsync((char *)b->out_soft + (size_t)f0 * N * ssz, s.soft.p, ssz * N * nf, cudaMemcpyDeviceToHost, s.st));
             if (b->out_errors) CU_TRY(cudaMemcpyAsync(b->out_errors + f0, s.errs.p, 4 * (size_t)nf, cudaMemcpyDeviceToHost, s.st));
             if (b->out_flags)  CU_TRY(cudaMemcpyAsync(b->out_flags + f0, s.flags.p, (size_t)nf, cudaMemcpyDeviceToHost, s.st));
         }

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_fast_kernel(const CodeDev c, 
     const Real alpha = (Real)p.alpha, delta = (Real)p.delta;
     const bool normalized = (p.flags & LDPC_GPU_F_NORMALIZED_MS) != 0, offset = (p.flags & LDPC_GPU_F_OFFSET_MS) != 0;
     const uint32_t qflags = p.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES);
-    const bool fcond = !io.y || io.y_dtype == LDPC_GPU_DT_F32;      // fp32 instantiation: fp32 front end on fp32 samples
+    const bool fcond = !io.y || io.y_dtype != LDPC_GPU_DT_F64;      // fp32 instantiation: fp32 front end on fp32 samples
 
     CtaTotals tot; tot.clear();
 
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
     const Real alpha = (Real)p.alpha, delta = (Real)p.delta;
     const bool normalized = (p.flags & LDPC_GPU_F_NORMALIZED_MS) != 0, offset = (p.flags & LDPC_GPU_F_OFFSET_MS) != 0;
     const uint32_t qflags = p.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES);
-    const bool fcond = !io.y || io.y_dtype == LDPC_GPU_DT_F32;      // fp32 instantiation: fp32 front end on fp32 samples
+    const bool fcond = !io.y || io.y_dtype != LDPC_GPU_DT_F64;      // fp32 instantiation: fp32 front end on fp32 samples
 
     CtaTotals tot; tot.clear();
     // Co-resident CTAs start together and do identical work, so they stay in lock step: both in the

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(NT_MAX, 1) ms_tile_kernel(const CodeDev c, con
     const Real alpha = (Real)p.alpha, delta = (Real)p.delta;
     const bool normalized = (p.flags & LDPC_GPU_F_NORMALIZED_MS) != 0, offset = (p.flags & LDPC_GPU_F_OFFSET_MS) != 0;
     const uint32_t qflags = p.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES);
-    const bool fcond = !io.y || io.y_dtype == LDPC_GPU_DT_F32;
+    const bool fcond = !io.y || io.y_dtype != LDPC_GPU_DT_F64;
     const long long ntiles = (io.n_frames + FI - 1) / FI;
     CtaTotals tot; tot.clear();
 

@@ -167,3 +167,15 @@ def test_forced_hbm_state_matches_shared_memory_path(variant, monkeypatch):
     _same(a, b, soft="exact" if cfg.kind != abi.KIND_GDBF else None)
     _same(orc.decode(cfg, snr, R, y, noise, rows, cw), b,
           soft=("exact" if cfg.kind in (abi.KIND_MINSUM, abi.KIND_DDBMP) else (1e-9 if cfg.kind == abi.KIND_BP else None)))
+
+
+def test_fp16_sample_input_equals_fp32_input_of_the_same_values():
+    """LDPC_GPU_DT_F16 only changes how the samples travel: binary16 -> fp32 is exact."""
+    cfg = cases.cfg_for("decodeNormalizedMinSum", precision=abi.PREC_F32)
+    dec = capi.Decoder(capi.Code(code_path("802_3_H")), cfg)
+    y, _, _, _ = cases.make_inputs(2048, cfg, 4.0, 0.8413, 40, 9)
+    y16 = y.astype(np.float16)
+    a = dec.decode(4.0, 0.8413, y16.astype(np.float32), y_dtype=abi.DT_F32)
+    b = dec.decode(4.0, 0.8413, y16, y_dtype=abi.DT_F16)
+    assert np.array_equal(a.bits, b.bits) and np.array_equal(a.soft, b.soft) and a.counters == b.counters
+    assert b.soft.dtype == np.float32
