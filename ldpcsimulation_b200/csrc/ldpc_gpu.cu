@@ -362,6 +362,11 @@ static int pick_kernel(ldpc_gpu_decoder *d)
             d->ws_stride = f64 ? ms_tile_state_bytes<double>(v) : ms_tile_state_bytes<float>(v);
             smem = f64 ? ms_tile_smem_bytes<double>(v) : ms_tile_smem_bytes<float>(v);
         }
+        if (algo == ALGO_BP && !f64 && !d->gstate && v.sched && v.regular_dc == 32 && v.regular_dv == 6 && v.N == 2048 && v.M <= 384 &&
+            !getenv("LDPC_GPU_GENERIC_BP")) {
+            d->fn = (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 2, false, ALGO_BP>;    // O(dc) phi-domain sum-product
+            block = 384;
+        }
         if (algo == ALGO_MS && v.idx16 && !d->gstate && !getenv("LDPC_GPU_GENERIC_MS")) {
             // degree-specialised min-sum kernel where an instantiation covers the code
             const bool rc = v.regular_dc > 0, rv = v.regular_dv > 0;
@@ -476,7 +481,8 @@ extern "C" int ldpc_gpu_decoder_create(const ldpc_gpu_code *code, const ldpc_gpu
     d->device = device; d->cfg = *cfg; d->N = code->N; d->M = code->M;
     cudaDeviceGetAttribute(&d->n_sm, cudaDevAttrMultiProcessorCount, device);
     if ((rc = build_device_code(d, code)) ||
-        (cfg->kind == LDPC_GPU_KIND_MINSUM && (rc = build_schedule(d, code, cfg->precision == LDPC_GPU_PREC_F64 ? 8 : 4))) ||
+        ((cfg->kind == LDPC_GPU_KIND_MINSUM || (cfg->kind == LDPC_GPU_KIND_BP && cfg->precision == LDPC_GPU_PREC_F32)) &&
+         (rc = build_schedule(d, code, cfg->precision == LDPC_GPU_PREC_F64 ? 8 : 4))) ||
         (rc = pick_kernel(d))) { ldpc_gpu_decoder_destroy(d); return rc; }
     for (Slot &s : d->slot) {
         if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&s.k0) != cudaSuccess ||

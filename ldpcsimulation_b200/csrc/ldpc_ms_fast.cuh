@@ -218,9 +218,16 @@ LDPC_DEVINL uint32_t row_off(const uint32_t (&offp)[NW], int k)
 // HALF: a check thread keeps only the second half of its row in registers and gathers the first half
 // again in its write pass (the gathers are conflict-free, so this trades 16 extra LDS per row for 16
 // registers per thread, which is what allows a third CTA per SM).
-template <typename Real, int DC, int DV, int NFIX, int NT_MAX, int MINB, bool HALF = false>
+// ALGO = ALGO_BP (fp32 only): sum-product on the same skeleton.  The row update is done in the
+// phi domain, phi(x) = -ln tanh(x/2) = log1p(2/expm1(x)):  |c2v_k| = phi(sum_{i != k} phi(|v_i|)),
+// because in fp32 tanhf saturates to 1 and the reference's product form (src/decodeBP.cpp:353-377)
+// yields inf.  The leave-one-out sum is total - own with the total kept in fp64, which keeps full fp32
+// accuracy even when one weak message dominates the total; cost O(dc) per row instead of the
+// reference's O(dc^2).  The fp64 parity instantiation stays on mp_kernel (reference order, O(dc^2)).
+template <typename Real, int DC, int DV, int NFIX, int NT_MAX, int MINB, bool HALF = false, int ALGO = ALGO_MS>
 __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c, const DecParams p, const FrameIO io)
 {
+    static_assert(ALGO == ALGO_MS || (sizeof(Real) == 4 && !HALF), "the phi-domain sum-product row update is the fp32 path");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrameScratch *fs = reinterpret_cast<FrameScratch *>(smem_raw);
     Real *msg = reinterpret_cast<Real *>(smem_raw + 16);
@@ -277,7 +284,11 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
             for (int q = 0; q < 4; q++) {
                 const int i = 4 * b + q;
                 Real vr; bool rneg;
-                if (sizeof(Real) == 4 && fcond) {
+                if (ALGO == ALGO_BP) {                                // src/decodeBP.cpp:186-193
+                    double v = 4.0 * y4[q] / p.N0;
+                    if (fabs(v) > p.MAXLLR) v = (neg_ge(v) ? -1.0 : 1.0) * p.MAXLLR;
+                    rneg = neg_ge(v); vr = (Real)v;
+                } else if (sizeof(Real) == 4 && fcond) {
                     const float vf = condition_ms_f32((float)y4[q], p, qflags);
                     vr = (Real)vf; rneg = !(vf > 0.0f);
                 } else {
@@ -311,6 +322,37 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
             // ---- check-node phase ----------------------------------------------------------------
 #ifndef LDPC_EXPERIMENT_SKIP_CN
             for (int j = tid; j < M; j += nt) {
+                if (ALGO == ALGO_BP) {
+                    Real t[DC];                                       // phi(|v_k|) carrying the sign of v_k
+                    double tot_phi = 0.0;
+                    typename SignOps<Real>::acc_t sgb = SignOps<Real>::zero();
+#pragma unroll
+                    for (int g = 0; g < NG; g++) {
+                        const uint4 w = __ldg(&c.sched[(size_t)g * M + j]);
+                        const uint32_t off[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const Real x = *reinterpret_cast<const Real *>(msgb + off[q]);
+                            const Real ph = bp_phi<Real>(absr(x));
+                            tot_phi += (double)ph;
+                            SignOps<Real>::fold(sgb, x);
+                            t[g * 4 + q] = SignOps<Real>::apply(ph, x);
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < NG; g++) {
+                        const uint4 w = __ldg(&c.sched[(size_t)g * M + j]);
+                        const uint32_t off[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const Real own = t[g * 4 + q];
+                            const Real excl = (Real)(tot_phi - (double)absr(own));
+                            const Real mag = bp_phi<Real>(excl > (Real)0 ? excl : (Real)0);
+                            *reinterpret_cast<Real *>(msgb + off[q]) = SignOps<Real>::apply(SignOps<Real>::presign(mag, sgb), own);
+                        }
+                    }
+                    continue;
+                }
                 constexpr int KEEP0 = HALF ? DC / 2 : 0;              // steps [KEEP0, DC) stay in registers
                 Real v[DC - KEEP0];
                 Real m1 = INF, m2 = INF;
@@ -361,7 +403,11 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
 #pragma unroll
                 for (int s = 0; s < DV; s++) { cm[s] = msg[s * N + col]; sum += cm[s]; }
 #pragma unroll
-                for (int s = 0; s < DV; s++) msg[s * N + col] = sum - cm[s];
+                for (int s = 0; s < DV; s++) {
+                    Real o = sum - cm[s];
+                    if (ALGO == ALGO_BP) o = rmin(rmax(o, -(Real)p.MAXLLR), (Real)p.MAXLLR);       // src/decodeBP.cpp:399-402
+                    msg[s * N + col] = o;
+                }
                 if (last) {
                     const int i = (int)__ldg(&c.var_of_col[col]);
                     if (!(sum > 0)) atomicOr(&dbits[i >> 5], 1u << (i & 31));

@@ -102,7 +102,7 @@ def test_t_extremes_and_ragged_batches():
 
 
 @pytest.mark.parametrize("variant,code", [("decodeMinSum", "PEG"), ("decodeNormalizedMinSum", "802_3_H"),
-                                          ("decodeOffsetMinSum", "802_3_H"), ("decodeBP", "PEG")])
+                                          ("decodeOffsetMinSum", "802_3_H"), ("decodeBP", "PEG"), ("decodeBP", "802_3_H")])
 def test_f32_within_tolerance(variant, code):
     """fp32 instantiation vs the double oracle.  Tolerance: a-posteriori sums within 1e-5 of the frame's
     largest |LLR| on frames the oracle converges on (non-converging min-sum trajectories are chaotic,
