@@ -87,6 +87,24 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the decode kernel, per launch, from the committed
+    `ncu --set full` capture of this same workload (profiles/); None if the capture is absent."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r1d_ncu_raw_ms_sched_final.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(k)
+            tot += float(vals[i]) * scale.get(units[i], 1.0)
+        return tot
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -318,10 +336,15 @@ def main():
         "gpu_launches": int(launches), "e2e_gpu_launches": int(e2e_launches),
         "kernel_ms_per_step": kernel_ms / args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "frac": (achieved / peak) if achieved else None, "traffic": profiled_traffic(),
+                     "traffic_source": "profiles/r1d_ncu_raw_ms_sched_final.csv (bytes per launch of 131072 frames)",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_frame": bytes_per_frame,
-                     "note": "messages never leave the SM (shared memory), so algorithmic message bytes over kernel time can "
-                             "exceed the HBM copy peak; see DESIGN.md for the shared-memory / issue-slot view"},
+                     "note": "messages never leave the SM (shared memory): DRAM traffic is nil, so algorithmic message bytes over "
+                             "kernel time exceed the HBM copy peak; the binding resources are shared-memory wavefronts, the ALU pipe "
+                             "and issue slots (DESIGN.md section 3, profiles/r1_summary.md)"},
+        "onchip": {"edge_updates_per_s": 2.0 * E_EDGES * WORKLOAD["T"] * F * args.steps / (kernel_ms * 1e-3) if kernel_ms > 0 else None,
+                   "issue_slots_per_edge_iteration": (148 * 4 * 32 * 1.965e9) / (E_EDGES * WORKLOAD["T"] * F * args.steps / (kernel_ms * 1e-3)) if kernel_ms > 0 else None},
         "geometry": geo, "counters": total, "ber": total["errors"] / max(1, total["totalBits"]),
         "fer": total["wordErrors"] / max(1, total["totalWords"]),
         "clocks": clocks,
