@@ -192,6 +192,13 @@ int  ldpc_gpu_code_create(int N, int M, int biggest_num_n, int biggest_num_m,
 int  ldpc_gpu_code_load_alist(const char *path, ldpc_gpu_code **out);
 int  ldpc_gpu_code_dims(const ldpc_gpu_code *code, int *N, int *M, int *E, int *dv_max, int *dc_max);
 int  ldpc_gpu_code_destroy(ldpc_gpu_code *code);
+/* SURVEY.md 8(f) N1 -- codewords for codes that ship without a data.enc (the reference lists
+ * codes/802_3/data_c.enc as missing, /.MISSING_LARGE_BLOBS:1): H is brought to reduced row-echelon
+ * form over GF(2) on the host (redundant rows allowed), the non-pivot columns carry Philox-random
+ * information bits.  bits01 is HOST [n][N] bytes 0/1, the layout ldpc_gpu_decoder_set_codewords and
+ * ldpc_gpu_batch.codeword take.  *rank (optional) receives rank(H).  Dense elimination: codes with
+ * M*N above 2^28 bits return LDPC_GPU_ERR_UNSUPPORTED. */
+int  ldpc_gpu_code_random_codewords(ldpc_gpu_code *code, uint64_t seed, int64_t n, uint8_t *bits01, int *rank);
 
 /* ---- decoder ------------------------------------------------------------ */
 int  ldpc_gpu_decoder_cfg_default(int kind, ldpc_gpu_decoder_cfg *cfg);

@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("LDPC_GPU_LIB", os.path.join(HERE, "_build", "libldpc_
 EXPORTS = [
     "ldpc_gpu_version", "ldpc_gpu_last_error", "ldpc_gpu_init", "ldpc_gpu_shutdown", "ldpc_gpu_device_count",
     "ldpc_gpu_code_create", "ldpc_gpu_code_load_alist", "ldpc_gpu_code_dims", "ldpc_gpu_code_destroy",
+    "ldpc_gpu_code_random_codewords",
     "ldpc_gpu_decoder_cfg_default", "ldpc_gpu_decoder_create", "ldpc_gpu_decoder_destroy",
     "ldpc_gpu_decoder_set_codewords", "ldpc_gpu_decode_batch", "ldpc_gpu_simulate", "ldpc_gpu_channel_dump",
     "ldpc_gpu_philox4x32", "ldpc_gpu_last_timing", "ldpc_gpu_decoder_geometry",
@@ -46,6 +47,7 @@ def lib():
         L.ldpc_gpu_code_load_alist.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.ldpc_gpu_code_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5
         L.ldpc_gpu_code_destroy.argtypes = [C.c_void_p]
+        L.ldpc_gpu_code_random_codewords.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.POINTER(C.c_int)]
         L.ldpc_gpu_decoder_cfg_default.argtypes = [C.c_int, C.POINTER(abi.DecoderCfg)]
         L.ldpc_gpu_decoder_create.argtypes = [C.c_void_p, C.POINTER(abi.DecoderCfg), C.c_int, C.POINTER(C.c_void_p)]
         L.ldpc_gpu_decoder_destroy.argtypes = [C.c_void_p]
@@ -93,6 +95,14 @@ class Code:
         v = [C.c_int() for _ in range(5)]
         check(lib().ldpc_gpu_code_dims(self.h, *[C.byref(x) for x in v]))
         self.N, self.M, self.E, self.dv_max, self.dc_max = [x.value for x in v]
+
+    def random_codewords(self, seed, n):
+        """[n][N] bytes 0/1 with H c = 0 (host-side GF(2) encoder); also sets self.rank."""
+        out = np.zeros((n, self.N), np.uint8)
+        rk = C.c_int()
+        check(lib().ldpc_gpu_code_random_codewords(self.h, seed, n, _ptr(out), C.byref(rk)))
+        self.rank = rk.value
+        return out
 
     def __del__(self):
         try:

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <fstream>
 #include <memory>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -74,6 +75,13 @@ struct ldpc_gpu_code {
     std::vector<int> nlist;   // [N*dv_max] 0-based check of slot s of variable i, -1 padded
     std::vector<int> mlist;   // [M*dc_max] 0-based variable of slot k of check j, -1 padded
     std::vector<int> vn_slot; // [M*dc_max] slot of check j inside variable mlist[j][k]'s nlist row
+    // encoder state (ldpc_gpu_code_random_codewords), built on first use
+    std::mutex enc_mutex;
+    bool enc_ready = false;
+    int rank = 0;
+    std::vector<int> pivot_col;                 // [rank] pivot column of RREF row r
+    std::vector<int> info_col;                  // [N - rank] free columns
+    std::vector<std::vector<int>> parity_of;    // [rank] free-column indices (into info_col) that RREF row r sums
 };
 
 extern "C" int ldpc_gpu_code_create(int N, int M, int dvm, int dcm, const int *num_nlist, const int *num_mlist,
@@ -172,6 +180,58 @@ extern "C" int ldpc_gpu_code_load_alist(const char *path, ldpc_gpu_code **out)
         if (cnt != num_m[j]) return set_err(LDPC_GPU_ERR_BAD_CODE, "row weight does not match its entries");
     }
     return ldpc_gpu_code_create((int)N, (int)M, (int)dvm, (int)dcm, num_n.data(), num_m.data(), nl.data(), ml.data(), out);
+}
+
+// GF(2) reduced row-echelon form of H, dense bit rows.
+static int build_encoder(ldpc_gpu_code *c)
+{
+    const int N = c->N, M = c->M;
+    if ((long long)N * M > (1ll << 28)) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "encoder: dense GF(2) elimination is limited to M*N <= 2^28 bits");
+    const int W = (N + 63) / 64;
+    std::vector<uint64_t> A((size_t)M * W, 0);
+    for (int j = 0; j < M; j++) for (int k = 0; k < c->row_deg[j]; k++) { const int i = c->mlist[(size_t)j * c->dc_max + k]; A[(size_t)j * W + (i >> 6)] ^= 1ull << (i & 63); }
+    c->pivot_col.clear();
+    int r = 0;
+    for (int col = 0; col < N && r < M; col++) {
+        int piv = -1;
+        for (int j = r; j < M; j++) if (A[(size_t)j * W + (col >> 6)] >> (col & 63) & 1) { piv = j; break; }
+        if (piv < 0) continue;
+        if (piv != r) for (int w = 0; w < W; w++) std::swap(A[(size_t)piv * W + w], A[(size_t)r * W + w]);
+        for (int j = 0; j < M; j++) if (j != r && (A[(size_t)j * W + (col >> 6)] >> (col & 63) & 1))
+            for (int w = 0; w < W; w++) A[(size_t)j * W + w] ^= A[(size_t)r * W + w];
+        c->pivot_col.push_back(col); r++;
+    }
+    c->rank = r;
+    std::vector<int> free_index(N, -1);
+    c->info_col.clear();
+    { size_t pi = 0; for (int col = 0; col < N; col++) { if (pi < c->pivot_col.size() && c->pivot_col[pi] == col) { pi++; continue; } free_index[col] = (int)c->info_col.size(); c->info_col.push_back(col); } }
+    c->parity_of.assign(r, std::vector<int>());
+    for (int q = 0; q < r; q++) for (int col = 0; col < N; col++) if (free_index[col] >= 0 && (A[(size_t)q * W + (col >> 6)] >> (col & 63) & 1)) c->parity_of[q].push_back(free_index[col]);
+    c->enc_ready = true;
+    return LDPC_GPU_OK;
+}
+
+extern "C" int ldpc_gpu_code_random_codewords(ldpc_gpu_code *c, uint64_t seed, int64_t n, uint8_t *bits01, int *rank)
+{
+    if (!c || (n > 0 && !bits01) || n < 0) return set_err(LDPC_GPU_ERR_INVALID_ARG, "bad argument");
+    {
+        std::lock_guard<std::mutex> lock(c->enc_mutex);
+        if (!c->enc_ready) { int rc = build_encoder(c); if (rc) return rc; }
+    }
+    if (rank) *rank = c->rank;
+    const int N = c->N, K = (int)c->info_col.size();
+    std::vector<uint8_t> u(K);
+    for (int64_t f = 0; f < n; f++) {
+        uint8_t *cw = bits01 + (size_t)f * N;
+        for (int b = 0; b * 128 < K; b++) {                        // 128 information bits per Philox block
+            uint32_t r4[4];
+            philox4x32_10((uint32_t)b, 3u, (uint32_t)f, (uint32_t)((uint64_t)f >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), r4);
+            for (int q = 0; q < 128 && b * 128 + q < K; q++) u[b * 128 + q] = (uint8_t)((r4[q >> 5] >> (q & 31)) & 1u);
+        }
+        for (int k = 0; k < K; k++) cw[c->info_col[k]] = u[k];
+        for (int q = 0; q < c->rank; q++) { uint8_t pbit = 0; for (int k : c->parity_of[q]) pbit ^= u[k]; cw[c->pivot_col[q]] = pbit; }
+    }
+    return LDPC_GPU_OK;
 }
 
 extern "C" int ldpc_gpu_code_dims(const ldpc_gpu_code *c, int *N, int *M, int *E, int *dv, int *dc)

@@ -22,6 +22,7 @@
 //   LDPC_DEVICES    comma list of CUDA ordinals; frames are sharded by frame-id range, one host
 //                   thread per GPU (default "0")
 //   LDPC_POLL       frames per launch between stop-rule polls
+//   LDPC_RANDOM_CODEWORDS=n   when no codeword file is given: send n random codewords of H (host GF(2) encoder)
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -207,6 +208,13 @@ int main(int argc, char *argv[])
     if (argc == (int)args.size() + 1) {
         cout << "\nUsing codewords from " << argv[idx] << endl;
         if (!load_codewords(argv[idx], N, cw, n_cw)) { cerr << "cannot read codewords from " << argv[idx] << endl; return 1; }
+    } else if (const char *rc = getenv("LDPC_RANDOM_CODEWORDS")) {
+        // no codeword file for this code (e.g. codes/802_3/data_c.enc is missing upstream): encode random ones
+        n_cw = atol(rc) > 0 ? atol(rc) : 500;
+        cw.resize((size_t)n_cw * N);
+        int rank = 0;
+        if (ldpc_gpu_code_random_codewords(code, 20261018ull, n_cw, cw.data(), &rank)) { cerr << "encoder: " << ldpc_gpu_last_error() << endl; return 1; }
+        cout << "\nUsing " << n_cw << " random codewords (rank(H) = " << rank << ").\n";
     } else cout << "\nUsing all-zero sequence.\n";
 
     const double N0 = pow(10.0, -SNR / 10.0) / R;
