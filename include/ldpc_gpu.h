@@ -77,6 +77,9 @@ extern "C" {
 /* ---- arithmetic of the message / metric path --------------------------- */
 #define LDPC_GPU_PREC_F64   0   /* parity instantiation: IEEE double, the reference's operation order */
 #define LDPC_GPU_PREC_F32   1   /* throughput instantiation: fp32 messages, same dataflow */
+#define LDPC_GPU_PREC_F16X2 2   /* min-sum family on regular scheduled codes only: two frames per thread in one
+                                   binary16 pair, v2c clamped to +-512.  NOT the reference's arithmetic: decisions
+                                   match on converging frames, BER/FER within confidence intervals */
 
 /* ---- where a caller buffer lives --------------------------------------- */
 #define LDPC_GPU_MEM_HOST    0

@@ -31,7 +31,7 @@ MACRO_FLAGS = {
     "noiseShaping": F_NOISESHAPING, "quantizeProbabilities": F_QUANTIZEPROBABILITIES, "redecode": F_REDECODE,
 }
 
-PREC_F64, PREC_F32 = 0, 1
+PREC_F64, PREC_F32, PREC_F16X2 = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 DT_F64, DT_F32, DT_F16 = 0, 1, 2
 HW_QBUF = 2648

@@ -23,6 +23,7 @@
 #include "ldpc_ms_fast.cuh"
 #include "ldpc_schedule.h"
 #include "ldpc_ms_tile.cuh"
+#include "ldpc_ms_h2.cuh"
 #include "ldpc_bf_kernels.cuh"
 
 using namespace ldpc;
@@ -396,6 +397,14 @@ static int pick_kernel(ldpc_gpu_decoder *d)
     if (kind == LDPC_GPU_KIND_MINSUM || kind == LDPC_GPU_KIND_BP || kind == LDPC_GPU_KIND_DDBMP) {
         if (v.dc_max > 64) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "message-passing kernels hold a row's signs in 64 bits: dc_max > 64");
         const int algo = kind == LDPC_GPU_KIND_MINSUM ? ALGO_MS : kind == LDPC_GPU_KIND_BP ? ALGO_BP : ALGO_DDBMP;
+        if (d->cfg.precision == LDPC_GPU_PREC_F16X2) {
+            if (!(v.sched && v.regular_dc == 32 && v.regular_dv == 6 && v.N == 2048 && v.M <= 384))
+                return set_err(LDPC_GPU_ERR_UNSUPPORTED, "LDPC_GPU_PREC_F16X2 is built for regular (6,32) codes of length 2048 with a conflict-free schedule (the 802.3an H)");
+            d->fn = (KernelFn)ms_h2_kernel<32, 6, 2048, 384, 2>;
+            d->frames_per_cta = 2;
+            smem = ms_h2_smem_bytes(v); block = 384;
+            goto geometry;
+        }
         smem = f64 ? mp_smem_bytes<double>(v, algo) : mp_smem_bytes<float>(v, algo);
         if (smem > (size_t)max_optin || getenv("LDPC_GPU_FORCE_HBM_STATE")) {
             d->gstate = true;
@@ -470,6 +479,7 @@ static int pick_kernel(ldpc_gpu_decoder *d)
         smem = hw_smem_bytes(v);
         block = std::min(1024, std::max(128, round32(std::max(v.M, v.N / 2))));
     } else return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown decoder kind");
+geometry:
     if (smem > (size_t)max_optin)
         return set_err(LDPC_GPU_ERR_UNSUPPORTED, "shared-memory scratch (" + std::to_string(smem) + " B) exceeds one SM");
     CU_TRY(cudaFuncSetAttribute((const void *)d->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -494,7 +504,10 @@ static int pick_kernel(ldpc_gpu_decoder *d)
 static int validate_cfg(const ldpc_gpu_decoder_cfg &c)
 {
     if (c.num_iterations < 0) return set_err(LDPC_GPU_ERR_INVALID_ARG, "num_iterations < 0");
-    if (c.precision != LDPC_GPU_PREC_F64 && c.precision != LDPC_GPU_PREC_F32) return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown precision");
+    if (c.precision != LDPC_GPU_PREC_F64 && c.precision != LDPC_GPU_PREC_F32 && c.precision != LDPC_GPU_PREC_F16X2)
+        return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown precision");
+    if (c.precision == LDPC_GPU_PREC_F16X2 && c.kind != LDPC_GPU_KIND_MINSUM)
+        return set_err(LDPC_GPU_ERR_UNSUPPORTED, "LDPC_GPU_PREC_F16X2 exists for the min-sum family only");
     if (c.kind == LDPC_GPU_KIND_GDBF) {
         if ((c.flags & LDPC_GPU_F_REDECODE) && (c.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_QUANTIZEPROBABILITIES)))
             return set_err(LDPC_GPU_ERR_UNSUPPORTED, "RNGDBF.cpp has no quantizeSamples / quantizeProbabilities code");
@@ -541,7 +554,7 @@ extern "C" int ldpc_gpu_decoder_create(const ldpc_gpu_code *code, const ldpc_gpu
     d->device = device; d->cfg = *cfg; d->N = code->N; d->M = code->M;
     cudaDeviceGetAttribute(&d->n_sm, cudaDevAttrMultiProcessorCount, device);
     if ((rc = build_device_code(d, code)) ||
-        ((cfg->kind == LDPC_GPU_KIND_MINSUM || (cfg->kind == LDPC_GPU_KIND_BP && cfg->precision == LDPC_GPU_PREC_F32)) &&
+        ((cfg->kind == LDPC_GPU_KIND_MINSUM || (cfg->kind == LDPC_GPU_KIND_BP && cfg->precision != LDPC_GPU_PREC_F64)) &&
          (rc = build_schedule(d, code, cfg->precision == LDPC_GPU_PREC_F64 ? 8 : 4))) ||
         (rc = pick_kernel(d))) { ldpc_gpu_decoder_destroy(d); return rc; }
     for (Slot &s : d->slot) {

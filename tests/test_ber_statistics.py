@@ -48,3 +48,17 @@ def test_fp32_fer_inside_fp64_confidence_interval(variant, code, snr, F):
     ref = capi.Decoder(code_h, cases.cfg_for(variant, code=code, num_iterations=10)).simulate(snr, R, 2026, 0, 20000).counters
     assert abs(same["uncodedErrors"] - ref["uncodedErrors"]) <= 2
     assert abs(same["wordErrors"] - ref["wordErrors"]) <= max(3, 0.05 * ref["wordErrors"])
+
+
+def test_f16x2_fer_inside_fp64_confidence_interval():
+    F = 400000
+    code_h = capi.Code(code_path("802_3_H"))
+    R = 0.8413
+    r64 = capi.Decoder(code_h, cases.cfg_for("decodeNormalizedMinSum", code="802_3_H", num_iterations=10)).simulate(3.6, R, 2026, 0, F).counters
+    rh = capi.Decoder(code_h, cases.cfg_for("decodeNormalizedMinSum", code="802_3_H", num_iterations=10,
+                                              precision=abi.PREC_F16X2)).simulate(3.6, R, 2026, F, F + 1).counters
+    lo, hi = _wilson(r64["wordErrors"], F)
+    mid, half = (lo + hi) / 2, (hi - lo) / 2 * math.sqrt(2)
+    assert rh["totalWords"] == F + 1
+    assert mid - half <= rh["wordErrors"] / (F + 1) <= mid + half, (r64, rh)
+    assert abs(rh["errors"] / rh["totalBits"] - r64["errors"] / r64["totalBits"]) <= 0.15 * r64["errors"] / r64["totalBits"]

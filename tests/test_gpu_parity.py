@@ -179,3 +179,38 @@ def test_fp16_sample_input_equals_fp32_input_of_the_same_values():
     b = dec.decode(4.0, 0.8413, y16, y_dtype=abi.DT_F16)
     assert np.array_equal(a.bits, b.bits) and np.array_equal(a.soft, b.soft) and a.counters == b.counters
     assert b.soft.dtype == np.float32
+
+
+@pytest.mark.parametrize("variant", ["decodeNormalizedMinSum", "decodeOffsetMinSum", "decodeMinSum"])
+def test_f16x2_decisions_on_converged_frames(variant):
+    """LDPC_GPU_PREC_F16X2 (two frames per thread, binary16 messages, clamped) is a labelled throughput
+    instantiation, not the reference's arithmetic.  What it must keep: the decisions of the double oracle
+    on frames that converge, for even and odd frame counts, with and without codewords."""
+    R, snr = 0.8413, 4.6
+    cfg64 = cases.cfg_for(variant, code="802_3_H", num_iterations=10)
+    cfgh = cases.cfg_for(variant, code="802_3_H", num_iterations=10, precision=abi.PREC_F16X2)
+    orc = Oracle("802_3_H")
+    code = capi.Code(code_path("802_3_H"))
+    dec = capi.Decoder(code, cfgh)
+    assert dec.geometry()["ctas_per_sm"] >= 2
+    cws = code.random_codewords(1, 8)
+    for F, use_cw in ((64, False), (33, True)):
+        y, noise, rows, cw = cases.make_inputs(orc.N, cfg64, snr, R, F, 99 + F, cws if use_cw else None)
+        a = orc.decode(cfg64, snr, R, y, codeword=cw)
+        b = dec.decode(snr, R, y, codeword=cw)
+        conv = a.errors == 0
+        assert conv.sum() >= 0.5 * F
+        assert np.array_equal(a.bits[conv], b.bits[conv])
+        assert np.array_equal(a.iters, b.iters)
+        assert b.counters["totalWords"] == F and b.counters["uncodedErrors"] == a.counters["uncodedErrors"]
+        rel = np.abs(np.sign(a.soft[conv]) - np.sign(b.soft[conv])).max()
+        assert rel == 0
+
+
+def test_f16x2_refuses_other_codes_and_decoders():
+    with pytest.raises(capi.LdpcGpuError) as e:
+        capi.Decoder(capi.Code(code_path("PEG")), cases.cfg_for("decodeMinSum", precision=abi.PREC_F16X2))
+    assert e.value.code == abi.ERR_UNSUPPORTED
+    with pytest.raises(capi.LdpcGpuError) as e:
+        capi.Decoder(capi.Code(code_path("802_3_H")), cases.cfg_for("decodeBP", precision=abi.PREC_F16X2))
+    assert e.value.code == abi.ERR_UNSUPPORTED

@@ -9,7 +9,7 @@ sys.path.insert(0, ROOT)
 from ldpcsimulation_b200 import abi, capi  # noqa: E402
 
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18
-prec = abi.PREC_F64 if (len(sys.argv) > 2 and sys.argv[2] == "f64") else abi.PREC_F32
+prec = {"f64": abi.PREC_F64, "f32": abi.PREC_F32, "f16x2": abi.PREC_F16X2}[sys.argv[2] if len(sys.argv) > 2 else "f32"]
 code = capi.Code(os.path.join(ROOT, "codes", "802_3", "802_3_H.alist"))
 for T in (0, 1, 2, 10, 20):
     cfg = abi.default_cfg(abi.KIND_MINSUM, flags=["quantizeSamples", "normalizedMS"], num_iterations=T, precision=prec,
