@@ -434,7 +434,7 @@ static int pick_kernel(ldpc_gpu_decoder *d)
         if (algo == ALGO_BP && !f64 && !d->gstate && v.sched && v.regular_dc == 32 && v.regular_dv == 6 && v.N == 2048 && v.M <= 384 &&
             !getenv("LDPC_GPU_GENERIC_BP")) {
             d->fn = (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 2, false, ALGO_BP>;    // O(dc) phi-domain sum-product
-            block = 384;
+            block = 384; smem = ms_sched_smem_bytes<float>(v);
         }
         if (algo == ALGO_MS && v.idx16 && !d->gstate && !getenv("LDPC_GPU_GENERIC_MS")) {
             // degree-specialised min-sum kernel where an instantiation covers the code
@@ -443,6 +443,8 @@ static int pick_kernel(ldpc_gpu_decoder *d)
 #define MS_FAST(DC, DV, RC, RV) (f64 ? (KernelFn)ms_fast_kernel<double, DC, DV, RC, RV, 1024, 1> : (KernelFn)ms_fast_kernel<float, DC, DV, RC, RV, 1024, 1>)
             const char *mb = getenv("LDPC_GPU_MINB");
             if (v.sched && v.regular_dc == 32 && v.regular_dv == 6 && v.N == 2048 && v.M <= 384)   // the 802.3an H, scheduled
+                smem = f64 ? ms_sched_smem_bytes<double>(v) : ms_sched_smem_bytes<float>(v);
+            if (v.sched && v.regular_dc == 32 && v.regular_dv == 6 && v.N == 2048 && v.M <= 384)
                 fast = f64 ? (KernelFn)ms_sched_kernel<double, 32, 6, 2048, 384, 1>
                            : ((mb && atoi(mb) == 13) ? (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 3, true>
                               : (mb && atoi(mb) == 12) ? (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 2, true>
@@ -473,11 +475,14 @@ static int pick_kernel(ldpc_gpu_decoder *d)
         d->fn = d->gstate ? (f64 ? (KernelFn)gdbf_kernel<double, true> : (KernelFn)gdbf_kernel<float, true>)
                           : (f64 ? (KernelFn)gdbf_kernel<double, false> : (KernelFn)gdbf_kernel<float, false>);
         block = std::min(1024, std::max(128, round32(std::max(v.M, (v.N + 3) / 4))));
+        if (v.M <= 512 && v.N <= 4096) block = 256;                           // measured on the 802.3an H: 256 > 384 > 512
+        if (const char *gb = getenv("LDPC_GPU_GDBF_BLOCK")) block = std::max(64, atoi(gb) & ~31);
     } else if (kind == LDPC_GPU_KIND_NGDBF_HW) {
         if (v.N >= LDPC_GPU_HW_QBUF) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "NGDBFhw's 2648-entry noise window needs N < 2648 (src/NGDBFhw.cpp:151)");
         d->fn = (KernelFn)hw_kernel;
         smem = hw_smem_bytes(v);
-        block = std::min(1024, std::max(128, round32(std::max(v.M, v.N / 2))));
+        block = std::min(1024, std::max(128, round32(v.M)));                // measured: one check per thread, 3 CTAs/SM
+        if (const char *hb = getenv("LDPC_GPU_HW_BLOCK")) block = std::max(64, atoi(hb) & ~31);
     } else return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown decoder kind");
 geometry:
     if (smem > (size_t)max_optin)

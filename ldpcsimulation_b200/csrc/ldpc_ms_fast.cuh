@@ -51,6 +51,10 @@ template <> LDPC_DEVINL double rmax<double>(double a, double b) { return fmax(a,
 
 // DC / DV: compile-time bounds of the row / column weight.  REGC / REGV: every row / column has
 // exactly that weight (no per-slot predicate).
+template <typename Real> struct Vec2;
+template <> struct Vec2<float> { typedef float2 type; };
+template <> struct Vec2<double> { typedef double2 type; };
+
 // NT_MAX / MINB: launch bounds (threads per CTA, CTAs per SM the register allocation must allow).
 template <typename Real, int DC, int DV, bool REGC, bool REGV, int NT_MAX, int MINB>
 __global__ void __launch_bounds__(NT_MAX, MINB) ms_fast_kernel(const CodeDev c, const DecParams p, const FrameIO io)
@@ -268,53 +272,85 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
     }
 #endif
 
+    // ---- channel front end, software-pipelined across frames ----------------------------------------
+    // gen(fx, b) produces the four conditioned samples of block b of frame fx into the staging buffer
+    // ybuf (storage-column order), the raw hard decisions into rnext and the uncodedErrors increments
+    // into *unc_next.  The first frame of a CTA is generated up front by all threads; every later frame
+    // is generated WHILE the previous one iterates, by the threads that have no column left in the last
+    // round of the variable phase (N = 2048 columns over 384 threads: 256 threads idle at the barrier),
+    // so the Philox / Box-Muller / quantiser work (11 % of the kernel's instructions, profiles/
+    // r1_summary.md) disappears from the critical path.
+    Real *ybuf = reinterpret_cast<Real *>(dbits + nwords);
+    uint32_t *rnext = reinterpret_cast<uint32_t *>(ybuf + N);
+    int *unc_next = reinterpret_cast<int *>(rnext + nwords);
+    auto gen = [&](long long fx, const uint8_t *cwx, int b) {
+        double y4[4];
+        raw_samples4(io, p, c, fx, cwx, b, y4);
+        const uint2 cc = __ldg(reinterpret_cast<const uint2 *>(c.col_of_var) + b);      // four uint16 columns
+        uint32_t nib = 0; int unc = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = 4 * b + q;
+            Real vr; bool rneg;
+            if (ALGO == ALGO_BP) {                                // src/decodeBP.cpp:186-193
+                double v = 4.0 * y4[q] / p.N0;
+                if (fabs(v) > p.MAXLLR) v = (neg_ge(v) ? -1.0 : 1.0) * p.MAXLLR;
+                rneg = neg_ge(v); vr = (Real)v;
+            } else if (sizeof(Real) == 4 && fcond) {
+                const float vf = condition_ms_f32((float)y4[q], p, qflags);
+                vr = (Real)vf; rneg = !(vf > 0.0f);
+            } else {                                              // src/decodeMinSum.cpp:214-238
+                double v = y4[q];
+                if (qflags & LDPC_GPU_F_QUANTIZE_SAMPLES) v = quantize_ms(v, p);
+                if (qflags & LDPC_GPU_F_SATURATE_SAMPLES) { if (v > p.Ymax) v = p.Ymax; if (v < -p.Ymax) v = -p.Ymax; }
+                rneg = !(v > 0);
+                vr = (Real)v;
+            }
+            const int col = (int)(((q < 2 ? cc.x : cc.y) >> (16 * (q & 1))) & 0xffffu);
+            ybuf[col] = vr;
+            unc += (int)(rneg != ((cwx ? cwx[i] : 0) != 0));
+            nib |= (uint32_t)rneg << q;
+        }
+        if (nib) atomicOr(&rnext[(4 * b) >> 5], nib << ((4 * b) & 31));
+        if (unc) atomicAdd(unc_next, unc);
+    };
+    const int vn_rem = (N / 2) % nt;                              // threads >= vn_rem idle in the last variable round
+    const int gen_threads = vn_rem ? nt - vn_rem : nt;
+    const int gen_id = vn_rem ? tid - vn_rem : tid;
+
+    if ((long long)blockIdx.x < io.n_frames) {                        // the CTA's first frame
+        for (int w = tid; w < nwords; w += nt) rnext[w] = 0u;
+        if (tid == 0) *unc_next = 0;
+        __syncthreads();
+        const uint8_t *cw0 = codeword_row(io, c, blockIdx.x);
+        for (int b = tid; b < nblk; b += nt) gen(blockIdx.x, cw0, b);
+        __syncthreads();
+    }
+
     for (long long f = blockIdx.x; f < io.n_frames; f += gridDim.x) {
         const uint8_t *cw = codeword_row(io, c, f);
-        if (tid == 0) { fs->uncoded = 0; fs->errors = 0; fs->flag = 0; }
-        for (int w = tid; w < nwords; w += nt) dbits[w] = 0u;
-        __syncthreads();
-
-        int unc = 0;
-        for (int b = tid; b < nblk; b += nt) {
-            double y4[4];
-            raw_samples4(io, p, c, f, cw, b, y4);
-            const uint2 cc = __ldg(reinterpret_cast<const uint2 *>(c.col_of_var) + b);      // four uint16 columns
-            uint32_t nib = 0;
+        // install the staged frame: messages start as the channel value (initializeSymMessages, :364-370)
+        if (tid == 0) { fs->uncoded = *unc_next; fs->errors = 0; fs->flag = 0; }
+        for (int w = tid; w < nwords; w += nt) dbits[w] = rnext[w];
+        for (int col = tid; col < N; col += nt) {
+            const Real vr = ybuf[col];
+            yq[col] = vr;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int i = 4 * b + q;
-                Real vr; bool rneg;
-                if (ALGO == ALGO_BP) {                                // src/decodeBP.cpp:186-193
-                    double v = 4.0 * y4[q] / p.N0;
-                    if (fabs(v) > p.MAXLLR) v = (neg_ge(v) ? -1.0 : 1.0) * p.MAXLLR;
-                    rneg = neg_ge(v); vr = (Real)v;
-                } else if (sizeof(Real) == 4 && fcond) {
-                    const float vf = condition_ms_f32((float)y4[q], p, qflags);
-                    vr = (Real)vf; rneg = !(vf > 0.0f);
-                } else {
-                    double v = y4[q];
-                    if (qflags & LDPC_GPU_F_QUANTIZE_SAMPLES) v = quantize_ms(v, p);
-                    if (qflags & LDPC_GPU_F_SATURATE_SAMPLES) { if (v > p.Ymax) v = p.Ymax; if (v < -p.Ymax) v = -p.Ymax; }
-                    rneg = !(v > 0);
-                    vr = (Real)v;
-                }
-                const int col = (int)(((q < 2 ? cc.x : cc.y) >> (16 * (q & 1))) & 0xffffu);
-                yq[col] = vr;
-                const int cb = cw ? cw[i] : 0;
-                unc += (int)(rneg != (cb != 0));
-                nib |= (uint32_t)rneg << q;
-#pragma unroll
-                for (int s = 0; s < DV; s++) msg[s * N + col] = vr;
-                if (io.out_soft && p.T == 0) {
-                    if (io.y_dtype == LDPC_GPU_DT_F64) ((double *)io.out_soft)[(size_t)f * N + i] = (double)vr;
-                    else ((float *)io.out_soft)[(size_t)f * N + i] = (float)vr;
-                }
+            for (int s = 0; s < DV; s++) msg[s * N + col] = vr;
+            if (io.out_soft && p.T == 0) {
+                const int i = (int)__ldg(&c.var_of_col[col]);
+                if (io.y_dtype == LDPC_GPU_DT_F64) ((double *)io.out_soft)[(size_t)f * N + i] = (double)vr;
+                else ((float *)io.out_soft)[(size_t)f * N + i] = (float)vr;
             }
-            if (nib) atomicOr(&dbits[(4 * b) >> 5], nib << ((4 * b) & 31));
         }
-        for (int o = 16; o; o >>= 1) unc += __shfl_xor_sync(0xffffffffu, unc, o);
-        if (lane == 0 && unc) atomicAdd(&fs->uncoded, unc);
         __syncthreads();
+        for (int w = tid; w < nwords; w += nt) rnext[w] = 0u;
+        if (tid == 0) *unc_next = 0;
+        const long long fnext = f + gridDim.x;
+        const bool have_next = fnext < io.n_frames;
+        const uint8_t *cwn = have_next ? codeword_row(io, c, fnext) : nullptr;
+        int gen_done = 0;                                             // blocks of the next frame staged so far (uniform)
+        if (p.T == 0) __syncthreads();
 
         for (int it = 0; it < p.T; it++) {
             const bool last = (it == p.T - 1);
@@ -396,33 +432,57 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
 #endif
             __syncthreads();
             // ---- variable-node phase (storage columns) --------------------------------------------
+            // Two adjacent columns per thread, moved as 8/16-byte vectors: same bytes and layout, half the
+            // LDS/STS instructions.  The kernel is bound by the SM-wide issue rate of memory instructions
+            // (profiles/r1_summary.md), not by shared-memory bytes.
 #ifndef LDPC_EXPERIMENT_SKIP_VN
-            for (int col = tid; col < N; col += nt) {
-                Real cm[DV];
-                Real sum = yq[col];
+            for (int cp = tid; cp < N / 2; cp += nt) {
+                typedef typename Vec2<Real>::type V2;
+                const int col = 2 * cp;
+                V2 cm[DV];
+                V2 sum = *reinterpret_cast<const V2 *>(&yq[col]);
 #pragma unroll
-                for (int s = 0; s < DV; s++) { cm[s] = msg[s * N + col]; sum += cm[s]; }
+                for (int s = 0; s < DV; s++) { cm[s] = *reinterpret_cast<const V2 *>(&msg[s * N + col]); sum.x += cm[s].x; sum.y += cm[s].y; }
 #pragma unroll
                 for (int s = 0; s < DV; s++) {
-                    Real o = sum - cm[s];
-                    if (ALGO == ALGO_BP) o = rmin(rmax(o, -(Real)p.MAXLLR), (Real)p.MAXLLR);       // src/decodeBP.cpp:399-402
-                    msg[s * N + col] = o;
+                    V2 o; o.x = sum.x - cm[s].x; o.y = sum.y - cm[s].y;
+                    if (ALGO == ALGO_BP) {                            // src/decodeBP.cpp:399-402
+                        o.x = rmin(rmax(o.x, -(Real)p.MAXLLR), (Real)p.MAXLLR); o.y = rmin(rmax(o.y, -(Real)p.MAXLLR), (Real)p.MAXLLR);
+                    }
+                    *reinterpret_cast<V2 *>(&msg[s * N + col]) = o;
                 }
                 if (last) {
-                    const int i = (int)__ldg(&c.var_of_col[col]);
-                    if (!(sum > 0)) atomicOr(&dbits[i >> 5], 1u << (i & 31));
+                    const unsigned vv = __ldg(reinterpret_cast<const unsigned *>(c.var_of_col) + cp);   // two uint16 variable ids
+                    const int i0 = (int)(vv & 0xffffu), i1 = (int)(vv >> 16);
+                    if (!(sum.x > 0)) atomicOr(&dbits[i0 >> 5], 1u << (i0 & 31));
+                    if (!(sum.y > 0)) atomicOr(&dbits[i1 >> 5], 1u << (i1 & 31));
                     if (io.out_soft) {
-                        if (io.y_dtype == LDPC_GPU_DT_F64) ((double *)io.out_soft)[(size_t)f * N + i] = (double)sum;
-                        else ((float *)io.out_soft)[(size_t)f * N + i] = (float)sum;
+                        if (io.y_dtype == LDPC_GPU_DT_F64) { ((double *)io.out_soft)[(size_t)f * N + i0] = (double)sum.x; ((double *)io.out_soft)[(size_t)f * N + i1] = (double)sum.y; }
+                        else { ((float *)io.out_soft)[(size_t)f * N + i0] = (float)sum.x; ((float *)io.out_soft)[(size_t)f * N + i1] = (float)sum.y; }
                     }
                 }
             }
 #endif
+            if (have_next && gen_done < nblk) {                       // idle threads stage the next frame
+                if (gen_id >= 0 && gen_done + gen_id < nblk) gen(fnext, cwn, gen_done + gen_id);
+                gen_done += gen_threads;
+            }
             __syncthreads();
         }
         finish_frame(c, p, io, f, cw, dbits, fs, p.T, /*satisfied: evaluated on demand*/ -1, 0, 0, 1, -1, tot);
+        if (have_next) for (int b = gen_done + tid; b < nblk; b += nt) gen(fnext, cwn, b);      // what T iterations did not cover
+        __syncthreads();
     }
     if (tid == 0) tot.flush(io.counters);
+}
+
+// Dynamic shared memory of ms_sched_kernel: scratch, messages, channel values, decisions, and the
+// staging buffer / raw decisions / uncoded count of the next frame.
+template <typename Real>
+static inline size_t ms_sched_smem_bytes(const CodeDev &c)
+{
+    const size_t nwords = (size_t)(c.N + 31) / 32;
+    return (16 + sizeof(Real) * ((size_t)c.dvN + 2 * (size_t)c.N) + 8 * nwords + 16 + 15) & ~(size_t)15;
 }
 
 } // namespace ldpc
