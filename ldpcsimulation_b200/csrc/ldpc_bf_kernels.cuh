@@ -256,41 +256,55 @@ __global__ void gdbf_kernel(const CodeDev c, const DecParams p, const FrameIO io
 // ---------------------------------------------------------------------------------------------
 // NGDBFhw: src/NGDBFhw.cpp.  All-integer flip metric on 5-bit sign-magnitude samples; the 2648-entry
 // per-frame noise buffer is read through a window that slides by one entry per iteration.
+//
+// Bit-packed state: decisions d (1 bit per variable, one word per warp of variables) and syndromes s
+// (1 bit per check, M/32 words).  The reference recomputes every syndrome from d at the top of each
+// iteration (checkNodeUpdates, :546-563); the syndrome is linear in d over GF(2), so here it is computed
+// in full once per phase and then UPDATED: a variable that flips toggles the syndromes of its checks
+// (atomicXor into a toggle mask that is folded in between iterations).  Same values, a few hundred
+// toggles instead of E gathers per iteration.  The flip metric reads the syndromes of the iteration's
+// start, as the reference does (its symNodeUpdates only reads `syndrome`, :565-593).
+// Samples and noise are unpacked to their odd-integer values (+-(2k+1), unpack() :665-677) once per frame.
 // ---------------------------------------------------------------------------------------------
 static inline size_t hw_smem_bytes(const CodeDev &c)
 {
-    size_t n = 16 + (size_t)c.N * 3 + LDPC_GPU_HW_QBUF + (size_t)c.M + 16;
-    n = (n + 15) & ~(size_t)15;
-    n += 4 * (size_t)((c.N + 31) / 32) + 16;
+    const size_t nwords = (size_t)(c.N + 31) / 32, mwords = (size_t)(c.M + 31) / 32;
+    size_t n = 16 + 4 * (3 * nwords + 2 * mwords) + 2 * (size_t)c.dv_max * c.N + (size_t)c.N + LDPC_GPU_HW_QBUF + 64;
     return (n + 15) & ~(size_t)15;
 }
 
 __global__ void hw_kernel(const CodeDev c, const DecParams p, const FrameIO io)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = c.N, M = c.M, nwords = (N + 31) >> 5, mwords = (M + 31) >> 5, npad = nwords << 5, nblk = (N + 3) >> 2;
+    const int T = p.T, QB = LDPC_GPU_HW_QBUF, dvm = c.dv_max;
     FrameScratch *fs = reinterpret_cast<FrameScratch *>(smem_raw);
-    unsigned char *yprime = smem_raw + 16;                // 5-bit codes
-    signed char *d = reinterpret_cast<signed char *>(yprime + c.N);     // stored as +-1 (d01 = (1-d)/2)
-    signed char *r = d + c.N;
-    unsigned char *qprime = reinterpret_cast<unsigned char *>(r + c.N);
-    unsigned char *syn = qprime + LDPC_GPU_HW_QBUF;       // 0/1
-    size_t off = (size_t)(syn + c.M - smem_raw); off = (off + 15) & ~(size_t)15;
-    uint32_t *dbits = reinterpret_cast<uint32_t *>(smem_raw + off);
-
+    uint32_t *dbits = reinterpret_cast<uint32_t *>(smem_raw + 16);      // current decisions, 1 <-> d = 1
+    uint32_t *rbits = dbits + nwords;                                   // received hard decisions
+    uint32_t *cbits = rbits + nwords;                                   // codeword bits
+    uint32_t *syn = cbits + nwords;                                     // syndrome bits, 1 <-> unsatisfied
+    uint32_t *tog = syn + mwords;                                       // toggles of the running iteration
+    uint16_t *chk = reinterpret_cast<uint16_t *>(tog + mwords);         // [dv_max][N] check of slot s of variable i
+    signed char *yval = reinterpret_cast<signed char *>(chk + (size_t)dvm * N);   // unpack(y')   in [-31, 31], odd
+    signed char *qval = yval + N;                                       // unpack(q')
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-    const int N = c.N, M = c.M, nblk = (N + 3) >> 2, T = p.T, QB = LDPC_GPU_HW_QBUF;
     const int maxPhases = p.maxphase > 0 ? p.maxphase : 1;
     CtaTotals tot; tot.clear();
+
+    for (int e = tid; e < dvm * N; e += nt) chk[e] = (uint16_t)c.vn_chk[e];      // once per CTA: the graph, variable side
+    __syncthreads();
 
     for (long long f = blockIdx.x; f < io.n_frames; f += gridDim.x) {
         const uint8_t *cw = codeword_row(io, c, f);
         const unsigned long long fid = (unsigned long long)(io.frame_begin + f);
         if (tid == 0) { fs->uncoded = 0; fs->errors = 0; fs->flag = 0; }
+        for (int w = tid; w < nwords; w += nt) { rbits[w] = 0u; cbits[w] = 0u; }
         __syncthreads();
         int unc = 0;
         for (int b = tid; b < nblk; b += nt) {                        // :218-237
             double y4[4];
             raw_samples4(io, p, c, f, cw, b, y4);
+            uint32_t rn = 0, cn = 0;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int i = 4 * b + q;
@@ -300,9 +314,11 @@ __global__ void hw_kernel(const CodeDev c, const DecParams p, const FrameIO io)
                 const bool rneg = !(v > 0);
                 const int cb = cw ? cw[i] : 0;
                 unc += (int)(rneg && cb);                             // r*c < 0 with c in {0,1} (:141,230)
-                r[i] = rneg ? -1 : 1;
-                yprime[i] = (unsigned char)hw_pack(v / p.hw_two_w, p);
+                rn |= (uint32_t)rneg << q; cn |= (uint32_t)(cb != 0) << q;
+                yval[i] = (signed char)hw_unpack(hw_pack(v / p.hw_two_w, p));
             }
+            if (rn) atomicOr(&rbits[(4 * b) >> 5], rn << ((4 * b) & 31));
+            if (cn) atomicOr(&cbits[(4 * b) >> 5], cn << ((4 * b) & 31));
         }
         for (int b = tid; b < (QB + 3) / 4; b += nt) {                // :239-252
             double n4[4];
@@ -319,7 +335,7 @@ __global__ void hw_kernel(const CodeDev c, const DecParams p, const FrameIO io)
                 const double qv = p.noiseSigma * n4[q];
                 double qm = ((qv - p.theta0) / p.hw_two_w - 1.0);
                 if (qm > p.hw_lmax) qm = p.hw_lmax; else if (qm < -p.hw_lmax) qm = -p.hw_lmax;
-                qprime[i] = (unsigned char)hw_pack(qm, p);
+                qval[i] = (signed char)hw_unpack(hw_pack(qm, p));
             }
         }
         for (int o = 16; o; o >>= 1) unc += __shfl_xor_sync(0xffffffffu, unc, o);
@@ -329,36 +345,55 @@ __global__ void hw_kernel(const CodeDev c, const DecParams p, const FrameIO io)
         int qpointer = io.qpointer0 ? io.qpointer0[f] : 0;
         int leastIterations = T, leastErrors = N, satisfied = 1, it = 0;
         for (int phase = 0; phase < maxPhases; phase++) {             // :280-373
-            for (int i = tid; i < N; i += nt) d[i] = r[i];
+            for (int w = tid; w < nwords; w += nt) dbits[w] = rbits[w];
+            for (int w = tid; w < mwords; w += nt) tog[w] = 0u;
+            __syncthreads();
+            // full syndrome of the starting decisions (checkNodeUpdates, :546-563), once per phase
+            for (int j0 = tid; j0 < (mwords << 5); j0 += nt) {
+                unsigned par = 0;
+                if (j0 < M) {
+                    const int deg = c.cn_deg[j0];
+                    for (int k = 0; k < deg; k++) { const uint32_t i = c.cn_var[(size_t)k * M + j0]; par ^= dbits[i >> 5] >> (i & 31); }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, (par & 1u) != 0);
+                if (lane == 0) syn[j0 >> 5] = bal;
+            }
             __syncthreads();
             for (it = 0; it < T; it++) {
-                int bad = 0;
-                for (int j = tid; j < M; j += nt) {                   // checkNodeUpdates :546-563
-                    const int deg = c.cn_deg[j];
-                    int ng = 0;
-                    for (int k = 0; k < deg; k++) ng ^= (d[c.cn_var[(size_t)k * M + j]] < 0);
-                    syn[j] = (unsigned char)ng;
-                    bad |= ng;
-                }
-                satisfied = (__syncthreads_or(bad) == 0);
-                if (satisfied) break;
-                for (int i = tid; i < N; i += nt) {                   // symNodeUpdates :565-593
-                    const int deg = c.vn_deg[i];
-                    int E = (int)d[i] * hw_unpack(yprime[i]);         // (1-2d01) = d
-                    int SSum = 0;
-                    for (int sl = 0; sl < deg; sl++) SSum += 1 - (int)syn[c.vn_chk[(size_t)sl * N + i]];
-                    E += SSum * p.hw_Smult + hw_unpack(qprime[i + qpointer]);
-                    if (E <= p.hw_theta) d[i] = -d[i];
+                unsigned any = 0;
+                for (int w = 0; w < mwords; w++) any |= syn[w];
+                satisfied = (any == 0);
+                if (satisfied) break;                                 // :297-299
+                // symNodeUpdates :565-593, variables of a warp share one decision word
+                for (int i0 = tid; i0 < npad; i0 += nt) {
+                    const bool valid = i0 < N;
+                    const uint32_t dw = dbits[i0 >> 5];
+                    bool nd = (dw >> lane) & 1u;
+                    if (valid) {
+                        const int deg = c.vn_deg[i0];
+                        const int d01 = (int)nd;
+                        int sat = 0;
+                        for (int sl = 0; sl < deg; sl++) { const int j = chk[sl * N + i0]; sat += 1 - (int)((syn[j >> 5] >> (j & 31)) & 1u); }
+                        const int E = (1 - 2 * d01) * (int)yval[i0] + sat * p.hw_Smult + (int)qval[i0 + qpointer];
+                        if (E <= p.hw_theta) {
+                            nd = !nd;
+                            for (int sl = 0; sl < deg; sl++) { const int j = chk[sl * N + i0]; atomicXor(&tog[j >> 5], 1u << (j & 31)); }
+                        }
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, valid && nd);
+                    if (lane == 0) dbits[i0 >> 5] = bal;
                 }
                 qpointer++;                                           // :356-358
                 if (qpointer >= QB - N) qpointer = 0;
                 __syncthreads();
+                for (int w = tid; w < mwords; w += nt) { syn[w] ^= tog[w]; tog[w] = 0u; }
+                __syncthreads();
             }
             // countDecisionErrors against c in {0,1} (:362-372)
+            int le = 0;
+            for (int w = tid; w < nwords; w += nt) le += __popc(dbits[w] ^ cbits[w]);
             if (tid == 0) fs->errors = 0;
             __syncthreads();
-            int le = 0;
-            for (int i = tid; i < N; i += nt) le += (int)((d[i] < 0) != ((cw ? cw[i] : 0) != 0));
             for (int o = 16; o; o >>= 1) le += __shfl_xor_sync(0xffffffffu, le, o);
             if (lane == 0 && le) atomicAdd(&fs->errors, le);
             __syncthreads();
@@ -367,7 +402,6 @@ __global__ void hw_kernel(const CodeDev c, const DecParams p, const FrameIO io)
             if (it < leastIterations) leastIterations = it;
             __syncthreads();
         }
-        pack_decisions(c, d, dbits);
         if (tid == 0) fs->errors = 0;
         __syncthreads();
         finish_frame(c, p, io, f, cw, dbits, fs, leastIterations, satisfied, 0, 0, maxPhases, leastErrors, tot);
