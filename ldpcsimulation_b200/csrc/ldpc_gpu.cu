@@ -275,7 +275,6 @@ struct ldpc_gpu_decoder {
     KernelFn fn = nullptr;
     int block = 0, smem = 0, ctas_per_sm = 0, grid_full = 0;
     bool gstate = false; size_t ws_stride = 0; unsigned char *d_ws = nullptr;   // HBM-resident frame state
-    long long stagger_cycles = 0;
     int frames_per_cta = 1;                                                      // > 1: frame-interleaved tile kernel
     DecParams base;
     Slot slot[2];
@@ -320,7 +319,7 @@ template <typename T> static int upload(ldpc_gpu_decoder *d, const std::vector<T
 static int build_schedule(ldpc_gpu_decoder *d, const ldpc_gpu_code *c, size_t real_bytes)
 {
     CodeDev &v = d->dev;
-    v.sched = nullptr; v.sched16 = nullptr; v.col_of_var = nullptr; v.var_of_col = nullptr;
+    v.sched = nullptr; v.col_of_var = nullptr; v.var_of_col = nullptr;
     if (v.regular_dc <= 0 || v.regular_dv <= 0 || v.regular_dc % 4 || v.N > 65535 || getenv("LDPC_GPU_NO_SCHED")) return LDPC_GPU_OK;
     const int N = v.N, M = v.M, dc = v.regular_dc, dvm = c->dv_max, dcm = c->dc_max;
     std::vector<int> ml((size_t)M * dc);
@@ -339,14 +338,6 @@ static int build_schedule(ldpc_gpu_decoder *d, const ldpc_gpu_code *c, size_t re
     const uint32_t *pt; const uint16_t *p1, *p2; int rc;
     if ((rc = upload(d, tab, &pt)) || (rc = upload(d, cov, &p1)) || (rc = upload(d, voc, &p2))) return rc;
     v.sched = reinterpret_cast<const uint4 *>(pt); v.col_of_var = p1; v.var_of_col = p2;
-    if ((size_t)v.dvN * real_bytes <= 65536 && dc % 8 == 0) {     // uint16 byte offsets: the row fits dc/2 registers
-        std::vector<uint16_t> t16((size_t)(dc / 8) * M * 8, 0);
-        for (int j = 0; j < M; j++) for (int t = 0; t < dc; t++)
-            t16[((size_t)(t / 8) * M + j) * 8 + (t % 8)] = (uint16_t)tab[((size_t)(t / 4) * M + j) * 4 + (t % 4)];
-        const uint16_t *p16;
-        if ((rc = upload(d, t16, &p16))) return rc;
-        v.sched16 = reinterpret_cast<const uint4 *>(p16);
-    }
     return LDPC_GPU_OK;
 }
 
@@ -433,7 +424,7 @@ static int pick_kernel(ldpc_gpu_decoder *d)
         }
         if (algo == ALGO_BP && !f64 && !d->gstate && v.sched && v.regular_dc == 32 && v.regular_dv == 6 && v.N == 2048 && v.M <= 384 &&
             !getenv("LDPC_GPU_GENERIC_BP")) {
-            d->fn = (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 2, false, ALGO_BP>;    // O(dc) phi-domain sum-product
+            d->fn = (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 2, ALGO_BP>;    // O(dc) phi-domain sum-product
             block = 384; smem = ms_sched_smem_bytes<float>(v);
         }
         if (algo == ALGO_MS && v.idx16 && !d->gstate && !getenv("LDPC_GPU_GENERIC_MS")) {
@@ -441,20 +432,11 @@ static int pick_kernel(ldpc_gpu_decoder *d)
             const bool rc = v.regular_dc > 0, rv = v.regular_dv > 0;
             KernelFn fast = nullptr;
 #define MS_FAST(DC, DV, RC, RV) (f64 ? (KernelFn)ms_fast_kernel<double, DC, DV, RC, RV, 1024, 1> : (KernelFn)ms_fast_kernel<float, DC, DV, RC, RV, 1024, 1>)
-            const char *mb = getenv("LDPC_GPU_MINB");
-            if (v.sched && v.regular_dc == 32 && v.regular_dv == 6 && v.N == 2048 && v.M <= 384)   // the 802.3an H, scheduled
+            if (v.sched && v.regular_dc == 32 && v.regular_dv == 6 && v.N == 2048 && v.M <= 384) {   // the 802.3an H, scheduled
                 smem = f64 ? ms_sched_smem_bytes<double>(v) : ms_sched_smem_bytes<float>(v);
-            if (v.sched && v.regular_dc == 32 && v.regular_dv == 6 && v.N == 2048 && v.M <= 384)
-                fast = f64 ? (KernelFn)ms_sched_kernel<double, 32, 6, 2048, 384, 1>
-                           : ((mb && atoi(mb) == 13) ? (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 3, true>
-                              : (mb && atoi(mb) == 12) ? (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 2, true>
-                              : (mb && atoi(mb) == 3) ? (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 3>
-                              : (mb && atoi(mb) == 1) ? (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 1>
-                                                      : (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 2>);
-            else if (v.regular_dc == 32 && v.regular_dv == 6 && v.M <= 384 && !f64)     // the 802.3an H: 384 check threads per frame
-                fast = (mb && atoi(mb) == 3) ? (KernelFn)ms_fast_kernel<float, 32, 6, true, true, 384, 3>
-                     : (mb && atoi(mb) == 1) ? (KernelFn)ms_fast_kernel<float, 32, 6, true, true, 384, 1>
-                                             : (KernelFn)ms_fast_kernel<float, 32, 6, true, true, 384, 2>;   // measured best (profiles/r1_tuning.md)
+                // 2 CTAs/SM at 80 registers is the measured optimum for fp32 (1 CTA: -15 %, 3 CTAs: spills, -30 %)
+                fast = f64 ? (KernelFn)ms_sched_kernel<double, 32, 6, 2048, 384, 1> : (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 2>;
+            }
             else if (v.regular_dc == 32 && v.regular_dv == 6) fast = MS_FAST(32, 6, true, true);
             else if (v.regular_dc == 32 && v.dv_max <= 6) fast = MS_FAST(32, 6, true, false);
             else if (v.dc_max <= 8 && v.regular_dv == 3) fast = MS_FAST(8, 3, false, true);
@@ -663,7 +645,6 @@ static int launch(ldpc_gpu_decoder *d, const DecParams &p, const FrameIO &io, cu
     const long long want = std::min<long long>((io.n_frames + d->frames_per_cta - 1) / d->frames_per_cta, d->grid_full);
     if (want <= 0) return LDPC_GPU_OK;
     FrameIO io2 = io; io2.workspace = d->d_ws; io2.ws_stride = d->ws_stride;
-    { const char *sg = getenv("LDPC_GPU_STAGGER"); io2.stagger_cycles = sg ? atoll(sg) : d->stagger_cycles; }
     d->fn<<<(unsigned)want, d->block, d->smem, st>>>(d->dev, p, io2);
     CU_TRY(cudaGetLastError());
     d->last_launches++;

@@ -19,17 +19,11 @@ namespace ldpc {
 
 template <typename Real> struct SignOps;
 template <> struct SignOps<float> {
-    typedef uint32_t acc_t;                     // number of negative messages seen (parity = sign product)
+    typedef uint32_t acc_t;                     // XOR of the raw bit patterns: bit 31 = sign product
     static LDPC_DEVINL acc_t zero() { return 0u; }
-    // acc += sign bit, as hi32(bits * 2) + acc: one IMAD.HI on the FMA pipe (the ALU pipe is the busy one here)
-#ifndef LDPC_SIGN_XOR
-    static LDPC_DEVINL void fold(acc_t &a, float v) { a = __umulhi(__float_as_uint(v), 2u) + a; }
-#else
-    static LDPC_DEVINL void fold(acc_t &a, float v) { a ^= __float_as_uint(v) >> 31; }
-#endif
-    static LDPC_DEVINL acc_t merge(acc_t a, acc_t b) { return a + b; }
+    static LDPC_DEVINL void fold(acc_t &a, float v) { a ^= __float_as_uint(v); }
     // magnitude (>= 0) carrying the row's sign product
-    static LDPC_DEVINL float presign(float mag, acc_t a) { return __uint_as_float(__float_as_uint(mag) ^ (a << 31)); }
+    static LDPC_DEVINL float presign(float mag, acc_t a) { return __uint_as_float(__float_as_uint(mag) ^ (a & 0x80000000u)); }
     // times sgn(v_k)
     static LDPC_DEVINL float apply(float presigned, float v) { return __uint_as_float(__float_as_uint(presigned) ^ (__float_as_uint(v) & 0x80000000u)); }
 };
@@ -37,7 +31,6 @@ template <> struct SignOps<double> {
     typedef bool acc_t;
     static LDPC_DEVINL acc_t zero() { return false; }
     static LDPC_DEVINL void fold(acc_t &a, double v) { a ^= neg_ge(v); }
-    static LDPC_DEVINL acc_t merge(acc_t a, acc_t b) { return a ^ b; }
     static LDPC_DEVINL double presign(double mag, acc_t a) { return a ? -mag : mag; }
     static LDPC_DEVINL double apply(double presigned, double v) { return neg_ge(v) ? -presigned : presigned; }
 };
@@ -206,32 +199,16 @@ namespace ldpc {
 //     compile-time slot strides (immediate offsets);
 //   * decisions are scattered back to true variable order once, in the last iteration.
 // ---------------------------------------------------------------------------------------------
-// Step k's byte offset out of the thread's register-resident row schedule (two uint16 per word),
-// unpacked on the FMA pipe (IMAD.HI / IMAD): the ALU pipe is the busy one in the check phase.
-template <int NW>
-LDPC_DEVINL uint32_t row_off(const uint32_t (&offp)[NW], int k)
-{
-    const uint32_t x = offp[k >> 1];
-    uint32_t hi, lo;
-    asm("mul.hi.u32 %0, %1, 65536;" : "=r"(hi) : "r"(x));
-    if (k & 1) return hi;
-    asm("mad.lo.u32 %0, %1, 0xFFFF0000, %2;" : "=r"(lo) : "r"(hi), "r"(x));
-    return lo;
-}
-
-// HALF: a check thread keeps only the second half of its row in registers and gathers the first half
-// again in its write pass (the gathers are conflict-free, so this trades 16 extra LDS per row for 16
-// registers per thread, which is what allows a third CTA per SM).
 // ALGO = ALGO_BP (fp32 only): sum-product on the same skeleton.  The row update is done in the
 // phi domain, phi(x) = -ln tanh(x/2) = log1p(2/expm1(x)):  |c2v_k| = phi(sum_{i != k} phi(|v_i|)),
 // because in fp32 tanhf saturates to 1 and the reference's product form (src/decodeBP.cpp:353-377)
 // yields inf.  The leave-one-out sum is total - own with the total kept in fp64, which keeps full fp32
 // accuracy even when one weak message dominates the total; cost O(dc) per row instead of the
 // reference's O(dc^2).  The fp64 parity instantiation stays on mp_kernel (reference order, O(dc^2)).
-template <typename Real, int DC, int DV, int NFIX, int NT_MAX, int MINB, bool HALF = false, int ALGO = ALGO_MS>
+template <typename Real, int DC, int DV, int NFIX, int NT_MAX, int MINB, int ALGO = ALGO_MS>
 __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c, const DecParams p, const FrameIO io)
 {
-    static_assert(ALGO == ALGO_MS || (sizeof(Real) == 4 && !HALF), "the phi-domain sum-product row update is the fp32 path");
+    static_assert(ALGO == ALGO_MS || sizeof(Real) == 4, "the phi-domain sum-product row update is the fp32 path");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrameScratch *fs = reinterpret_cast<FrameScratch *>(smem_raw);
     Real *msg = reinterpret_cast<Real *>(smem_raw + 16);
@@ -252,26 +229,6 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
     const bool fcond = !io.y || io.y_dtype != LDPC_GPU_DT_F64;      // fp32 instantiation: fp32 front end on fp32 samples
 
     CtaTotals tot; tot.clear();
-    // Co-resident CTAs start together and do identical work, so they stay in lock step: both in the
-    // ALU-bound check phase, then both in the LSU-bound variable phase.  Starting the second CTA of
-    // every SM a fraction of an iteration late lets the two phases overlap (profiles/r1_summary.md).
-    if (io.stagger_cycles > 0 && blockIdx.x >= gridDim.x / 2) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < io.stagger_cycles) { }
-    }
-#ifdef LDPC_REG_OFFSETS
-    // thread j owns row j for every frame of the launch: its schedule stays in registers
-    uint32_t offp[DC / 2];
-    {
-        const int j = tid < M ? tid : 0;
-#pragma unroll
-        for (int g = 0; g < DC / 8; g++) {
-            const uint4 w = __ldg(&c.sched16[(size_t)g * M + j]);
-            offp[4 * g + 0] = w.x; offp[4 * g + 1] = w.y; offp[4 * g + 2] = w.z; offp[4 * g + 3] = w.w;
-        }
-    }
-#endif
-
     // ---- channel front end, software-pipelined across frames ----------------------------------------
     // gen(fx, b) produces the four conditioned samples of block b of frame fx into the staging buffer
     // ybuf (storage-column order), the raw hard decisions into rnext and the uncodedErrors increments
@@ -389,8 +346,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
                     }
                     continue;
                 }
-                constexpr int KEEP0 = HALF ? DC / 2 : 0;              // steps [KEEP0, DC) stay in registers
-                Real v[DC - KEEP0];
+                Real v[DC];
                 Real m1 = INF, m2 = INF;
                 typename SignOps<Real>::acc_t sg = SignOps<Real>::zero();
 #pragma unroll
@@ -400,12 +356,11 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const int k = g * 4 + q;
-                        const Real x = *reinterpret_cast<const Real *>(msgb + off[q]);
-                        if (k >= KEEP0) v[k - KEEP0] = x;
-                        const Real a = absr(x);
+                        v[k] = *reinterpret_cast<const Real *>(msgb + off[q]);
+                        const Real a = absr(v[k]);
                         m2 = rmin(m2, rmax(m1, a));
                         m1 = rmin(m1, a);
-                        SignOps<Real>::fold(sg, x);
+                        SignOps<Real>::fold(sg, v[k]);
                     }
                 }
                 Real o1 = m1, o2 = m2;
@@ -416,16 +371,14 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
                 if (offset) { o1 = o1 - delta; o1 = (o1 > 0) ? o1 : (Real)0; o2 = o2 - delta; o2 = (o2 > 0) ? o2 : (Real)0; }
                 const Real s1 = SignOps<Real>::presign(o1, sg), s2 = SignOps<Real>::presign(o2, sg);
 #pragma unroll
-                for (int g = NG - 1; g >= 0; g--) {                   // register-resident half first
+                for (int g = 0; g < NG; g++) {
                     const uint4 w = __ldg(&c.sched[(size_t)g * M + j]);
                     const uint32_t off[4] = { w.x, w.y, w.z, w.w };
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const int k = g * 4 + q;
-                        Real *slot = reinterpret_cast<Real *>(msgb + off[q]);
-                        const Real x = (k >= KEEP0) ? v[k >= KEEP0 ? k - KEEP0 : 0] : *slot;
-                        const Real sel = (absr(x) == m1) ? s2 : s1;
-                        *slot = SignOps<Real>::apply(sel, x);
+                        const Real sel = (absr(v[k]) == m1) ? s2 : s1;
+                        *reinterpret_cast<Real *>(msgb + off[q]) = SignOps<Real>::apply(sel, v[k]);
                     }
                 }
             }

@@ -29,7 +29,6 @@ struct CodeDev {
     const uint32_t*vn_chk;   // [s*N + i]  check of slot s of variable i, padded with 0
     // bank-conflict-free check schedule of a regular code (ldpc_schedule.h), or NULL
     const uint4   *sched;    // [(t/4)][j]  four BYTE offsets (s*N + col(i))*sizeof(Real) of steps 4(t/4)..+3 of row j
-    const uint4   *sched16;  // [(t/8)][j]  the same as eight uint16 byte offsets per vector (when they fit 16 bits), or NULL
     const uint16_t*col_of_var; // [N] storage column of variable i
     const uint16_t*var_of_col; // [N] inverse
 };
@@ -78,7 +77,6 @@ struct FrameIO {
     unsigned long long *it_hist;  // device [iter_hist_len] or NULL
     unsigned long long *ph_hist;  // device [maxphase] or NULL
     unsigned long long seed;
-    long long stagger_cycles;     // start delay of the second CTA of each SM (phase offset), 0 = none
     unsigned char *workspace;     // device, gridDim.x * ws_stride bytes: per-CTA frame state of the HBM-resident
     size_t         ws_stride;     //   instantiations (codes whose state exceeds one SM's shared memory)
     // channel_dump outputs
