@@ -254,6 +254,179 @@ __global__ void gdbf_kernel(const CodeDev c, const DecParams p, const FrameIO io
 }
 
 // ---------------------------------------------------------------------------------------------
+// gdbf_par_kernel: the parallel-flipping members of the family (everything except -D sequentialmode
+// and -D modeswitching), restructured like hw_kernel below: decisions and syndromes are bit-packed,
+// and because the syndrome is linear in d over GF(2) it is computed in full once per phase and then
+// updated by the bits that flip (atomicXor into a toggle mask folded in between iterations) instead of
+// being recomputed from d through E gathers every iteration (checkNodeUpdates, decodeGDBF.cpp:517-534).
+// The flip metric is accumulated in the reference's order (d*y, then +w*s_j in nlist order, then the
+// perturbation, :541-556) and reads the syndromes of the iteration's start, so the fp64 instantiation
+// stays bit-exact.  Graph (variable side) cached in shared memory as uint16 once per CTA.
+// ---------------------------------------------------------------------------------------------
+template <typename Real>
+static inline size_t gdbf_par_smem_bytes(const CodeDev &c)
+{
+    const size_t nwords = (size_t)(c.N + 31) / 32, mwords = (size_t)(c.M + 31) / 32;
+    size_t n = 16 + sizeof(Real) * 3 * (size_t)c.N + 4 * (size_t)c.N + 4 * (2 * nwords + 2 * mwords) + 2 * (size_t)c.dv_max * c.N + 64;
+    return (n + 15) & ~(size_t)15;
+}
+
+template <typename Real>
+__global__ void gdbf_par_kernel(const CodeDev c, const DecParams p, const FrameIO io)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = c.N, M = c.M, nwords = (N + 31) >> 5, mwords = (M + 31) >> 5, nblk = (N + 3) >> 2, dvm = c.dv_max;
+    FrameScratch *fs = reinterpret_cast<FrameScratch *>(smem_raw);
+    Real *yq = reinterpret_cast<Real *>(smem_raw + 16);
+    Real *theta = yq + N, *shape = theta + N;
+    int *dsum = reinterpret_cast<int *>(shape + N);
+    uint32_t *dbits = reinterpret_cast<uint32_t *>(dsum + N);          // 1 <-> d = -1
+    uint32_t *rbits = dbits + nwords;
+    uint32_t *syn = rbits + nwords;                                     // 1 <-> s_j = -1 (unsatisfied)
+    uint32_t *tog = syn + mwords;
+    uint16_t *chk = reinterpret_cast<uint16_t *>(tog + mwords);         // [dv_max][N]
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, T = p.T, W = p.windowsize;
+    const uint32_t fl = p.flags;
+    const bool redecode = (fl & LDPC_GPU_F_REDECODE) != 0;
+    const int maxphase = redecode ? (p.maxphase > 0 ? p.maxphase : 1) : 1;
+    const Real theta0 = (Real)p.theta, lambda = (Real)p.lambda, noiseSigma = (Real)p.noiseSigma;
+    CtaTotals tot; tot.clear();
+
+    for (int e = tid; e < dvm * N; e += nt) chk[e] = (uint16_t)c.vn_chk[e];
+    __syncthreads();
+
+    for (long long f = blockIdx.x; f < io.n_frames; f += gridDim.x) {
+        const uint8_t *cw = codeword_row(io, c, f);
+        const unsigned long long fid = (unsigned long long)(io.frame_begin + f);
+        if (tid == 0) { fs->uncoded = 0; fs->errors = 0; fs->flag = 0; }
+        for (int w = tid; w < nwords; w += nt) rbits[w] = 0u;
+        __syncthreads();
+        // ---- channel front end: src/decodeGDBF.cpp:251-274 / src/RNGDBF.cpp:251-275
+        int unc = 0;
+        for (int b = tid; b < nblk; b += nt) {
+            double y4[4];
+            raw_samples4(io, p, c, f, cw, b, y4);
+            uint32_t rn = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = 4 * b + q;
+                if (i >= N) break;
+                double v = y4[q];
+                if (fl & LDPC_GPU_F_SATURATE_SAMPLES) if (fabs(v) > p.Ymax) v *= p.Ymax / fabs(v);
+                const bool rneg = !(v > 0);
+                if (fl & LDPC_GPU_F_QUANTIZE_SAMPLES) v = quantize_gdbf(v, p);
+                yq[i] = (Real)v;
+                unc += (int)(rneg != ((cw ? cw[i] : 0) != 0));
+                rn |= (uint32_t)rneg << q;
+                dsum[i] = 0; shape[i] = (Real)0; theta[i] = theta0;
+            }
+            if (rn) atomicOr(&rbits[(4 * b) >> 5], rn << ((4 * b) & 31));
+        }
+        for (int o = 16; o; o >>= 1) unc += __shfl_xor_sync(0xffffffffu, unc, o);
+        if (lane == 0 && unc) atomicAdd(&fs->uncoded, unc);
+        __syncthreads();
+
+        int it = 0, total_it = 0, phase = 0, satisfied = 1, smoothed = 0, smoothing_used = 0;
+        long long row = 0;
+        while (phase < maxphase) {                                    // src/RNGDBF.cpp:280-400
+            for (int w = tid; w < nwords; w += nt) dbits[w] = rbits[w];
+            for (int w = tid; w < mwords; w += nt) tog[w] = 0u;
+            if (redecode || phase == 0) for (int i = tid; i < N; i += nt) { dsum[i] = 0; if (fl & LDPC_GPU_F_THRESHOLDADAPTATION) theta[i] = theta0; }
+            __syncthreads();
+            for (int j0 = tid; j0 < (mwords << 5); j0 += nt) {        // full syndrome of the starting decisions
+                unsigned par = 0;
+                if (j0 < M) {
+                    const int deg = c.cn_deg[j0];
+                    for (int k = 0; k < deg; k++) { const uint32_t i = c.cn_var[(size_t)k * M + j0]; par ^= dbits[i >> 5] >> (i & 31); }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, (par & 1u) != 0);
+                if (lane == 0) syn[j0 >> 5] = bal;
+            }
+            __syncthreads();
+            for (it = 0; it < T; it++) {
+                unsigned any = 0;
+                for (int w = 0; w < mwords; w++) any |= syn[w];
+                satisfied = (any == 0);
+                if (satisfied) break;                                 // :305-306
+                const long long row_pert = (fl & LDPC_GPU_F_ADDNOISE) ? row++ : -1;
+                const long long row_unif = (fl & LDPC_GPU_F_QUANTIZEPROBABILITIES) ? row++ : -1;
+                const bool smooth_now = (fl & LDPC_GPU_F_OUTPUTSMOOTHING) && it > T - W;
+                for (int b = tid; b < nblk; b += nt) {                // symNodeUpdates, :536-621, four variables per thread
+                    double pert4[4] = {0, 0, 0, 0}, unif4[4] = {0, 0, 0, 0};
+                    if (row_pert >= 0) {                              // :318-333
+                        if (io.noise) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) if (4 * b + q < N) pert4[q] = io.noise[((size_t)f * io.noise_rows + row_pert) * N + 4 * b + q];
+                        } else if (fl & LDPC_GPU_F_UNIFORMNOISE) uniform4(io.seed, fid, (uint32_t)b, (uint32_t)row_pert, STREAM_DECODER, pert4);
+                        else { float n4[4]; normal4(io.seed, fid, (uint32_t)b, (uint32_t)row_pert, STREAM_DECODER, n4);
+#pragma unroll
+                               for (int q = 0; q < 4; q++) pert4[q] = (double)n4[q]; }
+                    }
+                    if (row_unif >= 0) {
+                        if (io.noise) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) if (4 * b + q < N) unif4[q] = io.noise[((size_t)f * io.noise_rows + row_unif) * N + 4 * b + q];
+                        } else uniform4(io.seed, fid, (uint32_t)b, (uint32_t)row_unif, STREAM_DECODER, unif4);
+                    }
+                    const uint32_t dword = dbits[(4 * b) >> 5];
+                    uint32_t flipmask = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int i = 4 * b + q;
+                        if (i >= N) break;
+                        const int deg = c.vn_deg[i];
+                        const bool dneg = (dword >> ((4 * b + q) & 31)) & 1u;
+                        Real E = dneg ? -yq[i] : yq[i];                              // d[i]*y[i]
+                        Real wgt = (Real)1;
+                        if (fl & LDPC_GPU_F_WEIGHTSYNDROMES)
+                            wgt = redecode ? (Real)(p.alpha * p.Ymax / (double)deg) : (Real)p.alpha;   // RNGDBF.cpp:566 / decodeGDBF.cpp:550
+                        for (int sl = 0; sl < deg; sl++) { const int j = chk[sl * N + i]; E += ((syn[j >> 5] >> (j & 31)) & 1u) ? -wgt : wgt; }
+                        if (row_pert >= 0) {
+                            Real smp = (fl & LDPC_GPU_F_UNIFORMNOISE) ? (Real)(p.uni_scale * (pert4[q] - 0.5)) : (Real)(p.noiseSigma * pert4[q]);
+                            if (fl & LDPC_GPU_F_NOISESHAPING) { const Real prev = shape[i]; shape[i] = smp; smp = smp - prev; }
+                            E += smp;
+                        }
+                        bool flip;
+                        if (fl & LDPC_GPU_F_QUANTIZEPROBABILITIES) {               // :561-597
+                            const double val = ((double)(-E + theta[i])) / (double)noiseSigma;
+                            const double pcdf = 0.5 * erfc(-val * 0.70710678118654752440);
+                            const double lv[8] = { 0, 0.0625, 0.125, 0.25, 0.34375, 0.4106, 0.68359, 1 };
+                            double md = 1; int mi = 0;
+#pragma unroll
+                            for (int l = 0; l < 8; l++) { double t = lv[l] - pcdf; t = t * t; if (t < md) { md = t; mi = l; } }
+                            flip = unif4[q] < lv[mi];
+                        } else flip = E < theta[i];                                  // mu == 1
+                        if (flip) {
+                            flipmask |= 1u << q;
+                            for (int sl = 0; sl < deg; sl++) { const int j = chk[sl * N + i]; atomicXor(&tog[j >> 5], 1u << (j & 31)); }
+                        } else if (fl & LDPC_GPU_F_THRESHOLDADAPTATION) theta[i] *= lambda;   // :612-617
+                        if (smooth_now) dsum[i] += (dneg != flip) ? -1 : 1;                   // :348-354, d after the flip
+                    }
+                    if (flipmask) atomicXor(&dbits[(4 * b) >> 5], flipmask << ((4 * b) & 31));
+                }
+                __syncthreads();
+                for (int w = tid; w < mwords; w += nt) { syn[w] ^= tog[w]; tog[w] = 0u; }
+                __syncthreads();
+            }
+            if (fl & LDPC_GPU_F_OUTPUTSMOOTHING) {
+                if (!satisfied) {                                                     // :358-367
+                    for (int w = tid; w < nwords; w += nt) dbits[w] = 0u;
+                    __syncthreads();
+                    for (int i = tid; i < N; i += nt) if (!(dsum[i] > 0)) atomicOr(&dbits[i >> 5], 1u << (i & 31));
+                    smoothed = 1;
+                } else smoothed = 0;
+                if (it > T - W) smoothing_used++;                                     // :371-374
+            }
+            total_it += it; phase++;
+            __syncthreads();
+            if (!redecode || satisfied) break;                                        // src/RNGDBF.cpp:398-399
+        }
+        finish_frame(c, p, io, f, cw, dbits, fs, total_it, satisfied, smoothed, smoothing_used, phase, -1, tot);
+    }
+    if (tid == 0) tot.flush(io.counters);
+}
+
+// ---------------------------------------------------------------------------------------------
 // NGDBFhw: src/NGDBFhw.cpp.  All-integer flip metric on 5-bit sign-magnitude samples; the 2648-entry
 // per-frame noise buffer is read through a window that slides by one entry per iteration.
 //

@@ -456,6 +456,13 @@ static int pick_kernel(ldpc_gpu_decoder *d)
         }
         d->fn = d->gstate ? (f64 ? (KernelFn)gdbf_kernel<double, true> : (KernelFn)gdbf_kernel<float, true>)
                           : (f64 ? (KernelFn)gdbf_kernel<double, false> : (KernelFn)gdbf_kernel<float, false>);
+        // parallel-flipping variants on codes that fit an SM: bit-packed kernel with incremental syndromes
+        const size_t par_smem = f64 ? gdbf_par_smem_bytes<double>(v) : gdbf_par_smem_bytes<float>(v);
+        if (!d->gstate && !(d->cfg.flags & (LDPC_GPU_F_SEQUENTIALMODE | LDPC_GPU_F_MODESWITCHING)) && v.M <= 65535 &&
+            par_smem <= (size_t)max_optin && !getenv("LDPC_GPU_GENERIC_GDBF")) {
+            d->fn = f64 ? (KernelFn)gdbf_par_kernel<double> : (KernelFn)gdbf_par_kernel<float>;
+            smem = par_smem;
+        }
         block = std::min(1024, std::max(128, round32(std::max(v.M, (v.N + 3) / 4))));
         if (v.M <= 512 && v.N <= 4096) block = 256;                           // measured on the 802.3an H: 256 > 384 > 512
         if (const char *gb = getenv("LDPC_GPU_GDBF_BLOCK")) block = std::max(64, atoi(gb) & ~31);
