@@ -21,6 +21,7 @@
 
 #include "ldpc_mp_kernels.cuh"
 #include "ldpc_ms_fast.cuh"
+#include "ldpc_ms_rc.cuh"
 #include "ldpc_schedule.h"
 #include "ldpc_ms_tile.cuh"
 #include "ldpc_ms_h2.cuh"
@@ -319,7 +320,7 @@ template <typename T> static int upload(ldpc_gpu_decoder *d, const std::vector<T
 static int build_schedule(ldpc_gpu_decoder *d, const ldpc_gpu_code *c, size_t real_bytes)
 {
     CodeDev &v = d->dev;
-    v.sched = nullptr; v.col_of_var = nullptr; v.var_of_col = nullptr;
+    v.sched = nullptr; v.col_of_var = nullptr; v.var_of_col = nullptr; v.row_slot = nullptr;
     if (v.regular_dc <= 0 || v.regular_dv <= 0 || v.regular_dc % 4 || v.N > 65535 || getenv("LDPC_GPU_NO_SCHED")) return LDPC_GPU_OK;
     const int N = v.N, M = v.M, dc = v.regular_dc, dvm = c->dv_max, dcm = c->dc_max;
     std::vector<int> ml((size_t)M * dc);
@@ -338,6 +339,14 @@ static int build_schedule(ldpc_gpu_decoder *d, const ldpc_gpu_code *c, size_t re
     const uint32_t *pt; const uint16_t *p1, *p2; int rc;
     if ((rc = upload(d, tab, &pt)) || (rc = upload(d, cov, &p1)) || (rc = upload(d, voc, &p2))) return rc;
     v.sched = reinterpret_cast<const uint4 *>(pt); v.col_of_var = p1; v.var_of_col = p2;
+    // rows whose edges all sit in one slot of their variables' lists (block-structured codes): ldpc_ms_rc.cuh
+    std::vector<uint8_t> rslot(M);
+    bool uniform = true;
+    for (int j = 0; j < M && uniform; j++) {
+        rslot[j] = (uint8_t)c->vn_slot[(size_t)j * dcm];
+        for (int k = 1; k < dc; k++) if (c->vn_slot[(size_t)j * dcm + k] != rslot[j]) { uniform = false; break; }
+    }
+    if (uniform) { const uint8_t *p3; if ((rc = upload(d, rslot, &p3))) return rc; v.row_slot = p3; }
     return LDPC_GPU_OK;
 }
 
@@ -436,6 +445,11 @@ static int pick_kernel(ldpc_gpu_decoder *d)
                 smem = f64 ? ms_sched_smem_bytes<double>(v) : ms_sched_smem_bytes<float>(v);
                 // 2 CTAs/SM at 80 registers is the measured optimum for fp32 (1 CTA: -15 %, 3 CTAs: spills, -30 %)
                 fast = f64 ? (KernelFn)ms_sched_kernel<double, 32, 6, 2048, 384, 1> : (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 2>;
+                if (v.row_slot && !getenv("LDPC_GPU_NO_RC")) {        // c2v resident in the row thread's registers (ldpc_ms_rc.cuh)
+                    smem = f64 ? ms_rc_smem_bytes<double>(v) : ms_rc_smem_bytes<float>(v);
+                    fast = f64 ? (KernelFn)ms_rc_kernel<double, 32, 6, 2048, 384, 1> : (KernelFn)ms_rc_kernel<float, 32, 6, 2048, 384, 2>;
+                    block = 384;
+                }
             }
             else if (v.regular_dc == 32 && v.regular_dv == 6) fast = MS_FAST(32, 6, true, true);
             else if (v.regular_dc == 32 && v.dv_max <= 6) fast = MS_FAST(32, 6, true, false);

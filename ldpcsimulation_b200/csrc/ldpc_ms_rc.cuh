@@ -1,0 +1,264 @@
+// ldpc_ms_rc.cuh -- min-sum family, scheduled kernel with the check-to-variable messages of a row
+// kept in the REGISTERS of the row's thread from one iteration to the next.
+//
+// ms_sched_kernel (ldpc_ms_fast.cuh) moves every edge through shared memory four times per
+// iteration: v2c read + c2v write in the check phase, c2v read + v2c write in the variable phase.
+// Here the variable phase only publishes the a-posteriori sum  S_i = y_i + sum_s c2v_(s,i)  (one word
+// per variable, the reference's `sum`, src/decodeMinSum.cpp:452-476), and the check thread rebuilds
+//     v2c_k = S_i(k) - c2v_k(previous iteration)
+// which is the reference's own expression (`sum - check_to_sym`, same operands, same order, so the
+// result is bit-identical in fp64 and in fp32) from the c2v it produced itself one iteration earlier
+// and still holds in registers.  Per edge and iteration: 3 shared-memory accesses instead of 4, and the
+// variable phase shrinks from (dv loads, dv subtractions, dv stores) to (dv loads, dv additions, 1 store).
+// The first iteration falls out of the same code: c2v = 0 and S = y give v2c = y
+// (initializeSymMessages, :364-370), so the front end no longer writes dv copies of the channel value.
+//
+// Requirements (checked by the host, ldpc_gpu.cu): a conflict-free row schedule, one thread per check
+// row (M <= blockDim), and every edge of a row sitting in the same slot of its variable's list
+// (row_slot[j]; true for the 802.3an H, whose rows 64b..64b+63 touch every variable exactly once, and
+// for any block-structured code with one block row per slot).  The slot makes the address of S_i a
+// compile-time displacement from the address of the edge's message, so no per-edge address arithmetic
+// is added to the ALU-bound check phase.
+#pragma once
+#include "ldpc_ms_fast.cuh"
+
+namespace ldpc {
+
+template <typename Real> LDPC_DEVINL uint32_t sgbits(typename SignOps<Real>::acc_t a);
+template <> LDPC_DEVINL uint32_t sgbits<float>(uint32_t a) { return a; }
+template <> LDPC_DEVINL uint32_t sgbits<double>(bool a) { return a ? 0x80000000u : 0u; }
+
+template <typename Real> LDPC_DEVINL void fold2(typename SignOps<Real>::acc_t &a, Real x, Real y);
+template <> LDPC_DEVINL void fold2<float>(uint32_t &a, float x, float y) { a = a ^ __float_as_uint(x) ^ __float_as_uint(y); }
+template <> LDPC_DEVINL void fold2<double>(bool &a, double x, double y) { SignOps<double>::fold(a, x); SignOps<double>::fold(a, y); }
+
+// One check row.  sdisp = byte displacement from the edge's message word msg[s*N + col] to S[col]
+// (warp-uniform: the caller derives it from a uniform loop counter, so it lives in a uniform register
+// and is folded into the load's address, LDS [R + UR + imm]).
+template <typename Real, int DC>
+LDPC_DEVINL void rc_check_row(unsigned char *msgb, const int sdisp, const uint4 *__restrict__ sched, const int M, const int j, Real (&v)[DC],
+                              const bool normalized, const bool offset, const Real alpha, const Real inv_alpha, const Real delta)
+{
+    constexpr int NG = DC / 4;
+    Real m1 = real_inf<Real>(), m2 = real_inf<Real>();
+    typename SignOps<Real>::acc_t sg = SignOps<Real>::zero();
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+        const uint4 w = __ldg(&sched[(size_t)g * M + j]);
+        const uint32_t off[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = g * 4 + q;
+            v[k] = *reinterpret_cast<const Real *>(msgb + sdisp + off[q]) - v[k];          // v2c = sum - c2v
+        }
+        // two edges per update of (min1, min2): lo / hi of the pair, then three-input minima (FMNMX3 on
+        // sm_100a): 5 min/max instructions per pair instead of 6.  min / max are exact, so any association
+        // gives the reference's min1 and min2 bit for bit.
+#pragma unroll
+        for (int q = 0; q < 4; q += 2) {
+            fold2<Real>(sg, v[g * 4 + q], v[g * 4 + q + 1]);                               // one three-input LOP3 per pair
+            const Real a = absr(v[g * 4 + q]), b = absr(v[g * 4 + q + 1]);
+            const Real lo = rmin(a, b), hi = rmax(a, b);
+            m2 = rmin(rmin(rmax(m1, lo), m2), hi);
+            m1 = rmin(m1, lo);
+        }
+    }
+    Real o1 = m1, o2 = m2;
+    if (normalized) {
+        if (sizeof(Real) == 8) { o1 = o1 / alpha; o2 = o2 / alpha; }
+        else { o1 = o1 * inv_alpha; o2 = o2 * inv_alpha; }
+    }
+    if (offset) { o1 = o1 - delta; o1 = (o1 > 0) ? o1 : (Real)0; o2 = o2 - delta; o2 = (o2 > 0) ? o2 : (Real)0; }
+    if (sizeof(Real) == 4 && !offset) {
+        // fp32, plain / normalised: the select (|v| == min1) ? min2 : min1 without FSETP + FSEL.  With
+        // t = min(|v|, min2) -- which is min1 exactly when this edge attains the row minimum alone, and
+        // min2 otherwise -- the wanted magnitude has the bit pattern bits(min1) + bits(min2) - bits(t)
+        // (integer arithmetic on the patterns, exact).  Normalisation is then one multiplication per edge
+        // by +-1/alpha carrying the row's sign product: the same rounding of the same operands as scaling
+        // min1 / min2 once per row.  Per edge: FMNMX + LOP3 on the (binding) ALU pipe, IMAD + FMUL on the
+        // otherwise idle FMA pipe, instead of FSETP + FSEL + LOP3 all on the ALU pipe.
+        const float m1f = (float)m1, m2f = (float)m2;
+        const uint32_t K = __float_as_uint(m1f) + __float_as_uint(m2f);
+        const float mult = SignOps<float>::presign(normalized ? (float)inv_alpha : 1.0f, (SignOps<float>::acc_t)sgbits<Real>(sg));
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+            const uint4 w = __ldg(&sched[(size_t)g * M + j]);
+            const uint32_t off[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int k = g * 4 + q;
+                const float vk = (float)v[k];
+                const float t = fminf(fabsf(vk), m2f);
+                uint32_t rb;
+                asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(rb) : "r"(__float_as_uint(t)), "r"(K));   // K - bits(t), FMA pipe
+                const float o = __fmul_rn(__uint_as_float(rb), mult);
+                const float c2v = SignOps<float>::apply(o, vk);
+                v[k] = (Real)c2v;                                                        // kept for the next iteration
+                *reinterpret_cast<float *>(msgb + off[q]) = c2v;
+            }
+        }
+        return;
+    }
+    const Real s1 = SignOps<Real>::presign(o1, sg), s2 = SignOps<Real>::presign(o2, sg);
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+        const uint4 w = __ldg(&sched[(size_t)g * M + j]);
+        const uint32_t off[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = g * 4 + q;
+            const Real sel = (absr(v[k]) == m1) ? s2 : s1;
+            v[k] = SignOps<Real>::apply(sel, v[k]);                                      // c2v, kept for the next iteration
+            *reinterpret_cast<Real *>(msgb + off[q]) = v[k];
+        }
+    }
+}
+
+template <typename Real, int DC, int DV, int NFIX, int NT_MAX, int MINB>
+__global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, const DecParams p, const FrameIO io)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    static_assert(DV <= 8, "slot dispatch covers dv <= 8");
+    FrameScratch *fs = reinterpret_cast<FrameScratch *>(smem_raw);
+    Real *msg = reinterpret_cast<Real *>(smem_raw + 16);                       // [DV*N] c2v
+    constexpr int N = NFIX;
+    Real *S = msg + DV * N;                                                    // [N] a-posteriori sums
+    Real *yq = S + N;                                                          // [N] channel values
+    uint32_t *dbits = reinterpret_cast<uint32_t *>(yq + N);
+    unsigned char *msgb = reinterpret_cast<unsigned char *>(msg);
+    constexpr int NB = N * (int)sizeof(Real);                                  // bytes per slot plane
+
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int M = c.M;
+    constexpr int nwords = (N + 31) >> 5, nblk = (N + 3) >> 2;
+    static_assert(DC % 4 == 0 && N % 32 == 0, "scheduled kernel needs dc % 4 == 0 and N % 32 == 0");
+    const Real alpha = (Real)p.alpha, delta = (Real)p.delta, inv_alpha = (Real)p.inv_alpha_f;
+    const bool normalized = (p.flags & LDPC_GPU_F_NORMALIZED_MS) != 0, offset = (p.flags & LDPC_GPU_F_OFFSET_MS) != 0;
+    const uint32_t qflags = p.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES);
+    const bool fcond = !io.y || io.y_dtype != LDPC_GPU_DT_F64;
+    const bool has_row = tid < M;
+    const int slot = has_row ? (int)__ldg(&c.row_slot[tid]) : -1;
+
+    CtaTotals tot; tot.clear();
+    // channel front end, software-pipelined across frames exactly as in ms_sched_kernel
+    Real *ybuf = reinterpret_cast<Real *>(dbits + nwords);
+    uint32_t *rnext = reinterpret_cast<uint32_t *>(ybuf + N);
+    int *unc_next = reinterpret_cast<int *>(rnext + nwords);
+    auto gen = [&](long long fx, const uint8_t *cwx, int b) {
+        double y4[4];
+        raw_samples4(io, p, c, fx, cwx, b, y4);
+        const uint2 cc = __ldg(reinterpret_cast<const uint2 *>(c.col_of_var) + b);
+        uint32_t nib = 0; int unc = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = 4 * b + q;
+            Real vr; bool rneg;
+            if (sizeof(Real) == 4 && fcond) {
+                const float vf = condition_ms_f32((float)y4[q], p, qflags);
+                vr = (Real)vf; rneg = !(vf > 0.0f);
+            } else {                                              // src/decodeMinSum.cpp:214-238
+                double v = y4[q];
+                if (qflags & LDPC_GPU_F_QUANTIZE_SAMPLES) v = quantize_ms(v, p);
+                if (qflags & LDPC_GPU_F_SATURATE_SAMPLES) { if (v > p.Ymax) v = p.Ymax; if (v < -p.Ymax) v = -p.Ymax; }
+                rneg = !(v > 0);
+                vr = (Real)v;
+            }
+            const int col = (int)(((q < 2 ? cc.x : cc.y) >> (16 * (q & 1))) & 0xffffu);
+            ybuf[col] = vr;
+            unc += (int)(rneg != ((cwx ? cwx[i] : 0) != 0));
+            nib |= (uint32_t)rneg << q;
+        }
+        if (nib) atomicOr(&rnext[(4 * b) >> 5], nib << ((4 * b) & 31));
+        if (unc) atomicAdd(unc_next, unc);
+    };
+    const int vn_rem = (N / 2) % nt;
+    const int gen_threads = vn_rem ? nt - vn_rem : nt;
+    const int gen_id = vn_rem ? tid - vn_rem : tid;
+
+    if ((long long)blockIdx.x < io.n_frames) {
+        for (int w = tid; w < nwords; w += nt) rnext[w] = 0u;
+        if (tid == 0) *unc_next = 0;
+        __syncthreads();
+        const uint8_t *cw0 = codeword_row(io, c, blockIdx.x);
+        for (int b = tid; b < nblk; b += nt) gen(blockIdx.x, cw0, b);
+        __syncthreads();
+    }
+
+    Real v[DC];                                                                // this thread's row: c2v of the previous iteration
+    for (long long f = blockIdx.x; f < io.n_frames; f += gridDim.x) {
+        const uint8_t *cw = codeword_row(io, c, f);
+        if (tid == 0) { fs->uncoded = *unc_next; fs->errors = 0; fs->flag = 0; }
+        for (int w = tid; w < nwords; w += nt) dbits[w] = rnext[w];
+        for (int cp = tid; cp < N / 2; cp += nt) {
+            typedef typename Vec2<Real>::type V2;
+            const V2 vr = *reinterpret_cast<const V2 *>(&ybuf[2 * cp]);
+            *reinterpret_cast<V2 *>(&yq[2 * cp]) = vr;
+            *reinterpret_cast<V2 *>(&S[2 * cp]) = vr;
+            if (io.out_soft && p.T == 0) {
+                const unsigned vv = __ldg(reinterpret_cast<const unsigned *>(c.var_of_col) + cp);
+                const int i0 = (int)(vv & 0xffffu), i1 = (int)(vv >> 16);
+                if (io.y_dtype == LDPC_GPU_DT_F64) { ((double *)io.out_soft)[(size_t)f * N + i0] = (double)vr.x; ((double *)io.out_soft)[(size_t)f * N + i1] = (double)vr.y; }
+                else { ((float *)io.out_soft)[(size_t)f * N + i0] = (float)vr.x; ((float *)io.out_soft)[(size_t)f * N + i1] = (float)vr.y; }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < DC; k++) v[k] = (Real)0;
+        __syncthreads();
+        for (int w = tid; w < nwords; w += nt) rnext[w] = 0u;
+        if (tid == 0) *unc_next = 0;
+        const long long fnext = f + gridDim.x;
+        const bool have_next = fnext < io.n_frames;
+        const uint8_t *cwn = have_next ? codeword_row(io, c, fnext) : nullptr;
+        int gen_done = 0;
+        if (p.T == 0) __syncthreads();
+
+        for (int it = 0; it < p.T; it++) {
+            const bool last = (it == p.T - 1);
+            if (last) for (int w = tid; w < nwords; w += nt) dbits[w] = 0u;
+            // ---- check-node phase: one row per thread, slot-specialised addressing ------------------
+            // The slot loop is NOT unrolled on purpose: one copy of the row code (six copies thrash the
+            // instruction cache: measured 10 % slower than ms_sched_kernel), `s` is uniform.
+#pragma unroll 1
+            for (int s = 0; s < DV; s++)
+                if (slot == s) rc_check_row<Real, DC>(msgb, (DV - s) * NB, c.sched, M, tid, v, normalized, offset, alpha, inv_alpha, delta);
+            __syncthreads();
+            // ---- variable-node phase: S = y + sum_s c2v, two adjacent storage columns per thread ------
+            for (int cp = tid; cp < N / 2; cp += nt) {
+                typedef typename Vec2<Real>::type V2;
+                const int col = 2 * cp;
+                V2 sum = *reinterpret_cast<const V2 *>(&yq[col]);
+#pragma unroll
+                for (int s = 0; s < DV; s++) { const V2 cm = *reinterpret_cast<const V2 *>(&msg[s * N + col]); sum.x += cm.x; sum.y += cm.y; }
+                *reinterpret_cast<V2 *>(&S[col]) = sum;
+                if (last) {
+                    const unsigned vv = __ldg(reinterpret_cast<const unsigned *>(c.var_of_col) + cp);
+                    const int i0 = (int)(vv & 0xffffu), i1 = (int)(vv >> 16);
+                    if (!(sum.x > 0)) atomicOr(&dbits[i0 >> 5], 1u << (i0 & 31));
+                    if (!(sum.y > 0)) atomicOr(&dbits[i1 >> 5], 1u << (i1 & 31));
+                    if (io.out_soft) {
+                        if (io.y_dtype == LDPC_GPU_DT_F64) { ((double *)io.out_soft)[(size_t)f * N + i0] = (double)sum.x; ((double *)io.out_soft)[(size_t)f * N + i1] = (double)sum.y; }
+                        else { ((float *)io.out_soft)[(size_t)f * N + i0] = (float)sum.x; ((float *)io.out_soft)[(size_t)f * N + i1] = (float)sum.y; }
+                    }
+                }
+            }
+            if (have_next && gen_done < nblk) {
+                if (gen_id >= 0 && gen_done + gen_id < nblk) gen(fnext, cwn, gen_done + gen_id);
+                gen_done += gen_threads;
+            }
+            __syncthreads();
+        }
+        finish_frame(c, p, io, f, cw, dbits, fs, p.T, -1, 0, 0, 1, -1, tot);
+        if (have_next) for (int b = gen_done + tid; b < nblk; b += nt) gen(fnext, cwn, b);
+        __syncthreads();
+    }
+    if (tid == 0) tot.flush(io.counters);
+}
+
+template <typename Real>
+static inline size_t ms_rc_smem_bytes(const CodeDev &c)
+{
+    const size_t nwords = (size_t)(c.N + 31) / 32;
+    return (16 + sizeof(Real) * ((size_t)c.dvN + 3 * (size_t)c.N) + 8 * nwords + 16 + 15) & ~(size_t)15;
+}
+
+} // namespace ldpc

@@ -31,6 +31,7 @@ struct CodeDev {
     const uint4   *sched;    // [(t/4)][j]  four BYTE offsets (s*N + col(i))*sizeof(Real) of steps 4(t/4)..+3 of row j
     const uint16_t*col_of_var; // [N] storage column of variable i
     const uint16_t*var_of_col; // [N] inverse
+    const uint8_t *row_slot; // [M] slot shared by every edge of row j (ldpc_ms_rc.cuh), or NULL when rows mix slots
 };
 
 // Decoder configuration + per-call channel constants, all derived on the host in double with the
