@@ -32,11 +32,13 @@ template <typename Real> LDPC_DEVINL void fold2(typename SignOps<Real>::acc_t &a
 template <> LDPC_DEVINL void fold2<float>(uint32_t &a, float x, float y) { a = a ^ __float_as_uint(x) ^ __float_as_uint(y); }
 template <> LDPC_DEVINL void fold2<double>(bool &a, double x, double y) { SignOps<double>::fold(a, x); SignOps<double>::fold(a, y); }
 
-// One check row.  sdisp = byte displacement from the edge's message word msg[s*N + col] to S[col]
-// (warp-uniform: the caller derives it from a uniform loop counter, so it lives in a uniform register
-// and is folded into the load's address, LDS [R + UR + imm]).
-template <typename Real, int DC>
-LDPC_DEVINL void rc_check_row(unsigned char *msgb, const int sdisp, const uint4 *__restrict__ sched, const int M, const int j, Real (&v)[DC],
+// One check row.  The byte displacement from the edge's message word msg[slot*N + col] to S[col] is
+// (DV - slot) * NB: the slot-dependent part is folded into each offset by one IMAD (the FMA pipe is idle in
+// this phase, the ALU pipe is the busy one; written as PTX mad so that it is neither hoisted into an
+// ALU-pipe IADD3 nor needs a replicated code path per slot, which thrashed the instruction cache:
+// measured 10 % slower than ms_sched_kernel), the constant part is an immediate of the LDS.
+template <typename Real, int DC, int DV, int NB>
+LDPC_DEVINL void rc_check_row(unsigned char *msgb, const int slot, const uint4 *__restrict__ sched, const int M, const int j, Real (&v)[DC],
                               const bool normalized, const bool offset, const Real alpha, const Real inv_alpha, const Real delta)
 {
     constexpr int NG = DC / 4;
@@ -49,7 +51,9 @@ LDPC_DEVINL void rc_check_row(unsigned char *msgb, const int sdisp, const uint4 
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int k = g * 4 + q;
-            v[k] = *reinterpret_cast<const Real *>(msgb + sdisp + off[q]) - v[k];          // v2c = sum - c2v
+            uint32_t so;
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(so) : "r"((uint32_t)slot), "r"((uint32_t)-NB), "r"(off[q]));
+            v[k] = *reinterpret_cast<const Real *>(msgb + DV * NB + so) - v[k];            // v2c = sum - c2v
         }
         // two edges per update of (min1, min2): lo / hi of the pair, then three-input minima (FMNMX3 on
         // sm_100a): 5 min/max instructions per pair instead of 6.  min / max are exact, so any association
@@ -215,12 +219,8 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
         for (int it = 0; it < p.T; it++) {
             const bool last = (it == p.T - 1);
             if (last) for (int w = tid; w < nwords; w += nt) dbits[w] = 0u;
-            // ---- check-node phase: one row per thread, slot-specialised addressing ------------------
-            // The slot loop is NOT unrolled on purpose: one copy of the row code (six copies thrash the
-            // instruction cache: measured 10 % slower than ms_sched_kernel), `s` is uniform.
-#pragma unroll 1
-            for (int s = 0; s < DV; s++)
-                if (slot == s) rc_check_row<Real, DC>(msgb, (DV - s) * NB, c.sched, M, tid, v, normalized, offset, alpha, inv_alpha, delta);
+            // ---- check-node phase: one row per thread ------------------------------------------------
+            if (has_row) rc_check_row<Real, DC, DV, NB>(msgb, slot, c.sched, M, tid, v, normalized, offset, alpha, inv_alpha, delta);
             __syncthreads();
             // ---- variable-node phase: S = y + sum_s c2v, two adjacent storage columns per thread ------
             for (int cp = tid; cp < N / 2; cp += nt) {
@@ -241,9 +241,12 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
                     }
                 }
             }
+            // next frame's channel samples: in iteration 0 every thread generates one block (all warps in
+            // flight hide the generator's long dependent chain), later iterations use the threads that have
+            // no column pair left in the last variable round
             if (have_next && gen_done < nblk) {
-                if (gen_id >= 0 && gen_done + gen_id < nblk) gen(fnext, cwn, gen_done + gen_id);
-                gen_done += gen_threads;
+                if (it == 0) { if (tid < nblk) gen(fnext, cwn, tid); gen_done = nt; }
+                else { if (gen_id >= 0 && gen_done + gen_id < nblk) gen(fnext, cwn, gen_done + gen_id); gen_done += gen_threads; }
             }
             __syncthreads();
         }
