@@ -87,11 +87,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+PROFILE_CSV = "profiles/r1g_ncu_raw_ms_rc_final.csv"      # `ncu --set full` capture of the headline kernel on this workload
+
+
 def profiled_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the decode kernel, per launch, from the committed
     `ncu --set full` capture of this same workload (profiles/); None if the capture is absent."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1d_ncu_raw_ms_sched_final.csv")
+    path = os.path.join(ROOT, PROFILE_CSV)
     try:
         rows = list(csv.reader(open(path)))
         hdr, units, vals = rows[0], rows[1], rows[2]
@@ -361,7 +364,7 @@ def main():
         "kernel_ms_per_step": kernel_ms / args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": profiled_traffic(),
-                     "traffic_source": "profiles/r1d_ncu_raw_ms_sched_final.csv (bytes per launch of 131072 frames)",
+                     "traffic_source": PROFILE_CSV + " (bytes per launch of 131072 frames)",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_frame": bytes_per_frame,
                      "note": "messages never leave the SM (shared memory): DRAM traffic is nil, so algorithmic message bytes over "

@@ -169,6 +169,28 @@ def test_forced_hbm_state_matches_shared_memory_path(variant, monkeypatch):
           soft=("exact" if cfg.kind in (abi.KIND_MINSUM, abi.KIND_DDBMP) else (1e-9 if cfg.kind == abi.KIND_BP else None)))
 
 
+@pytest.mark.parametrize("prec", [abi.PREC_F64, abi.PREC_F32])
+@pytest.mark.parametrize("variant", ["decodeNormalizedMinSum", "decodeOffsetMinSum", "decodeMinSum", "decodeSaturatedMinSum"])
+def test_register_resident_c2v_kernel_equals_scheduled_kernel(variant, prec, monkeypatch):
+    """ms_rc_kernel (c2v in the row thread's registers, variable phase publishes only the a-posteriori sum,
+    integer-pattern select) computes v2c = sum - c2v with the operands and order of ms_sched_kernel:
+    decisions, iteration counts, counters AND a-posteriori sums are bit-identical, in fp32 as in fp64."""
+    R, snr = 0.8413, 3.8
+    code = capi.Code(code_path("802_3_H"))
+    cws = code.random_codewords(5, 4)
+    for T in (0, 1, 2, 9):
+        cfg = cases.cfg_for(variant, code="802_3_H", num_iterations=T, precision=prec)
+        y, noise, rows, cw = cases.make_inputs(2048, cfg, snr, R, 37, 1000 + T, cws if T != 1 else None)
+        monkeypatch.delenv("LDPC_GPU_NO_RC", raising=False)
+        rc = capi.Decoder(code, cfg)
+        assert rc.geometry()["smem_bytes"] == 16 + (4 if prec == abi.PREC_F32 else 8) * 2048 * 9 + 8 * 64 + 16
+        a = rc.decode(snr, R, y, codeword=cw)
+        monkeypatch.setenv("LDPC_GPU_NO_RC", "1")
+        b = capi.Decoder(code, cfg).decode(snr, R, y, codeword=cw)
+        assert np.array_equal(a.bits, b.bits) and np.array_equal(a.iters, b.iters) and np.array_equal(a.flags, b.flags)
+        assert np.array_equal(a.soft, b.soft) and a.counters == b.counters
+
+
 def test_fp16_sample_input_equals_fp32_input_of_the_same_values():
     """LDPC_GPU_DT_F16 only changes how the samples travel: binary16 -> fp32 is exact."""
     cfg = cases.cfg_for("decodeNormalizedMinSum", precision=abi.PREC_F32)
