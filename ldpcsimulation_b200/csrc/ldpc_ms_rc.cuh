@@ -118,6 +118,91 @@ LDPC_DEVINL void rc_check_row(unsigned char *msgb, const int slot, const uint4 *
     }
 }
 
+// d = min(|a|, |b|) carrying sign(a) XOR sign(b): FMNMX.XORSIGN, one ALU-pipe instruction (sm_86+).
+LDPC_DEVINL float min_xorsign_abs(float a, float b)
+{
+    float d;
+    asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+
+// fp32 check row.  Same results as rc_check_row<float> bit for bit, with the sign algebra folded into the
+// min / max instructions:
+//   pass 1: min1 is carried as a SIGNED value whose sign bit is the XOR of the signs seen so far
+//           (min.xorsign.abs), so the row's sign product costs nothing; (min1, min2) advance two edges at a
+//           time with a three-input minimum (FMNMX3): 5 ALU-pipe instructions per pair of edges;
+//   pass 2: ts = min.xorsign.abs(v, min2) is min(|v|, min2) with the sign of v; min(|v|, min2) is min1 exactly
+//           when this edge alone attains the row minimum and min2 otherwise, so the wanted magnitude
+//           (|v| == min1 ? min2 : min1) has the bit pattern bits(min1) + bits(min2) - bits(min(|v|, min2)), and
+//           subtracting bits(ts) instead leaves the sign of v in bit 31 (-2^31 = +2^31 mod 2^32).  One FMUL by
+//           +-1/alpha (the row's sign product) finishes the message: the same rounding of the same operands
+//           as scaling min1 / min2 once per row.  1 ALU-pipe + 2 FMA-pipe instructions per edge instead of
+//           FSETP + FSEL + LOP3 on the ALU pipe, which is the pipe that bounds this phase.
+// The offset variant keeps the generic second pass (its clamp at zero needs the magnitude).
+template <int DC, int DV, int NB>
+LDPC_DEVINL void rc_check_row_f32(unsigned char *msgb, const int slot, const uint4 *__restrict__ sched, const int M, const int j, float (&v)[DC],
+                                  const bool normalized, const bool offset, const float inv_alpha, const float delta)
+{
+    constexpr int NG = DC / 4;
+    float m1 = real_inf<float>(), m2 = real_inf<float>();
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+        const uint4 w = __ldg(&sched[(size_t)g * M + j]);
+        const uint32_t off[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = g * 4 + q;
+            uint32_t so;
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(so) : "r"((uint32_t)slot), "r"((uint32_t)-NB), "r"(off[q]));
+            v[k] = *reinterpret_cast<const float *>(msgb + DV * NB + so) - v[k];          // v2c = sum - c2v
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q += 2) {
+            const float a = v[g * 4 + q], b = v[g * 4 + q + 1];
+            const float lo = min_xorsign_abs(a, b), hi = fmaxf(fabsf(a), fabsf(b));
+            m2 = fminf(fminf(fmaxf(fabsf(m1), fabsf(lo)), m2), hi);
+            m1 = min_xorsign_abs(m1, lo);
+        }
+    }
+    const uint32_t sg = __float_as_uint(m1);                                             // bit 31 = the row's sign product
+    m1 = fabsf(m1);
+    if (!offset) {
+        const uint32_t K = __float_as_uint(m1) + __float_as_uint(m2);
+        const float mult = SignOps<float>::presign(normalized ? inv_alpha : 1.0f, sg);
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+            const uint4 w = __ldg(&sched[(size_t)g * M + j]);
+            const uint32_t off[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int k = g * 4 + q;
+                const float ts = min_xorsign_abs(v[k], m2);
+                uint32_t rb;
+                asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(rb) : "r"(__float_as_uint(ts)), "r"(K));   // K - bits(ts), FMA pipe
+                v[k] = __fmul_rn(__uint_as_float(rb), mult);                             // c2v, kept for the next iteration
+                *reinterpret_cast<float *>(msgb + off[q]) = v[k];
+            }
+        }
+        return;
+    }
+    float o1 = m1, o2 = m2;
+    if (normalized) { o1 = o1 * inv_alpha; o2 = o2 * inv_alpha; }
+    o1 = o1 - delta; o1 = (o1 > 0) ? o1 : 0.0f; o2 = o2 - delta; o2 = (o2 > 0) ? o2 : 0.0f;
+    const float s1 = SignOps<float>::presign(o1, sg), s2 = SignOps<float>::presign(o2, sg);
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+        const uint4 w = __ldg(&sched[(size_t)g * M + j]);
+        const uint32_t off[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = g * 4 + q;
+            const float sel = (fabsf(v[k]) == m1) ? s2 : s1;
+            v[k] = SignOps<float>::apply(sel, v[k]);
+            *reinterpret_cast<float *>(msgb + off[q]) = v[k];
+        }
+    }
+}
+
 template <typename Real, int DC, int DV, int NFIX, int NT_MAX, int MINB>
 __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, const DecParams p, const FrameIO io)
 {
@@ -220,7 +305,10 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
             const bool last = (it == p.T - 1);
             if (last) for (int w = tid; w < nwords; w += nt) dbits[w] = 0u;
             // ---- check-node phase: one row per thread ------------------------------------------------
-            if (has_row) rc_check_row<Real, DC, DV, NB>(msgb, slot, c.sched, M, tid, v, normalized, offset, alpha, inv_alpha, delta);
+            if (has_row) {
+                if constexpr (sizeof(Real) == 4) rc_check_row_f32<DC, DV, NB>(msgb, slot, c.sched, M, tid, v, normalized, offset, inv_alpha, delta);
+                else rc_check_row<Real, DC, DV, NB>(msgb, slot, c.sched, M, tid, v, normalized, offset, alpha, inv_alpha, delta);
+            }
             __syncthreads();
             // ---- variable-node phase: S = y + sum_s c2v, two adjacent storage columns per thread ------
             for (int cp = tid; cp < N / 2; cp += nt) {
