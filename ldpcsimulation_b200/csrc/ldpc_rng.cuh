@@ -52,13 +52,12 @@ __device__ __forceinline__ void box_muller_pair(uint32_t a, uint32_t b, float &n
     float pc = __fmaf_rn(2.443315711809948e-5f, z, -1.388731625493765e-3f);
     pc = __fmaf_rn(pc, z, 4.166664568298827e-2f);
     const float c = __fmaf_rn(__fmul_rn(pc, z), z, __fmaf_rn(-0.5f, z, 1.0f));
-    float cs, sn;
-    switch (k & 3) {
-    case 0:  cs = c;  sn = s;  break;
-    case 1:  cs = -s; sn = c;  break;
-    case 2:  cs = -c; sn = -s; break;
-    default: cs = s;  sn = -c; break;
-    }
+    // quadrant k: (cos, sin) = (c, s), (-s, c), (-c, -s), (s, -c); written without branches (a switch diverges
+    // four ways inside a warp); negation is a sign-bit flip, exactly what unary minus does
+    const bool swp = (k & 1) != 0;
+    const uint32_t cneg = ((uint32_t)(k + 1) & 2u) << 30, sneg = ((uint32_t)k & 2u) << 30;
+    const float cs = __uint_as_float(__float_as_uint(swp ? s : c) ^ cneg);
+    const float sn = __uint_as_float(__float_as_uint(swp ? c : s) ^ sneg);
     const unsigned long long v = (unsigned long long)b + 1ull;      // [1, 2^32]
     int e = 63 - __clzll((long long)v);
     const uint32_t top = (uint32_t)((v << (63 - e)) >> 40);         // 24 bits, leading one set
