@@ -118,6 +118,10 @@ LDPC_DEVINL void rc_check_row(unsigned char *msgb, const int slot, const uint4 *
     }
 }
 
+#ifndef RC_NPRE
+#define RC_NPRE 2          // schedule words (4 edges each) fetched ahead of the check phase's barrier
+#endif
+
 // d = min(|a|, |b|) carrying sign(a) XOR sign(b): FMNMX.XORSIGN, one ALU-pipe instruction (sm_86+).
 LDPC_DEVINL float min_xorsign_abs(float a, float b)
 {
@@ -140,14 +144,14 @@ LDPC_DEVINL float min_xorsign_abs(float a, float b)
 //           FSETP + FSEL + LOP3 on the ALU pipe, which is the pipe that bounds this phase.
 // The offset variant keeps the generic second pass (its clamp at zero needs the magnitude).
 template <int DC, int DV, int NB>
-LDPC_DEVINL void rc_check_row_f32(unsigned char *msgb, const int slot, const uint4 *__restrict__ sched, const int M, const int j, float (&v)[DC],
+LDPC_DEVINL void rc_check_row_f32(unsigned char *msgb, const int slot, const uint4 (&sw)[RC_NPRE], const uint4 *__restrict__ sched, const int M, const int j, float (&v)[DC],
                                   const bool normalized, const bool offset, const float inv_alpha, const float delta)
 {
     constexpr int NG = DC / 4;
     float m1 = real_inf<float>(), m2 = real_inf<float>();
 #pragma unroll
     for (int g = 0; g < NG; g++) {
-        const uint4 w = __ldg(&sched[(size_t)g * M + j]);
+        const uint4 w = (g < RC_NPRE) ? sw[g] : __ldg(&sched[(size_t)g * M + j]);
         const uint32_t off[4] = { w.x, w.y, w.z, w.w };
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -171,7 +175,7 @@ LDPC_DEVINL void rc_check_row_f32(unsigned char *msgb, const int slot, const uin
         const float mult = SignOps<float>::presign(normalized ? inv_alpha : 1.0f, sg);
 #pragma unroll
         for (int g = 0; g < NG; g++) {
-            const uint4 w = __ldg(&sched[(size_t)g * M + j]);
+            const uint4 w = (g < RC_NPRE) ? sw[g] : __ldg(&sched[(size_t)g * M + j]);
             const uint32_t off[4] = { w.x, w.y, w.z, w.w };
 #pragma unroll
             for (int q = 0; q < 4; q++) {
@@ -191,7 +195,7 @@ LDPC_DEVINL void rc_check_row_f32(unsigned char *msgb, const int slot, const uin
     const float s1 = SignOps<float>::presign(o1, sg), s2 = SignOps<float>::presign(o2, sg);
 #pragma unroll
     for (int g = 0; g < NG; g++) {
-        const uint4 w = __ldg(&sched[(size_t)g * M + j]);
+        const uint4 w = (g < RC_NPRE) ? sw[g] : __ldg(&sched[(size_t)g * M + j]);
         const uint32_t off[4] = { w.x, w.y, w.z, w.w };
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -274,6 +278,18 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
     }
 
     Real v[DC];                                                                // this thread's row: c2v of the previous iteration
+    // fp32: the row's schedule words are fetched BEFORE the barrier that opens a check phase (the registers
+    // are free during the variable phase), so their L1 latency overlaps the barrier wait instead of stalling
+    // all twelve warps at once right after it (long_scoreboard was 10 % of the check-phase samples)
+    uint4 sw[RC_NPRE];
+    auto fetch_schedule = [&]() {
+        if constexpr (sizeof(Real) == 4) {
+            if (has_row) {
+#pragma unroll
+                for (int g = 0; g < RC_NPRE; g++) sw[g] = __ldg(&c.sched[(size_t)g * M + tid]);
+            }
+        }
+    };
     for (long long f = blockIdx.x; f < io.n_frames; f += gridDim.x) {
         const uint8_t *cw = codeword_row(io, c, f);
         if (tid == 0) { fs->uncoded = *unc_next; fs->errors = 0; fs->flag = 0; }
@@ -292,6 +308,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
         }
 #pragma unroll
         for (int k = 0; k < DC; k++) v[k] = (Real)0;
+        fetch_schedule();
         __syncthreads();
         for (int w = tid; w < nwords; w += nt) rnext[w] = 0u;
         if (tid == 0) *unc_next = 0;
@@ -306,7 +323,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
             if (last) for (int w = tid; w < nwords; w += nt) dbits[w] = 0u;
             // ---- check-node phase: one row per thread ------------------------------------------------
             if (has_row) {
-                if constexpr (sizeof(Real) == 4) rc_check_row_f32<DC, DV, NB>(msgb, slot, c.sched, M, tid, v, normalized, offset, inv_alpha, delta);
+                if constexpr (sizeof(Real) == 4) rc_check_row_f32<DC, DV, NB>(msgb, slot, sw, c.sched, M, tid, v, normalized, offset, inv_alpha, delta);
                 else rc_check_row<Real, DC, DV, NB>(msgb, slot, c.sched, M, tid, v, normalized, offset, alpha, inv_alpha, delta);
             }
             __syncthreads();
@@ -336,6 +353,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
                 if (it == 0) { if (tid < nblk) gen(fnext, cwn, tid); gen_done = nt; }
                 else { if (gen_id >= 0 && gen_done + gen_id < nblk) gen(fnext, cwn, gen_done + gen_id); gen_done += gen_threads; }
             }
+            if (!last) fetch_schedule();
             __syncthreads();
         }
         finish_frame(c, p, io, f, cw, dbits, fs, p.T, -1, 0, 0, 1, -1, tot);
