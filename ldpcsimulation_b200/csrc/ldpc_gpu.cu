@@ -421,11 +421,12 @@ static int pick_kernel(ldpc_gpu_decoder *d)
         block = std::min(1024, std::max(128, round32(v.M)));
         if (algo == ALGO_MS && d->gstate && v.dv_max <= 8 && v.dc_max <= 64 && !getenv("LDPC_GPU_NO_TILE")) {
             // HBM-bound codes: frame-interleaved tile kernel (ldpc_ms_tile.cuh)
-#define TILE_PICK(DC, NT) (f64 ? (v.idx16 ? (KernelFn)ms_tile_kernel<double, uint16_t, DC, 8, NT> : (KernelFn)ms_tile_kernel<double, uint32_t, DC, 8, NT>) \
-                               : (v.idx16 ? (KernelFn)ms_tile_kernel<float, uint16_t, DC, 8, NT> : (KernelFn)ms_tile_kernel<float, uint32_t, DC, 8, NT>))
-            if (v.dc_max <= 8) { d->fn = TILE_PICK(8, 1024); block = 1024; }      // measured: 1024 > 512 threads per tile
-            else if (v.dc_max <= 32) { d->fn = TILE_PICK(32, 512); block = 512; }
-            else { d->fn = TILE_PICK(64, 256); block = 256; }
+#define TILE_PICK(DC, NT, VB) (f64 ? (v.idx16 ? (KernelFn)ms_tile_kernel<double, uint16_t, DC, 8, NT, (VB < 8 ? 8 : VB)> : (KernelFn)ms_tile_kernel<double, uint32_t, DC, 8, NT, (VB < 8 ? 8 : VB)>) \
+                                   : (v.idx16 ? (KernelFn)ms_tile_kernel<float, uint16_t, DC, 8, NT, VB> : (KernelFn)ms_tile_kernel<float, uint32_t, DC, 8, NT, VB>))
+            // 16-byte accesses where the row fits the register file (dc <= 8: 8 x 16 B per thread in flight)
+            if (v.dc_max <= 8) { d->fn = TILE_PICK(8, 512, 16); block = 512; }
+            else if (v.dc_max <= 32) { d->fn = TILE_PICK(32, 512, 4); block = 512; }
+            else { d->fn = TILE_PICK(64, 256, 4); block = 256; }
 #undef TILE_PICK
             d->frames_per_cta = f64 ? TileFI<double>::value : TileFI<float>::value;
             d->ws_stride = f64 ? ms_tile_state_bytes<double>(v) : ms_tile_state_bytes<float>(v);

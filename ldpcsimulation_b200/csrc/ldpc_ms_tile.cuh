@@ -19,7 +19,15 @@
 
 namespace ldpc {
 
-template <typename Real> struct TileFI { enum { value = 32 / sizeof(Real) }; };
+// Bytes of one (edge, tile) entry = FI * sizeof(Real), and bytes one thread moves per access (FPT frames).
+// 64-byte entries moved as 16-byte vectors: a warp's gather is 8 rows x 64 B = 512 B per instruction, as
+// in a streaming copy.  Measured on DVB-S2 fp32 (profiles/r1_summary.md): 32-byte entries, 4-byte accesses
+// 52 % of the HBM copy peak (all warps in long_scoreboard, 32 KB in flight per SM); 64-byte entries alone +3 %.
+#ifndef LDPC_TILE_BYTES
+#define LDPC_TILE_BYTES 64
+#endif
+template <typename Real> struct TileFI { enum { value = LDPC_TILE_BYTES / sizeof(Real) }; };
+template <typename Real, int W> struct alignas(sizeof(Real) * W) TilePack { Real x[W]; };
 
 template <typename Real>
 static inline size_t ms_tile_state_bytes(const CodeDev &c)
@@ -34,10 +42,12 @@ static inline size_t ms_tile_smem_bytes(const CodeDev &c)
 }
 
 // DCMAX / DVMAX: compile-time bounds of the row / column weights (register arrays).
-template <typename Real, typename IdxT, int DCMAX, int DVMAX, int NT_MAX>
+// VB: bytes one thread moves per access (VB / sizeof(Real) frame lanes per thread).
+template <typename Real, typename IdxT, int DCMAX, int DVMAX, int NT_MAX, int VB>
 __global__ void __launch_bounds__(NT_MAX, 1) ms_tile_kernel(const CodeDev c, const DecParams p, const FrameIO io)
 {
-    constexpr int FI = TileFI<Real>::value;
+    constexpr int FI = TileFI<Real>::value, FPT = VB / (int)sizeof(Real), LPN = FI / FPT;     // LPN: lanes per node
+    typedef TilePack<Real, FPT> PK;
     constexpr int VPL = IdxVec<IdxT>::VPL, NG = (DCMAX + VPL - 1) / VPL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrameScratch *fs = reinterpret_cast<FrameScratch *>(smem_raw);                       // [FI]
@@ -101,55 +111,76 @@ __global__ void __launch_bounds__(NT_MAX, 1) ms_tile_kernel(const CodeDev c, con
         for (int it = 0; it < p.T; it++) {
             const bool last = (it == p.T - 1);
             if (last) for (int w = tid; w < FI * nwords; w += nt) dbits[w] = 0u;
-            // ---- check-node phase: (row, frame lane) per thread -------------------------------------
-            for (int t = tid; t < M * FI; t += nt) {
-                const int j = t / FI, fl = t % FI;
+            // ---- check-node phase: (row, group of FPT frame lanes) per thread ----------------------------
+            for (int t = tid; t < M * LPN; t += nt) {
+                const int j = t / LPN, fl = (t % LPN) * FPT;
                 const int deg = c.cn_deg[j];
                 uint4 w[NG];
 #pragma unroll
                 for (int g = 0; g < NG; g++) if (g * VPL < deg) w[g] = __ldg(&cnv[(size_t)g * M + j]);
-                Real v[DCMAX];
-                Real m1 = INF, m2 = INF;
-                typename SignOps<Real>::acc_t sg = SignOps<Real>::zero();
+                PK v[DCMAX];
 #pragma unroll
-                for (int k = 0; k < DCMAX; k++) if (k < deg) v[k] = msg[(size_t)IdxVec<IdxT>::get(w[k / VPL], k % VPL) * FI + fl];
+                for (int k = 0; k < DCMAX; k++) if (k < deg) v[k] = *reinterpret_cast<const PK *>(&msg[(size_t)IdxVec<IdxT>::get(w[k / VPL], k % VPL) * FI + fl]);
+                Real s1[FPT], s2[FPT], mm[FPT];
+#pragma unroll
+                for (int q = 0; q < FPT; q++) {
+                    Real m1 = INF, m2 = INF;
+                    typename SignOps<Real>::acc_t sg = SignOps<Real>::zero();
+#pragma unroll
+                    for (int k = 0; k < DCMAX; k++) if (k < deg) {
+                        const Real a = absr(v[k].x[q]);
+                        m2 = rmin(m2, rmax(m1, a)); m1 = rmin(m1, a);
+                        SignOps<Real>::fold(sg, v[k].x[q]);
+                    }
+                    Real o1 = m1, o2 = m2;
+                    if (normalized) {
+                        if (sizeof(Real) == 8) { o1 = o1 / alpha; o2 = o2 / alpha; }
+                        else { o1 = o1 * (Real)p.inv_alpha_f; o2 = o2 * (Real)p.inv_alpha_f; }
+                    }
+                    if (offset) { o1 = o1 - delta; o1 = (o1 > 0) ? o1 : (Real)0; o2 = o2 - delta; o2 = (o2 > 0) ? o2 : (Real)0; }
+                    s1[q] = SignOps<Real>::presign(o1, sg); s2[q] = SignOps<Real>::presign(o2, sg); mm[q] = m1;
+                }
 #pragma unroll
                 for (int k = 0; k < DCMAX; k++) if (k < deg) {
-                    const Real a = absr(v[k]);
-                    m2 = rmin(m2, rmax(m1, a)); m1 = rmin(m1, a);
-                    SignOps<Real>::fold(sg, v[k]);
-                }
-                Real o1 = m1, o2 = m2;
-                if (normalized) {
-                    if (sizeof(Real) == 8) { o1 = o1 / alpha; o2 = o2 / alpha; }
-                    else { o1 = o1 * (Real)p.inv_alpha_f; o2 = o2 * (Real)p.inv_alpha_f; }
-                }
-                if (offset) { o1 = o1 - delta; o1 = (o1 > 0) ? o1 : (Real)0; o2 = o2 - delta; o2 = (o2 > 0) ? o2 : (Real)0; }
-                const Real s1 = SignOps<Real>::presign(o1, sg), s2 = SignOps<Real>::presign(o2, sg);
+                    PK o;
 #pragma unroll
-                for (int k = 0; k < DCMAX; k++) if (k < deg) {
-                    const Real sel = (absr(v[k]) == m1) ? s2 : s1;
-                    msg[(size_t)IdxVec<IdxT>::get(w[k / VPL], k % VPL) * FI + fl] = SignOps<Real>::apply(sel, v[k]);
+                    for (int q = 0; q < FPT; q++) {
+                        const Real sel = (absr(v[k].x[q]) == mm[q]) ? s2[q] : s1[q];
+                        o.x[q] = SignOps<Real>::apply(sel, v[k].x[q]);
+                    }
+                    *reinterpret_cast<PK *>(&msg[(size_t)IdxVec<IdxT>::get(w[k / VPL], k % VPL) * FI + fl]) = o;
                 }
             }
             __syncthreads();
-            // ---- variable-node phase: (variable, frame lane) per thread ------------------------------
-            for (int t = tid; t < N * FI; t += nt) {
-                const int i = t / FI, fl = t % FI;
+            // ---- variable-node phase: (variable, group of FPT frame lanes) per thread ---------------------
+            // (two variables per trip was measured slower: 128 registers are not enough for both, 6.3 vs 7.1 Gbit/s)
+            for (int t = tid; t < N * LPN; t += nt) {
+                const int i = t / LPN, fl = (t % LPN) * FPT;
                 const int deg = c.vn_deg[i];
-                Real cm[DVMAX];
-                Real sum = yq[(size_t)i * FI + fl];
+                PK cm[DVMAX];
+                PK sum = *reinterpret_cast<const PK *>(&yq[(size_t)i * FI + fl]);
 #pragma unroll
-                for (int s = 0; s < DVMAX; s++) if (s < deg) cm[s] = msg[((size_t)s * N + i) * FI + fl];
+                for (int s = 0; s < DVMAX; s++) if (s < deg) cm[s] = *reinterpret_cast<const PK *>(&msg[((size_t)s * N + i) * FI + fl]);
 #pragma unroll
-                for (int s = 0; s < DVMAX; s++) if (s < deg) sum += cm[s];                // nlist order
+                for (int s = 0; s < DVMAX; s++) if (s < deg) {                             // nlist order
 #pragma unroll
-                for (int s = 0; s < DVMAX; s++) if (s < deg) msg[((size_t)s * N + i) * FI + fl] = sum - cm[s];
+                    for (int q = 0; q < FPT; q++) sum.x[q] += cm[s].x[q];
+                }
+#pragma unroll
+                for (int s = 0; s < DVMAX; s++) if (s < deg) {
+                    PK o;
+#pragma unroll
+                    for (int q = 0; q < FPT; q++) o.x[q] = sum.x[q] - cm[s].x[q];
+                    *reinterpret_cast<PK *>(&msg[((size_t)s * N + i) * FI + fl]) = o;
+                }
                 if (last) {
-                    if (!(sum > 0)) atomicOr(&dbits[fl * nwords + (i >> 5)], 1u << (i & 31));
-                    if (io.out_soft && f0 + fl < io.n_frames) {
-                        if (io.y_dtype == LDPC_GPU_DT_F64) ((double *)io.out_soft)[(size_t)(f0 + fl) * N + i] = (double)sum;
-                        else ((float *)io.out_soft)[(size_t)(f0 + fl) * N + i] = (float)sum;
+#pragma unroll
+                    for (int q = 0; q < FPT; q++) {
+                        if (!(sum.x[q] > 0)) atomicOr(&dbits[(fl + q) * nwords + (i >> 5)], 1u << (i & 31));
+                        if (io.out_soft && f0 + fl + q < io.n_frames) {
+                            if (io.y_dtype == LDPC_GPU_DT_F64) ((double *)io.out_soft)[(size_t)(f0 + fl + q) * N + i] = (double)sum.x[q];
+                            else ((float *)io.out_soft)[(size_t)(f0 + fl + q) * N + i] = (float)sum.x[q];
+                        }
                     }
                 }
             }

@@ -137,7 +137,7 @@ def test_dvbs2_hbm_resident(variant, prec):
     cfg = cases.cfg_for(variant, num_iterations=12, precision=prec, alpha=(1.25 if "MinSum" in variant else 0.7))
     orc = Oracle("dvbs2")
     dec = capi.Decoder(capi.Code(code_path("dvbs2")), cfg)
-    assert dec.geometry()["smem_bytes"] < 64 * 1024            # state is not in shared memory
+    assert dec.geometry()["smem_bytes"] < 160 * 1024           # messages are not in shared memory (only the tile's packed decisions)
     snr = 1.6 if cfg.kind == abi.KIND_MINSUM else 3.5
     y, noise, rows, cw = cases.make_inputs(orc.N, cfg, snr, 0.5, 3, 17)
     cfg64 = cases.cfg_for(variant, num_iterations=12, alpha=(1.25 if "MinSum" in variant else 0.7))
