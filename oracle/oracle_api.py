@@ -248,6 +248,20 @@ class Reference:
         return out
 
     def run_main(self, argv, stream_seed=1, stdout_path=None):
-        """Run the variant's unmodified main() on the harness's deterministic random() stream."""
-        arr = (C.c_char_p * (len(argv) + 1))(*[a.encode() for a in argv], None)
-        return self.L.ref_run_main(len(argv), arr, stream_seed, None if stdout_path is None else os.fsencode(stdout_path))
+        """Run the variant's unmodified main() on the harness's deterministic random() stream.
+
+        In a FRESH process: the reference keeps its parameters in mutable globals (num_iterations, theta, ...)
+        which main() only partly re-initialises and which earlier ref_decode_batch calls in this process
+        have overwritten."""
+        import subprocess
+        import sys
+        code = ("import ctypes as C, os, sys\n"
+                "L = C.CDLL(sys.argv[1])\n"
+                "L.ref_run_main.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_ulonglong, C.c_char_p]\n"
+                "argv = sys.argv[4:]\n"
+                "arr = (C.c_char_p * (len(argv) + 1))(*[a.encode() for a in argv], None)\n"
+                "out = None if sys.argv[3] == '-' else os.fsencode(sys.argv[3])\n"
+                "sys.exit(L.ref_run_main(len(argv), arr, int(sys.argv[2]), out) & 0xff)\n")
+        lib = os.path.join(HERE, "_ref", "libref_%s.so" % self.variant)
+        r = subprocess.run([sys.executable, "-c", code, lib, str(stream_seed), stdout_path or "-"] + list(argv))
+        return r.returncode
