@@ -30,28 +30,32 @@ template <> struct IdxVec<uint32_t> { enum { VPL = 4 }; static LDPC_DEVINL uint3
 
 template <typename Real> LDPC_DEVINL Real bp_phi(Real x);
 // phi(x) = -ln tanh(x/2) = log1p(2/expm1(x)); phi(0)=inf, phi(inf)=0
-// fp32: two branches, both within a few ulp and far cheaper than log1pf(2/expm1f(x)) (whose IEEE division and
-// special-case paths made the fp32 sum-product row cost ~190 instructions per edge):
-//   e = exp(-x) < 1/4 (x > 1.386):  phi = 2 atanh(e) = 2e (1 + z/3 + z^2/5 + ... + z^6/13), z = e^2 (next term 4e-10);
-//   otherwise:  phi = ln((2 - u)/u), u = 1 - e^-x = -expm1(-x) (no cancellation for small x); here phi >= 0.51,
-//               so the 2^-22 ABSOLUTE error of the hardware log2 (MUFU.LG2) is a relative error below 4e-7.
-template <> __device__ __noinline__ float bp_phi<float>(float x)       // one copy: 64 inlined copies per row overflow the instruction cache (no_instruction 15 % of the samples)
+// fp32: branch-free, on the hardware exp2 / log2 / reciprocal (MUFU), ~20 instructions.  log1pf(2/expm1f(x)) cost
+// ~95 instructions per call with its IEEE division and special-case paths, and a two-branch version diverged on
+// almost every warp (both are in the history of this file; profiles/r1_summary.md).
+//   e = exp(-x) = ex2(-x log2 e)                       (relative error ~2^-22, growing to ~1e-6 only where phi < 1e-6)
+//   e <  0.1 :  phi = 2 atanh(e) = 2e (1 + z/3 + z^2/5), z = e^2                       (next term 1.4e-7)
+//   e >= 0.1 :  phi = ln2 * lg2((2 - u)/u),  u = 1 - e^-x;  phi >= 0.2 there, so the 2^-22 ABSOLUTE error of
+//               MUFU.LG2 is a relative error below 1e-6;  for x < 1/8, where 1 - e cancels, u comes from the series
+//               x (1 - x/2 + x^2/6 - x^3/24 + x^4/120)                                    (next term 4e-8)
+// phi(0) = +inf, phi(inf) = 0.  Accuracy is what tests/test_gpu_parity.py::test_f32_within_tolerance checks: sums
+// within 2e-5 of the frame's largest |LLR| against the double oracle.
+LDPC_DEVINL float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+LDPC_DEVINL float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+LDPC_DEVINL float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <> LDPC_DEVINL float bp_phi<float>(float x)
 {
-    const float e = expf(-x);
-    if (e < 0.25f) {
-        const float z = __fmul_rn(e, e);
-        float q = 7.6923079788684845e-2f;                 // 1/13
-        q = __fmaf_rn(q, z, 9.0909093618392944e-2f);      // 1/11
-        q = __fmaf_rn(q, z, 1.1111111193895340e-1f);      // 1/9
-        q = __fmaf_rn(q, z, 1.4285714924335480e-1f);      // 1/7
-        q = __fmaf_rn(q, z, 2.0000000298023224e-1f);      // 1/5
-        q = __fmaf_rn(q, z, 3.3333334326744080e-1f);      // 1/3
-        q = __fmaf_rn(q, z, 1.0f);
-        return __fmul_rn(__fadd_rn(e, e), q);
-    }
-    const float u = -expm1f(-x);
-    const float r = __fdividef(__fadd_rn(2.0f, -u), u);   // u = 0 (x = 0) -> +inf -> phi = +inf
-    return __fmul_rn(0.693147182464599609375f, __log2f(r));
+    const float e = mufu_ex2(__fmul_rn(x, -1.4426950408889634f));
+    const float z = __fmul_rn(e, e);
+    float a = __fmaf_rn(z, 0.2f, 0.3333333432674408f);
+    a = __fmul_rn(__fadd_rn(e, e), __fmaf_rn(a, z, 1.0f));
+    float pu = __fmaf_rn(x, 8.3333337679505348e-3f, -4.1666667908430099e-2f);
+    pu = __fmaf_rn(pu, x, 1.6666667163372040e-1f);
+    pu = __fmaf_rn(pu, x, -0.5f);
+    pu = __fmul_rn(__fmaf_rn(pu, x, 1.0f), x);
+    const float u = (x < 0.125f) ? pu : __fadd_rn(1.0f, -e);
+    const float b = __fmul_rn(0.693147182464599609375f, mufu_lg2(__fmul_rn(__fadd_rn(2.0f, -u), mufu_rcp(u))));
+    return (e < 0.1f) ? a : b;
 }
 template <> LDPC_DEVINL double bp_phi<double>(double x) { return log1p(2.0 / expm1(x)); }
 
