@@ -24,15 +24,12 @@
 
 namespace ldpc {
 
-template <typename Real> LDPC_DEVINL uint32_t sgbits(typename SignOps<Real>::acc_t a);
-template <> LDPC_DEVINL uint32_t sgbits<float>(uint32_t a) { return a; }
-template <> LDPC_DEVINL uint32_t sgbits<double>(bool a) { return a ? 0x80000000u : 0u; }
-
 template <typename Real> LDPC_DEVINL void fold2(typename SignOps<Real>::acc_t &a, Real x, Real y);
 template <> LDPC_DEVINL void fold2<float>(uint32_t &a, float x, float y) { a = a ^ __float_as_uint(x) ^ __float_as_uint(y); }
 template <> LDPC_DEVINL void fold2<double>(bool &a, double x, double y) { SignOps<double>::fold(a, x); SignOps<double>::fold(a, y); }
 
-// One check row.  The byte displacement from the edge's message word msg[slot*N + col] to S[col] is
+// One check row, any precision (the fp64 parity instantiation uses this one; fp32 uses rc_check_row_f32 below).
+// The byte displacement from the edge's message word msg[slot*N + col] to S[col] is
 // (DV - slot) * NB: the slot-dependent part is folded into each offset by one IMAD (the FMA pipe is idle in
 // this phase, the ALU pipe is the busy one; written as PTX mad so that it is neither hoisted into an
 // ALU-pipe IADD3 nor needs a replicated code path per slot, which thrashed the instruction cache:
@@ -73,36 +70,6 @@ LDPC_DEVINL void rc_check_row(unsigned char *msgb, const int slot, const uint4 *
         else { o1 = o1 * inv_alpha; o2 = o2 * inv_alpha; }
     }
     if (offset) { o1 = o1 - delta; o1 = (o1 > 0) ? o1 : (Real)0; o2 = o2 - delta; o2 = (o2 > 0) ? o2 : (Real)0; }
-    if (sizeof(Real) == 4 && !offset) {
-        // fp32, plain / normalised: the select (|v| == min1) ? min2 : min1 without FSETP + FSEL.  With
-        // t = min(|v|, min2) -- which is min1 exactly when this edge attains the row minimum alone, and
-        // min2 otherwise -- the wanted magnitude has the bit pattern bits(min1) + bits(min2) - bits(t)
-        // (integer arithmetic on the patterns, exact).  Normalisation is then one multiplication per edge
-        // by +-1/alpha carrying the row's sign product: the same rounding of the same operands as scaling
-        // min1 / min2 once per row.  Per edge: FMNMX + LOP3 on the (binding) ALU pipe, IMAD + FMUL on the
-        // otherwise idle FMA pipe, instead of FSETP + FSEL + LOP3 all on the ALU pipe.
-        const float m1f = (float)m1, m2f = (float)m2;
-        const uint32_t K = __float_as_uint(m1f) + __float_as_uint(m2f);
-        const float mult = SignOps<float>::presign(normalized ? (float)inv_alpha : 1.0f, (SignOps<float>::acc_t)sgbits<Real>(sg));
-#pragma unroll
-        for (int g = 0; g < NG; g++) {
-            const uint4 w = __ldg(&sched[(size_t)g * M + j]);
-            const uint32_t off[4] = { w.x, w.y, w.z, w.w };
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int k = g * 4 + q;
-                const float vk = (float)v[k];
-                const float t = fminf(fabsf(vk), m2f);
-                uint32_t rb;
-                asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(rb) : "r"(__float_as_uint(t)), "r"(K));   // K - bits(t), FMA pipe
-                const float o = __fmul_rn(__uint_as_float(rb), mult);
-                const float c2v = SignOps<float>::apply(o, vk);
-                v[k] = (Real)c2v;                                                        // kept for the next iteration
-                *reinterpret_cast<float *>(msgb + off[q]) = c2v;
-            }
-        }
-        return;
-    }
     const Real s1 = SignOps<Real>::presign(o1, sg), s2 = SignOps<Real>::presign(o2, sg);
 #pragma unroll
     for (int g = 0; g < NG; g++) {
@@ -142,7 +109,6 @@ LDPC_DEVINL float min_xorsign_abs(float a, float b)
 //           +-1/alpha (the row's sign product) finishes the message: the same rounding of the same operands
 //           as scaling min1 / min2 once per row.  1 ALU-pipe + 2 FMA-pipe instructions per edge instead of
 //           FSETP + FSEL + LOP3 on the ALU pipe, which is the pipe that bounds this phase.
-// The offset variant keeps the generic second pass (its clamp at zero needs the magnitude).
 template <int DC, int DV, int NB>
 LDPC_DEVINL void rc_check_row_f32(unsigned char *msgb, const int slot, const uint4 (&sw)[RC_NPRE], const uint4 *__restrict__ sched, const int M, const int j, float (&v)[DC],
                                   const bool normalized, const bool offset, const float inv_alpha, const float delta)
@@ -170,29 +136,8 @@ LDPC_DEVINL void rc_check_row_f32(unsigned char *msgb, const int slot, const uin
     }
     const uint32_t sg = __float_as_uint(m1);                                             // bit 31 = the row's sign product
     m1 = fabsf(m1);
-    if (!offset) {
-        const uint32_t K = __float_as_uint(m1) + __float_as_uint(m2);
-        const float mult = SignOps<float>::presign(normalized ? inv_alpha : 1.0f, sg);
-#pragma unroll
-        for (int g = 0; g < NG; g++) {
-            const uint4 w = (g < RC_NPRE) ? sw[g] : __ldg(&sched[(size_t)g * M + j]);
-            const uint32_t off[4] = { w.x, w.y, w.z, w.w };
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int k = g * 4 + q;
-                const float ts = min_xorsign_abs(v[k], m2);
-                uint32_t rb;
-                asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(rb) : "r"(__float_as_uint(ts)), "r"(K));   // K - bits(ts), FMA pipe
-                v[k] = __fmul_rn(__uint_as_float(rb), mult);                             // c2v, kept for the next iteration
-                *reinterpret_cast<float *>(msgb + off[q]) = v[k];
-            }
-        }
-        return;
-    }
-    float o1 = m1, o2 = m2;
-    if (normalized) { o1 = o1 * inv_alpha; o2 = o2 * inv_alpha; }
-    o1 = o1 - delta; o1 = (o1 > 0) ? o1 : 0.0f; o2 = o2 - delta; o2 = (o2 > 0) ? o2 : 0.0f;
-    const float s1 = SignOps<float>::presign(o1, sg), s2 = SignOps<float>::presign(o2, sg);
+    const uint32_t K = __float_as_uint(m1) + __float_as_uint(m2);
+    const float mult = SignOps<float>::presign(normalized ? inv_alpha : 1.0f, sg);
 #pragma unroll
     for (int g = 0; g < NG; g++) {
         const uint4 w = (g < RC_NPRE) ? sw[g] : __ldg(&sched[(size_t)g * M + j]);
@@ -200,9 +145,15 @@ LDPC_DEVINL void rc_check_row_f32(unsigned char *msgb, const int slot, const uin
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int k = g * 4 + q;
-            const float sel = (fabsf(v[k]) == m1) ? s2 : s1;
-            v[k] = SignOps<float>::apply(sel, v[k]);
-            *reinterpret_cast<float *>(msgb + off[q]) = v[k];
+            const float ts = min_xorsign_abs(v[k], m2);
+            uint32_t rb;
+            asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(rb) : "r"(__float_as_uint(ts)), "r"(K));   // K - bits(ts), FMA pipe
+            float o = __fmul_rn(__uint_as_float(rb), mult);
+            // offset min-sum: sgn(o) max(|o| - delta, 0) = o - clamp(o, -delta, +delta), and the clamp is
+            // min.xorsign.abs(o, delta): the same subtraction of the same operands as the reference's, sign-symmetric
+            if (offset) o = __fadd_rn(o, -min_xorsign_abs(o, delta));
+            v[k] = o;                                                                    // c2v, kept for the next iteration
+            *reinterpret_cast<float *>(msgb + off[q]) = o;
         }
     }
 }
