@@ -25,6 +25,7 @@
 #include "ldpc_schedule.h"
 #include "ldpc_ms_tile.cuh"
 #include "ldpc_ms_h2.cuh"
+#include "ldpc_ms_h2rc.cuh"
 #include "ldpc_bf_kernels.cuh"
 
 using namespace ldpc;
@@ -403,6 +404,10 @@ static int pick_kernel(ldpc_gpu_decoder *d)
             d->fn = (KernelFn)ms_h2_kernel<32, 6, 2048, 384, 2>;
             d->frames_per_cta = 2;
             smem = ms_h2_smem_bytes(v); block = 384;
+            if (v.row_slot && !getenv("LDPC_GPU_NO_RC")) {                 // c2v pairs resident in registers (ldpc_ms_h2rc.cuh)
+                d->fn = (KernelFn)ms_h2rc_kernel<32, 6, 2048, 384, 2>;
+                smem = ms_h2rc_smem_bytes(v);
+            }
             goto geometry;
         }
         smem = f64 ? mp_smem_bytes<double>(v, algo) : mp_smem_bytes<float>(v, algo);

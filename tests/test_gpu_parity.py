@@ -191,6 +191,23 @@ def test_register_resident_c2v_kernel_equals_scheduled_kernel(variant, prec, mon
         assert np.array_equal(a.soft, b.soft) and a.counters == b.counters
 
 
+@pytest.mark.parametrize("variant", ["decodeNormalizedMinSum", "decodeOffsetMinSum", "decodeMinSum"])
+def test_f16x2_register_resident_kernel_equals_f16x2_scheduled_kernel(variant, monkeypatch):
+    """ms_h2rc_kernel reorganises ms_h2_kernel (c2v pairs in registers, sums published by the variable phase,
+    xorsign minima, integer-pattern select) without changing a single binary16 operation: bit-identical outputs."""
+    R, snr = 0.8413, 3.9
+    code = capi.Code(code_path("802_3_H"))
+    cws = code.random_codewords(9, 4)
+    for T, F in ((0, 6), (1, 7), (10, 41)):
+        cfg = cases.cfg_for(variant, code="802_3_H", num_iterations=T, precision=abi.PREC_F16X2)
+        y, noise, rows, cw = cases.make_inputs(2048, cfg, snr, R, F, 77 + T, cws if T else None)
+        monkeypatch.delenv("LDPC_GPU_NO_RC", raising=False)
+        a = capi.Decoder(code, cfg).decode(snr, R, y, codeword=cw)
+        monkeypatch.setenv("LDPC_GPU_NO_RC", "1")
+        b = capi.Decoder(code, cfg).decode(snr, R, y, codeword=cw)
+        assert np.array_equal(a.bits, b.bits) and np.array_equal(a.soft, b.soft) and a.counters == b.counters
+
+
 def test_fp16_sample_input_equals_fp32_input_of_the_same_values():
     """LDPC_GPU_DT_F16 only changes how the samples travel: binary16 -> fp32 is exact."""
     cfg = cases.cfg_for("decodeNormalizedMinSum", precision=abi.PREC_F32)
