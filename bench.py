@@ -108,6 +108,16 @@ def profiled_traffic():
         return None
 
 
+def profiled_metric(name):
+    """One metric of the committed ncu capture (PROFILE_CSV); None if absent."""
+    import csv
+    try:
+        rows = list(csv.reader(open(os.path.join(ROOT, PROFILE_CSV))))
+        return float(rows[2][rows[0].index(name)])
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -370,7 +380,11 @@ def main():
                      "note": "messages never leave the SM (shared memory): DRAM traffic is nil, so algorithmic message bytes over "
                              "kernel time exceed the HBM copy peak; the binding resources are shared-memory wavefronts, the ALU pipe "
                              "and issue slots (DESIGN.md section 3, profiles/r1_summary.md)"},
-        "onchip": {"edge_updates_per_s": 2.0 * E_EDGES * WORKLOAD["T"] * F * args.steps / (kernel_ms * 1e-3) if kernel_ms > 0 else None,
+        "onchip": {"profiled_l1tex_pct_of_peak": profiled_metric("l1tex__throughput.avg.pct_of_peak_sustained_active"),
+                   "profiled_issue_active_pct": profiled_metric("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                   "profiled_shared_wavefronts_pct_of_peak": profiled_metric("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+                   "profile": PROFILE_CSV,
+                   "edge_updates_per_s": 2.0 * E_EDGES * WORKLOAD["T"] * F * args.steps / (kernel_ms * 1e-3) if kernel_ms > 0 else None,
                    "issue_slots_per_edge_iteration": (148 * 4 * 32 * 1.965e9) / (E_EDGES * WORKLOAD["T"] * F * args.steps / (kernel_ms * 1e-3)) if kernel_ms > 0 else None},
         "geometry": geo, "counters": total, "ber": total["errors"] / max(1, total["totalBits"]),
         "fer": total["wordErrors"] / max(1, total["totalWords"]),
