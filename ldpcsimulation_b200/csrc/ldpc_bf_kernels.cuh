@@ -290,6 +290,11 @@ __global__ void gdbf_par_kernel(const CodeDev c, const DecParams p, const FrameI
     const bool redecode = (fl & LDPC_GPU_F_REDECODE) != 0;
     const int maxphase = redecode ? (p.maxphase > 0 ? p.maxphase : 1) : 1;
     const Real theta0 = (Real)p.theta, lambda = (Real)p.lambda, noiseSigma = (Real)p.noiseSigma;
+    // regular codes: the column weight and the syndrome weight are per-launch constants (the weight of -D redecode
+    // is a double division per variable and iteration otherwise, src/RNGDBF.cpp:566)
+    const int reg_dv = c.regular_dv;
+    const Real wgt_reg = !(fl & LDPC_GPU_F_WEIGHTSYNDROMES) ? (Real)1
+                         : (redecode ? (Real)(p.alpha * p.Ymax / (double)(reg_dv > 0 ? reg_dv : 1)) : (Real)p.alpha);
     CtaTotals tot; tot.clear();
 
     for (int e = tid; e < dvm * N; e += nt) chk[e] = (uint16_t)c.vn_chk[e];
@@ -374,11 +379,11 @@ __global__ void gdbf_par_kernel(const CodeDev c, const DecParams p, const FrameI
                     for (int q = 0; q < 4; q++) {
                         const int i = 4 * b + q;
                         if (i >= N) break;
-                        const int deg = c.vn_deg[i];
+                        const int deg = reg_dv > 0 ? reg_dv : (int)c.vn_deg[i];
                         const bool dneg = (dword >> ((4 * b + q) & 31)) & 1u;
                         Real E = dneg ? -yq[i] : yq[i];                              // d[i]*y[i]
-                        Real wgt = (Real)1;
-                        if (fl & LDPC_GPU_F_WEIGHTSYNDROMES)
+                        Real wgt = wgt_reg;
+                        if (reg_dv <= 0 && (fl & LDPC_GPU_F_WEIGHTSYNDROMES))
                             wgt = redecode ? (Real)(p.alpha * p.Ymax / (double)deg) : (Real)p.alpha;   // RNGDBF.cpp:566 / decodeGDBF.cpp:550
                         for (int sl = 0; sl < deg; sl++) { const int j = chk[sl * N + i]; E += ((syn[j >> 5] >> (j & 31)) & 1u) ? -wgt : wgt; }
                         if (row_pert >= 0) {
