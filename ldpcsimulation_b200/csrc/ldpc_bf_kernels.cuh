@@ -271,6 +271,8 @@ static inline size_t gdbf_par_smem_bytes(const CodeDev &c)
     return (n + 15) & ~(size_t)15;
 }
 
+template <typename Real> struct alignas(16) GdbfPack4 { Real x[4]; };
+
 template <typename Real>
 __global__ void gdbf_par_kernel(const CodeDev c, const DecParams p, const FrameIO io)
 {
@@ -295,6 +297,7 @@ __global__ void gdbf_par_kernel(const CodeDev c, const DecParams p, const FrameI
     const int reg_dv = c.regular_dv;
     const Real wgt_reg = !(fl & LDPC_GPU_F_WEIGHTSYNDROMES) ? (Real)1
                          : (redecode ? (Real)(p.alpha * p.Ymax / (double)(reg_dv > 0 ? reg_dv : 1)) : (Real)p.alpha);
+    const bool vec_ok = reg_dv > 0 && (N & 3) == 0 && (reinterpret_cast<size_t>(chk) & 7) == 0;
     CtaTotals tot; tot.clear();
 
     for (int e = tid; e < dvm * N; e += nt) chk[e] = (uint16_t)c.vn_chk[e];
@@ -375,6 +378,53 @@ __global__ void gdbf_par_kernel(const CodeDev c, const DecParams p, const FrameI
                     }
                     const uint32_t dword = dbits[(4 * b) >> 5];
                     uint32_t flipmask = 0;
+                    if (vec_ok) {
+                        // regular code, N % 4 == 0: the four variables of the thread move as vectors (one 16-byte access
+                        // for y and theta, one 8-byte access per slot for the four check indices) instead of scalar accesses
+                        // at a 16-byte lane stride (4-way bank conflicts: 42 % of the wavefronts were replays)
+                        const int i0 = 4 * b;
+                        const uint32_t d4 = (dword >> (i0 & 31)) & 15u;
+                        const GdbfPack4<Real> y4v = *reinterpret_cast<const GdbfPack4<Real> *>(&yq[i0]);
+                        GdbfPack4<Real> th4 = *reinterpret_cast<const GdbfPack4<Real> *>(&theta[i0]);
+                        Real E[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) E[q] = ((d4 >> q) & 1u) ? -y4v.x[q] : y4v.x[q];     // d[i]*y[i]
+                        for (int sl = 0; sl < reg_dv; sl++) {                                        // nlist order, per variable
+                            const uint2 c4 = *reinterpret_cast<const uint2 *>(&chk[sl * N + i0]);
+                            const int j4[4] = { (int)(c4.x & 0xffffu), (int)(c4.x >> 16), (int)(c4.y & 0xffffu), (int)(c4.y >> 16) };
+#pragma unroll
+                            for (int q = 0; q < 4; q++) E[q] += ((syn[j4[q] >> 5] >> (j4[q] & 31)) & 1u) ? -wgt_reg : wgt_reg;
+                        }
+                        bool th_dirty = false;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int i = i0 + q;
+                            const bool dneg = (d4 >> q) & 1u;
+                            if (row_pert >= 0) {
+                                Real smp = (fl & LDPC_GPU_F_UNIFORMNOISE) ? (Real)(p.uni_scale * (pert4[q] - 0.5)) : (Real)(p.noiseSigma * pert4[q]);
+                                if (fl & LDPC_GPU_F_NOISESHAPING) { const Real prev = shape[i]; shape[i] = smp; smp = smp - prev; }
+                                E[q] += smp;
+                            }
+                            bool flip;
+                            if (fl & LDPC_GPU_F_QUANTIZEPROBABILITIES) {               // :561-597
+                                const double val = ((double)(-E[q] + th4.x[q])) / (double)noiseSigma;
+                                const double pcdf = 0.5 * erfc(-val * 0.70710678118654752440);
+                                const double lv[8] = { 0, 0.0625, 0.125, 0.25, 0.34375, 0.4106, 0.68359, 1 };
+                                double md = 1; int mi = 0;
+#pragma unroll
+                                for (int l = 0; l < 8; l++) { double t = lv[l] - pcdf; t = t * t; if (t < md) { md = t; mi = l; } }
+                                flip = unif4[q] < lv[mi];
+                            } else flip = E[q] < th4.x[q];                               // mu == 1
+                            if (flip) {
+                                flipmask |= 1u << q;
+                                for (int sl = 0; sl < reg_dv; sl++) { const int j = chk[sl * N + i]; atomicXor(&tog[j >> 5], 1u << (j & 31)); }
+                            } else if (fl & LDPC_GPU_F_THRESHOLDADAPTATION) { th4.x[q] *= lambda; th_dirty = true; }   // :612-617
+                            if (smooth_now) dsum[i] += (dneg != flip) ? -1 : 1;                   // :348-354, d after the flip
+                        }
+                        if (th_dirty) *reinterpret_cast<GdbfPack4<Real> *>(&theta[i0]) = th4;
+                        if (flipmask) atomicXor(&dbits[i0 >> 5], flipmask << (i0 & 31));
+                        continue;
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const int i = 4 * b + q;
