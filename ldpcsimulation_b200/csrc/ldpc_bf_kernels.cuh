@@ -517,6 +517,7 @@ __global__ void hw_kernel(const CodeDev c, const DecParams p, const FrameIO io)
     signed char *qval = yval + N;                                       // unpack(q')
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const int maxPhases = p.maxphase > 0 ? p.maxphase : 1;
+    const int reg_dv = c.regular_dv;                                    // regular codes: no per-variable weight load
     CtaTotals tot; tot.clear();
 
     for (int e = tid; e < dvm * N; e += nt) chk[e] = (uint16_t)c.vn_chk[e];      // once per CTA: the graph, variable side
@@ -598,7 +599,7 @@ __global__ void hw_kernel(const CodeDev c, const DecParams p, const FrameIO io)
                     const uint32_t dw = dbits[i0 >> 5];
                     bool nd = (dw >> lane) & 1u;
                     if (valid) {
-                        const int deg = c.vn_deg[i0];
+                        const int deg = reg_dv > 0 ? reg_dv : (int)c.vn_deg[i0];
                         const int d01 = (int)nd;
                         int sat = 0;
                         for (int sl = 0; sl < deg; sl++) { const int j = chk[sl * N + i0]; sat += 1 - (int)((syn[j >> 5] >> (j & 31)) & 1u); }
