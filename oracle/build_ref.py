@@ -37,6 +37,9 @@ VARIANTS = {
     "decodeSeqATGDBF":         ("decodeGDBF.cpp", "HARNESS_GDBF", ["sequentialmode", "thresholdAdaptation"]),    # exercises the running-minimum quirk
     "decodeRSMNGDBF":          ("RNGDBF.cpp", "HARNESS_GDBF", ["redecode", "addNoise", "thresholdAdaptation", "weightSyndromes", "outputSmoothing", "saturateSamples"]),  # :45
     "NGDBFhw":                 ("NGDBFhw.cpp", "HARNESS_HW", []),                                        # scripts/demo_NGDBFhw_802_3.sh:24
+    # per-frame outcomes over NR re-decodes.  The Makefile's `redecodeStatistics` goal builds newstat.cpp
+    # (GSL); src/redecodeStatistics.cpp is the GSL-free program of the same purpose and compiles on its own.  main() only.
+    "redecodeStatistics":      ("redecodeStatistics.cpp", "HARNESS_MAINONLY", ["addNoise", "thresholdAdaptation", "weightSyndromes", "outputSmoothing", "saturateSamples"]),
 }
 
 

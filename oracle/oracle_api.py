@@ -248,6 +248,10 @@ class Reference:
         return out
 
     def run_main(self, argv, stream_seed=1, stdout_path=None):
+        return Reference.main(self.variant, argv, stream_seed, stdout_path)
+
+    @staticmethod
+    def main(variant, argv, stream_seed=1, stdout_path=None):
         """Run the variant's unmodified main() on the harness's deterministic random() stream.
 
         In a FRESH process: the reference keeps its parameters in mutable globals (num_iterations, theta, ...)
@@ -262,6 +266,6 @@ class Reference:
                 "arr = (C.c_char_p * (len(argv) + 1))(*[a.encode() for a in argv], None)\n"
                 "out = None if sys.argv[3] == '-' else os.fsencode(sys.argv[3])\n"
                 "sys.exit(L.ref_run_main(len(argv), arr, int(sys.argv[2]), out) & 0xff)\n")
-        lib = os.path.join(HERE, "_ref", "libref_%s.so" % self.variant)
+        lib = os.path.join(HERE, "_ref", "libref_%s.so" % variant)
         r = subprocess.run([sys.executable, "-c", code, lib, str(stream_seed), stdout_path or "-"] + list(argv))
         return r.returncode

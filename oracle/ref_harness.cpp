@@ -54,6 +54,10 @@ extern "C" long random(void)
 }
 extern "C" void srandom(unsigned int) { /* the seed is owned by the harness */ }
 
+#ifdef HARNESS_MAINONLY
+// Tools whose functions are file-specific (redecodeStatistics.cpp): only the random() shim and ref_run_main().
+int ref_main(int argc, char *argv[]);
+#else
 // ---- prototypes of the reference functions (external linkage in the reference TU) ---------
 int countDecisionErrors(vector<int> d, vector<int> c);
 #if defined(HARNESS_MS)
@@ -471,6 +475,8 @@ extern "C" int ref_decode_batch(const char *alist_path, const ldpc_gpu_decoder_c
 #endif
     return 0;
 }
+
+#endif  // HARNESS_MAINONLY
 
 // ---- whole-program run of the reference's main() on the shim's deterministic stream -------
 // argv is the variant's own positional command line.  stdout is silenced; the TSV line the

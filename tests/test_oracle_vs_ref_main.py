@@ -176,3 +176,36 @@ def test_ngdbfhw_main_totals(tmp_path):
     assert ref[1] == str(tot["errors"]) and ref[2] == str(tot["wordErrors"])
     assert ref[4] == _fmt(tot["totalIterations"] / tot["totalWords"])
     assert ref[6:8] == [str(tot["totalBits"]), str(tot["totalWords"])]
+
+
+def test_redecode_statistics_outcome_matrix(tmp_path):
+    """SURVEY.md 8(f) N2.  src/redecodeStatistics.cpp decodes every received frame NR times from the same channel
+    samples with fresh perturbation noise and logs one row of NR error weights per frame.  Replayed on the same
+    random() stream through the oracle: one RSMNGDBF decode with maxphase = 1 per re-decode (the file's symNodeUpdates
+    uses RNGDBF's weight alpha*Ymax/dv, :543-546), noise rows consumed only for the iterations that ran."""
+    code, R, snr, T, NR, NF = "PEG", 0.5, 4.2, 40, 4, 9
+    log = str(tmp_path / "outcomes.txt")
+    argv = ["redecodeStatistics", code_path(code), str(R), str(snr), str(T), str(NR), str(NF), "-0.9", log, "0.975", "0.988", "1.0", "4", "2.5"]
+    assert Reference.main("redecodeStatistics", argv, 31337) == 0
+    ref_rows = [[int(t) for t in line.split()] for line in open(log).read().strip().splitlines()]
+    assert len(ref_rows) == NF and all(len(r) == NR for r in ref_rows)
+    cfg = abi.default_cfg(abi.KIND_GDBF, flags=["redecode", "addNoise", "thresholdAdaptation", "weightSyndromes", "outputSmoothing", "saturateSamples"],
+                          num_iterations=T, theta=-0.9, noiseScale=0.975, alpha=1.0, windowsize=4, Ymax=2.5, maxphase=1, **{"lambda": 0.988})
+    orc = Oracle(code)
+    N = orc.N
+    sh = Shim(31337)
+    sigma = cases.sigma_of(snr, R)
+    mine = []
+    for f in range(NF):
+        y = np.array([1.0 + sigma * sh.rann() for _ in range(N)])[None, :]
+        row = []
+        for r in range(NR):
+            look = sh.copy()
+            noise = np.array([[look.rann() for _ in range(N)] for _ in range(T)])[None, :, :]
+            out = orc.decode(cfg, snr, R, y, noise, T, None)
+            for _ in range(int(out.iters[0]) * N):
+                sh.rann()
+            row.append(int(out.errors[0]))
+        mine.append(row)
+    assert mine == ref_rows
+    assert any(any(r) for r in ref_rows) and any(not all(r) for r in ref_rows)       # both outcomes occur
