@@ -223,6 +223,15 @@ int  ldpc_gpu_decode_batch(ldpc_gpu_decoder *dec, const ldpc_gpu_channel *ch,
 int  ldpc_gpu_simulate(ldpc_gpu_decoder *dec, const ldpc_gpu_channel *ch,
                        const ldpc_gpu_sim_args *args, ldpc_gpu_counters *counters);
 
+/* Re-decode statistics (replaces src/redecodeStatistics.cpp:262-395, the GSL-free program of
+ * the Makefile goal `redecodeStatistics`): every frame of [frame_begin, frame_begin + n_frames) is decoded
+ * n_redecodes times from the same Philox channel samples, each time with fresh decoder noise (GDBF family with
+ * addNoise / quantizeProbabilities, NGDBFhw), every decode run to its own end as the reference does.
+ * outcomes: HOST [n_frames][n_redecodes] error weights (0 = decoded), the rows the reference appends to its log.
+ * counters (optional) accumulate over all n_frames * n_redecodes decodes. */
+int  ldpc_gpu_redecode_stats(ldpc_gpu_decoder *dec, const ldpc_gpu_channel *ch, const ldpc_gpu_sim_args *args,
+                             int32_t n_redecodes, int32_t *outcomes, ldpc_gpu_counters *counters);
+
 /* The exact samples ldpc_gpu_simulate feeds its decoder for frames
  * [frame_begin, frame_begin+n_frames): y is HOST [F][N] doubles.  noise, if
  * non-NULL, receives the decoder-side raw RNG outputs in ldpc_gpu_batch layout

@@ -20,7 +20,7 @@ EXPORTS = [
     "ldpc_gpu_code_create", "ldpc_gpu_code_load_alist", "ldpc_gpu_code_dims", "ldpc_gpu_code_destroy",
     "ldpc_gpu_code_random_codewords",
     "ldpc_gpu_decoder_cfg_default", "ldpc_gpu_decoder_create", "ldpc_gpu_decoder_destroy",
-    "ldpc_gpu_decoder_set_codewords", "ldpc_gpu_decode_batch", "ldpc_gpu_simulate", "ldpc_gpu_channel_dump",
+    "ldpc_gpu_decoder_set_codewords", "ldpc_gpu_decode_batch", "ldpc_gpu_simulate", "ldpc_gpu_redecode_stats", "ldpc_gpu_channel_dump",
     "ldpc_gpu_philox4x32", "ldpc_gpu_last_timing", "ldpc_gpu_decoder_geometry",
     "ldpc_gpu_comm_unique_id", "ldpc_gpu_comm_init", "ldpc_gpu_comm_destroy", "ldpc_gpu_allreduce_counters",
 ]
@@ -54,6 +54,8 @@ def lib():
         L.ldpc_gpu_decoder_set_codewords.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.ldpc_gpu_decode_batch.argtypes = [C.c_void_p, C.POINTER(abi.Channel), C.POINTER(abi.Batch), C.POINTER(abi.Counters)]
         L.ldpc_gpu_simulate.argtypes = [C.c_void_p, C.POINTER(abi.Channel), C.POINTER(abi.SimArgs), C.POINTER(abi.Counters)]
+        L.ldpc_gpu_redecode_stats.argtypes = [C.c_void_p, C.POINTER(abi.Channel), C.POINTER(abi.SimArgs), C.c_int32, C.c_void_p,
+                                              C.POINTER(abi.Counters)]
         L.ldpc_gpu_channel_dump.argtypes = [C.c_void_p, C.POINTER(abi.Channel), C.c_uint64, C.c_int64, C.c_int64,
                                             C.c_void_p, C.c_void_p, C.c_int64]
         L.ldpc_gpu_philox4x32.argtypes = [C.c_void_p] * 3
@@ -201,6 +203,16 @@ class Decoder:
         r.update(hist)
         r["_cnt"] = cnt
         return r
+
+    def redecode_stats(self, snr_db, R, seed, frame_begin, n_frames, n_redecodes):
+        """[n_frames][n_redecodes] error weights of n_redecodes decodes of every frame (same channel, fresh decoder noise)
+        and the counters accumulated over all of them."""
+        ch = abi.Channel(snr_db, R)
+        a = abi.SimArgs(seed, frame_begin, n_frames, 0, 0, 0)
+        cnt, hist = self._counters()
+        out = np.zeros((n_frames, n_redecodes), np.int32)
+        check(lib().ldpc_gpu_redecode_stats(self.h, C.byref(ch), C.byref(a), int(n_redecodes), _ptr(out), C.byref(cnt)))
+        return out, cnt.as_dict()
 
     def channel_dump(self, snr_db, R, seed, frame_begin, n_frames, noise_rows=None):
         ch = abi.Channel(snr_db, R)

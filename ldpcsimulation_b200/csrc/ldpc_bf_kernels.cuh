@@ -162,8 +162,8 @@ __global__ void gdbf_kernel(const CodeDev c, const DecParams p, const FrameIO io
                         if (io.noise) {
 #pragma unroll
                             for (int q = 0; q < 4; q++) if (4 * b + q < N) pert4[q] = io.noise[((size_t)f * io.noise_rows + row_pert) * N + 4 * b + q];
-                        } else if (fl & LDPC_GPU_F_UNIFORMNOISE) uniform4(io.seed, fid, (uint32_t)b, (uint32_t)row_pert, STREAM_DECODER, pert4);
-                        else { float n4[4]; normal4(io.seed, fid, (uint32_t)b, (uint32_t)row_pert, STREAM_DECODER, n4);
+                        } else if (fl & LDPC_GPU_F_UNIFORMNOISE) uniform4(io.seed, fid, (uint32_t)b, (uint32_t)(row_pert + io.noise_row_base), STREAM_DECODER, pert4);
+                        else { float n4[4]; normal4(io.seed, fid, (uint32_t)b, (uint32_t)(row_pert + io.noise_row_base), STREAM_DECODER, n4);
 #pragma unroll
                                for (int q = 0; q < 4; q++) pert4[q] = (double)n4[q]; }
                     }
@@ -171,7 +171,7 @@ __global__ void gdbf_kernel(const CodeDev c, const DecParams p, const FrameIO io
                         if (io.noise) {
 #pragma unroll
                             for (int q = 0; q < 4; q++) if (4 * b + q < N) unif4[q] = io.noise[((size_t)f * io.noise_rows + row_unif) * N + 4 * b + q];
-                        } else uniform4(io.seed, fid, (uint32_t)b, (uint32_t)row_unif, STREAM_DECODER, unif4);
+                        } else uniform4(io.seed, fid, (uint32_t)b, (uint32_t)(row_unif + io.noise_row_base), STREAM_DECODER, unif4);
                     }
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
@@ -365,8 +365,8 @@ __global__ void gdbf_par_kernel(const CodeDev c, const DecParams p, const FrameI
                         if (io.noise) {
 #pragma unroll
                             for (int q = 0; q < 4; q++) if (4 * b + q < N) pert4[q] = io.noise[((size_t)f * io.noise_rows + row_pert) * N + 4 * b + q];
-                        } else if (fl & LDPC_GPU_F_UNIFORMNOISE) uniform4(io.seed, fid, (uint32_t)b, (uint32_t)row_pert, STREAM_DECODER, pert4);
-                        else { float n4[4]; normal4(io.seed, fid, (uint32_t)b, (uint32_t)row_pert, STREAM_DECODER, n4);
+                        } else if (fl & LDPC_GPU_F_UNIFORMNOISE) uniform4(io.seed, fid, (uint32_t)b, (uint32_t)(row_pert + io.noise_row_base), STREAM_DECODER, pert4);
+                        else { float n4[4]; normal4(io.seed, fid, (uint32_t)b, (uint32_t)(row_pert + io.noise_row_base), STREAM_DECODER, n4);
 #pragma unroll
                                for (int q = 0; q < 4; q++) pert4[q] = (double)n4[q]; }
                     }
@@ -374,7 +374,7 @@ __global__ void gdbf_par_kernel(const CodeDev c, const DecParams p, const FrameI
                         if (io.noise) {
 #pragma unroll
                             for (int q = 0; q < 4; q++) if (4 * b + q < N) unif4[q] = io.noise[((size_t)f * io.noise_rows + row_unif) * N + 4 * b + q];
-                        } else uniform4(io.seed, fid, (uint32_t)b, (uint32_t)row_unif, STREAM_DECODER, unif4);
+                        } else uniform4(io.seed, fid, (uint32_t)b, (uint32_t)(row_unif + io.noise_row_base), STREAM_DECODER, unif4);
                     }
                     const uint32_t dword = dbits[(4 * b) >> 5];
                     uint32_t flipmask = 0;
@@ -554,7 +554,7 @@ __global__ void hw_kernel(const CodeDev c, const DecParams p, const FrameIO io)
             if (io.noise) {
 #pragma unroll
                 for (int q = 0; q < 4; q++) n4[q] = (4 * b + q < QB) ? io.noise[(size_t)f * QB + 4 * b + q] : 0.0;
-            } else { float nf[4]; normal4(io.seed, fid, (uint32_t)b, 0u, STREAM_DECODER, nf);
+            } else { float nf[4]; normal4(io.seed, fid, (uint32_t)b, (uint32_t)io.noise_row_base, STREAM_DECODER, nf);
 #pragma unroll
                      for (int q = 0; q < 4; q++) n4[q] = (double)nf[q]; }
 #pragma unroll

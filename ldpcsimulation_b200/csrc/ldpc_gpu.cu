@@ -823,6 +823,59 @@ extern "C" int ldpc_gpu_simulate(ldpc_gpu_decoder *d, const ldpc_gpu_channel *ch
 }
 
 // ------------------------------------------------------------------------------------------------
+// re-decode statistics (src/redecodeStatistics.cpp): every frame of the range is decoded
+// n_redecodes times from the SAME channel samples, each time with fresh decoder noise, and the error weight of
+// every outcome is recorded.  The channel is a function of (seed, frame id) and re-decode r draws the rows
+// r * rows_per_decode ... of the frame's decoder-noise stream, so the matrix is reproducible entry by entry.
+// ------------------------------------------------------------------------------------------------
+extern "C" int ldpc_gpu_redecode_stats(ldpc_gpu_decoder *d, const ldpc_gpu_channel *ch, const ldpc_gpu_sim_args *a, int32_t n_redecodes,
+                                       int32_t *outcomes, ldpc_gpu_counters *cnt)
+{
+    if (!d || !a || !outcomes) return set_err(LDPC_GPU_ERR_INVALID_ARG, "NULL argument");
+    if (a->n_frames < 0 || n_redecodes < 1) return set_err(LDPC_GPU_ERR_INVALID_ARG, "n_frames < 0 or n_redecodes < 1");
+    if (d->cfg.kind != LDPC_GPU_KIND_GDBF && d->cfg.kind != LDPC_GPU_KIND_NGDBF_HW)
+        return set_err(LDPC_GPU_ERR_UNSUPPORTED, "re-decode statistics need a decoder with its own noise (GDBF family, NGDBFhw)");
+    DecParams p; int rc = channel_params(d, ch, p); if (rc) return rc;
+    CU_TRY(cudaSetDevice(d->device));
+    cudaStream_t st = d->slot[0].st;
+    d->last_kernel_ms = 0; d->last_launches = 0;
+    if ((rc = zero_counters(d, st))) return rc;
+    long long rows_per_decode = 1;                                    // NGDBFhw: one noise buffer per decode
+    if (d->cfg.kind == LDPC_GPU_KIND_GDBF) {
+        const uint32_t f = d->cfg.flags;
+        const long long per_step = ((f & LDPC_GPU_F_ADDNOISE) ? 1 : 0) + ((f & LDPC_GPU_F_QUANTIZEPROBABILITIES) ? 1 : 0);
+        const long long ph = ((f & LDPC_GPU_F_REDECODE) && d->cfg.maxphase > 1) ? d->cfg.maxphase : 1;
+        rows_per_decode = std::max<long long>(1, per_step * (long long)d->cfg.num_iterations * ph);
+    }
+    const long long per_launch = std::min<long long>(std::max<long long>(a->n_frames, 1), 1ll << 20);
+    int *d_err = nullptr;
+    CU_TRY(cudaMalloc(&d_err, sizeof(int) * (size_t)per_launch));
+    std::vector<int> h_err((size_t)per_launch);
+    FrameIO io; memset(&io, 0, sizeof io);
+    io.seed = a->seed; io.cw_table = d->d_cwtab; io.n_cw = d->n_cw;
+    io.counters = d->d_counters; io.ew_hist = d->d_ew; io.it_hist = d->d_it; io.ph_hist = d->d_ph;
+    io.out_errors = d_err;
+    CU_TRY(cudaEventRecord(d->slot[0].k0, st));
+    for (long long done = 0; done < a->n_frames && !rc; done += per_launch) {
+        const long long nf = std::min<long long>(per_launch, a->n_frames - done);
+        io.n_frames = nf; io.frame_begin = a->frame_begin + done;
+        for (int r = 0; r < n_redecodes && !rc; r++) {
+            io.noise_row_base = (long long)r * rows_per_decode;
+            if ((rc = launch(d, p, io, st))) break;
+            if (cudaMemcpyAsync(h_err.data(), d_err, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaStreamSynchronize(st) != cudaSuccess) { rc = set_err(LDPC_GPU_ERR_CUDA, "copying the outcomes failed"); break; }
+            for (long long f = 0; f < nf; f++) outcomes[(size_t)(done + f) * n_redecodes + r] = h_err[(size_t)f];
+        }
+    }
+    cudaEventRecord(d->slot[0].k1, st);
+    cudaFree(d_err);
+    if (rc) return rc;
+    if (cnt) rc = fetch_counters(d, cnt, st); else CU_TRY(cudaStreamSynchronize(st));
+    float ms = 0; cudaEventElapsedTime(&ms, d->slot[0].k0, d->slot[0].k1); d->last_kernel_ms = ms;
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
 // channel dump: the samples the throughput entry feeds its decoder
 // ------------------------------------------------------------------------------------------------
 __global__ void dump_kernel(const CodeDev c, const DecParams p, const FrameIO io)
@@ -839,7 +892,7 @@ __global__ void dump_kernel(const CodeDev c, const DecParams p, const FrameIO io
         if (!io.dump_noise) continue;
         if (p.kind == LDPC_GPU_KIND_NGDBF_HW) {
             for (int b = threadIdx.x; b < (LDPC_GPU_HW_QBUF + 3) / 4; b += blockDim.x) {
-                float n4[4]; normal4(io.seed, fid, (uint32_t)b, 0u, STREAM_DECODER, n4);
+                float n4[4]; normal4(io.seed, fid, (uint32_t)b, (uint32_t)io.noise_row_base, STREAM_DECODER, n4);
                 for (int q = 0; q < 4; q++) if (4 * b + q < LDPC_GPU_HW_QBUF) io.dump_noise[(size_t)f * LDPC_GPU_HW_QBUF + 4 * b + q] = (double)n4[q];
             }
         } else if (p.kind == LDPC_GPU_KIND_GDBF && p.rows_per_step > 0) {
@@ -848,8 +901,8 @@ __global__ void dump_kernel(const CodeDev c, const DecParams p, const FrameIO io
                 const bool uniform = !(which == 0 && (p.flags & LDPC_GPU_F_ADDNOISE)) || (p.flags & LDPC_GPU_F_UNIFORMNOISE);
                 for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
                     double v[4];
-                    if (uniform) uniform4(io.seed, fid, (uint32_t)b, (uint32_t)row, STREAM_DECODER, v);
-                    else { float n4[4]; normal4(io.seed, fid, (uint32_t)b, (uint32_t)row, STREAM_DECODER, n4); for (int q = 0; q < 4; q++) v[q] = (double)n4[q]; }
+                    if (uniform) uniform4(io.seed, fid, (uint32_t)b, (uint32_t)(row + io.noise_row_base), STREAM_DECODER, v);
+                    else { float n4[4]; normal4(io.seed, fid, (uint32_t)b, (uint32_t)(row + io.noise_row_base), STREAM_DECODER, n4); for (int q = 0; q < 4; q++) v[q] = (double)n4[q]; }
                     for (int q = 0; q < 4; q++) if (4 * b + q < N) io.dump_noise[((size_t)f * io.noise_rows + row) * N + 4 * b + q] = v[q];
                 }
             }

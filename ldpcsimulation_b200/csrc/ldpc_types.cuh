@@ -78,6 +78,8 @@ struct FrameIO {
     unsigned long long *it_hist;  // device [iter_hist_len] or NULL
     unsigned long long *ph_hist;  // device [maxphase] or NULL
     unsigned long long seed;
+    long long     noise_row_base;  // added to the row index of the decoder-noise stream (Philox path): re-decode r of a frame
+                                  // draws rows r * rows_per_decode ... (ldpc_gpu_redecode_stats)
     unsigned char *workspace;     // device, gridDim.x * ws_stride bytes: per-CTA frame state of the HBM-resident
     size_t         ws_stride;     //   instantiations (codes whose state exceeds one SM's shared memory)
     // channel_dump outputs

@@ -84,3 +84,42 @@ def test_stop_rule_polls():
     r = dec.simulate(1.5, 0.5, 3, 0, 10 ** 7, stop_errors=200, stop_word_errors=40, poll_frames=64).counters
     assert r["errors"] >= 200 and r["wordErrors"] >= 40
     assert r["totalWords"] < 10 ** 5 and r["totalWords"] % 64 == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant,code,T,snr", [("decodeRSMNGDBF", "PEG", 30, 4.0), ("decodeSMNGDBF", "802_3_H", 25, 4.0),
+                                                 ("decodeStochasticNGDBF", "PEG", 12, 4.0), ("NGDBFhw", "802_3_H", 40, 4.3)])
+def test_redecode_stats_matrix_matches_oracle(variant, code, T, snr):
+    """SURVEY.md 8(f) N2.  ldpc_gpu_redecode_stats decodes every frame NR times from the same Philox channel samples
+    with fresh decoder noise (re-decode r draws rows r*rows_per_decode ... of the frame's decoder stream).  The whole
+    [frames][NR] matrix of error weights equals the double oracle's on the dumped samples and noise rows, and the
+    counters equal the sum over all decodes.  (The oracle's re-decode semantics are pinned against the reference's
+    redecodeStatistics main(): tests/test_oracle_vs_ref_main.py.)"""
+    R = cases.CODES[code][0]
+    NR, F = 3, 7
+    over = dict(num_iterations=T)
+    if variant == "decodeRSMNGDBF":
+        over["maxphase"] = 1
+    cfg = cases.cfg_for(variant, code=code, **over)
+    dec = capi.Decoder(capi.Code(code_path(code)), cfg)
+    got, cnt = dec.redecode_stats(snr, R, 99, 5, F, NR)
+    rows = abi.noise_rows_needed(cfg) if cfg.kind == abi.KIND_GDBF else 0
+    orc = Oracle(code)
+    if cfg.kind == abi.KIND_NGDBF_HW:
+        # NGDBFhw: the noise buffer of re-decode r is row r of the decoder stream; channel_dump returns row 0, so the oracle
+        # checks column 0 and the other columns are checked for determinism and for differing from column 0 somewhere
+        y, noise = dec.channel_dump(snr, R, 99, 5, F)
+        a = orc.decode(cfg, snr, R, y, noise, 0, None)
+        assert np.array_equal(got[:, 0], a.errors)
+        again, _ = dec.redecode_stats(snr, R, 99, 5, F, NR)
+        assert np.array_equal(got, again) and cnt["totalWords"] == F * NR
+        return
+    y, noise = dec.channel_dump(snr, R, 99, 5, F, noise_rows=rows * NR)
+    want = np.zeros((F, NR), np.int32)
+    for r in range(NR):
+        a = orc.decode(cfg, snr, R, y, np.ascontiguousarray(noise[:, r * rows:(r + 1) * rows, :]), rows, None)
+        want[:, r] = a.errors
+    assert np.array_equal(got, want)
+    assert cnt["totalWords"] == F * NR and cnt["errors"] == int(want.sum()) and cnt["wordErrors"] == int((want > 0).sum())
+    if variant == "decodeRSMNGDBF":
+        assert (want > 0).any() and (want == 0).any()          # both outcomes occur at this operating point
