@@ -51,7 +51,7 @@ def build_library(force=False, verbose=False):
 
 HOST_BINARIES = ["decodeMinSum", "decodeOffsetMinSum", "decodeNormalizedMinSum", "decodeBP", "decodeDDBMP", "decodeGDBF",
                  "decodeMGDBF", "decodeSGDBF", "decodeStochasticNGDBF", "decodeMNGDBF", "decodeSMNGDBF", "decodeUniformSMNGDBF",
-                 "decodeRSMNGDBF", "decodeSMGDBF", "decodeSATGDBF", "decodeATGDBF", "NGDBFhw"]
+                 "decodeRSMNGDBF", "decodeSMGDBF", "decodeSATGDBF", "decodeATGDBF", "NGDBFhw", "redecodeStatistics"]
 
 
 def build_host(force=False):

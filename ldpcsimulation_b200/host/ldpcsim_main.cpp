@@ -130,6 +130,93 @@ struct Shard {
     ldpc_gpu_counters cnt; vector<int64_t> ew, ith, ph; int rc = 0; string err;
 };
 
+// redecodeStatistics: src/redecodeStatistics.cpp with the macro set of the noisy smoothed decoder
+// (addNoise thresholdAdaptation weightSyndromes outputSmoothing saturateSamples).  Every frame is decoded NR times from
+// the same channel samples with fresh perturbation noise; one row of NR error weights per frame is appended to the log
+// (src/redecodeStatistics.cpp:392-395, fprintVector :615-621).
+int redecode_main(int argc, char *argv[])
+{
+    const vector<string> args = { "alist", "R", "SNR", "T", "NR", "NF", "theta", "logfilename", "noiseScale", "lambda", "alpha",
+                                  "windowsize", "Ymax", "[codeword filename]" };
+    if ((argc != (int)args.size()) && (argc != (int)args.size() + 1)) {
+        cout << "Usage: " << argv[0];
+        for (size_t i = 0; i < args.size(); i++) cout << " " << args[i];
+        cout << "\n";
+        return 0;
+    }
+    ldpc_gpu_decoder_cfg cfg;
+    ldpc_gpu_decoder_cfg_default(LDPC_GPU_KIND_GDBF, &cfg);
+    cfg.flags = RD | AN | TA | WS | OS | SS;                      // RD with maxphase = 1: the file's weight alpha*Ymax/dv (:543-546), one phase per decode
+    cfg.maxphase = 1;
+    const char *pe = getenv("LDPC_PRECISION");
+    cfg.precision = (pe && string(pe) == "f32") ? LDPC_GPU_PREC_F32 : LDPC_GPU_PREC_F64;
+    int idx = 1;
+    ldpc_gpu_code *code = nullptr;
+    if (ldpc_gpu_code_load_alist(argv[idx++], &code)) { cerr << "alist: " << ldpc_gpu_last_error() << endl; return 1; }
+    int N, M, E, dv, dc;
+    ldpc_gpu_code_dims(code, &N, &M, &E, &dv, &dc);
+    cout << "PARAMETERS: \n alist = \t" << argv[1] << endl;
+    const double R = atof(argv[idx++]);   cout << " R = \t" << R << endl;
+    const double SNR = atof(argv[idx++]); cout << " SNR = \t" << SNR << endl;
+    cfg.num_iterations = atoi(argv[idx++]); cout << " T = \t" << cfg.num_iterations << endl;
+    const int NR = atoi(argv[idx++]);     cout << " NR = \t" << NR << endl;
+    const long NF = atol(argv[idx++]);    cout << " NF = \t" << NF << endl;
+    cfg.theta = atof(argv[idx++]);        cout << " theta = \t" << cfg.theta << endl;
+    const string logfilename = argv[idx++]; cout << " log = \t" << logfilename << endl;
+    cfg.noiseScale = atof(argv[idx++]);   cout << " noiseScale = \t" << cfg.noiseScale << endl;
+    cfg.lambda = atof(argv[idx++]);       cout << " lambda = \t" << cfg.lambda << endl;
+    cfg.alpha = atof(argv[idx++]);        cout << " alpha = \t" << cfg.alpha << endl;
+    cfg.windowsize = atoi(argv[idx++]);   cout << "windowsize = \t" << cfg.windowsize << endl;
+    cfg.Ymax = atof(argv[idx++]);         cout << " Ymax = \t" << cfg.Ymax << endl;
+    vector<uint8_t> cw; long n_cw = 0;
+    if (argc == (int)args.size() + 1) {
+        cout << "\nUsing codewords from " << argv[idx] << endl;
+        if (!load_codewords(argv[idx], N, cw, n_cw)) { cerr << "cannot read codewords from " << argv[idx] << endl; return 1; }
+    } else cout << "\nUsing all-zero sequence.\n";
+    if (NR < 1 || NF < 0) { cerr << "NR must be >= 1 and NF >= 0" << endl; return 1; }
+    vector<int> devs;
+    { const char *e = getenv("LDPC_DEVICES"); string sdev = e ? e : "0"; stringstream ss(sdev); string t;
+      while (getline(ss, t, ',')) if (!t.empty()) devs.push_back(atoi(t.c_str())); }
+    if (ldpc_gpu_init(devs.data(), (int)devs.size())) { cerr << "ldpc_gpu_init: " << ldpc_gpu_last_error() << endl; return 1; }
+    const char *es = getenv("LDPC_SEED");
+    const uint64_t philox_seed = es ? strtoull(es, 0, 10) : (uint64_t)time(0);
+    const ldpc_gpu_channel ch = { SNR, R };
+    const size_t G = devs.size();
+    vector<vector<int32_t>> out(G);
+    vector<ldpc_gpu_counters> cnt(G);
+    vector<int> rcs(G, 0); vector<string> errs(G);
+    vector<thread> th;
+    for (size_t g = 0; g < G; g++) {                              // contiguous frame-id ranges, one per GPU
+        const long long begin = (long long)NF * (long long)g / (long long)G, end = (long long)NF * (long long)(g + 1) / (long long)G;
+        out[g].assign((size_t)(end - begin) * NR, 0);
+        memset(&cnt[g], 0, sizeof cnt[g]);
+        th.emplace_back([&, g, begin, end]() {
+            ldpc_gpu_decoder *dec = nullptr;
+            if (ldpc_gpu_decoder_create(code, &cfg, devs[g], &dec)) { rcs[g] = 1; errs[g] = ldpc_gpu_last_error(); return; }
+            if (n_cw) ldpc_gpu_decoder_set_codewords(dec, cw.data(), n_cw);
+            ldpc_gpu_sim_args a = { philox_seed, begin, end - begin, 0, 0, 0 };
+            if (ldpc_gpu_redecode_stats(dec, &ch, &a, NR, out[g].data(), &cnt[g])) { rcs[g] = 1; errs[g] = ldpc_gpu_last_error(); }
+            ldpc_gpu_decoder_destroy(dec);
+        });
+    }
+    for (thread &t : th) t.join();
+    for (size_t g = 0; g < G; g++) if (rcs[g]) { cerr << "ldpc_gpu_redecode_stats: " << errs[g] << endl; return 1; }
+    ofstream of(logfilename.c_str(), ios::app);
+    long long errors = 0, totalBits = 0, totalIterations = 0, uncodedErrors = 0;
+    for (size_t g = 0; g < G; g++) {
+        const size_t rows = out[g].size() / (size_t)NR;
+        for (size_t fi = 0; fi < rows; fi++) { for (int r = 0; r < NR; r++) of << out[g][fi * NR + r] << "\t"; of << endl; }
+        errors += cnt[g].errors; totalIterations += cnt[g].totalIterations;
+        uncodedErrors += cnt[g].uncodedErrors / NR; totalBits += cnt[g].totalBits / NR;    // counted once per frame by the reference
+    }
+    of.close();
+    cout << "\nFinal result: " << errors << " bit errs in " << NF << " words, BER=" << (totalBits ? (double)errors / totalBits : 0.0)
+         << ". Average iterations = " << (NF ? (double)totalIterations / ((double)NF * NR) : 0.0) << ". Uncoded errors = " << uncodedErrors
+         << ", uncBER=" << (totalBits ? (double)uncodedErrors / totalBits : 0.0) << endl;
+    ldpc_gpu_code_destroy(code);
+    return 0;
+}
+
 } // namespace
 
 int main(int argc, char *argv[])
@@ -137,6 +224,8 @@ int main(int argc, char *argv[])
     string prog = argv[0];
     size_t slash = prog.find_last_of('/');
     string base = slash == string::npos ? prog : prog.substr(slash + 1);
+    if (base == "redecodeStatistics") return redecode_main(argc, argv);
+    if (argc >= 2 && string(argv[1]) == "redecodeStatistics") return redecode_main(argc - 1, argv + 1);
     const Variant *v = find_variant(base);
     if (!v && argc >= 2 && (v = find_variant(argv[1]))) { argv++; argc--; }
     if (!v) {

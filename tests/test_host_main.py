@@ -143,3 +143,36 @@ def test_ngdbfhw_main(tmp_path):
         assert Reference("NGDBFhw", "802_3_H").run_main(["NGDBFhw", alist, "4.5", "40", "1234", rlog], 99) == 0
         ref = open(rlog).read().rstrip("\n").split("\t")
         assert len(ref) == 16 and ref[8:] == cols[8:]
+
+
+@needs_bin
+@pytest.mark.ref
+@pytest.mark.skipif(not Reference.available("redecodeStatistics"), reason="oracle/_ref not built")
+def test_redecode_statistics_usage_matches_reference_main(tmp_path):
+    out = tmp_path / "ref_stdout.txt"
+    assert Reference.main("redecodeStatistics", ["redecodeStatistics"], 1, str(out)) == 0
+    r = subprocess.run(exe("redecodeStatistics"), capture_output=True, text=True)
+    assert r.returncode == 0 and _usage(r.stdout) == _usage(out.read_text())
+
+
+@needs_bin
+@pytest.mark.gpu
+def test_redecode_statistics_rows(tmp_path):
+    """bin/redecodeStatistics appends one row of NR tab-terminated error weights per frame (src/redecodeStatistics.cpp:
+    392-395, 615-621), equal to ldpc_gpu_redecode_stats through the Python binding for the same seed."""
+    log = tmp_path / "outcomes.txt"
+    T, NR, NF, snr, R = 30, 5, 23, 4.0, 0.5
+    env = dict(os.environ, LDPC_SEED="4711")
+    argv = exe("redecodeStatistics") + [code_path("PEG"), str(R), str(snr), str(T), str(NR), str(NF), "-0.9", str(log),
+                                        "0.975", "0.988", "1.0", "8", "2.5"]
+    r = subprocess.run(argv, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    text = log.read_text()
+    assert all(line.endswith("\t") for line in text.splitlines())
+    rows = np.array([[int(t) for t in line.split()] for line in text.splitlines()], np.int32)
+    assert rows.shape == (NF, NR)
+    cfg = abi.default_cfg(abi.KIND_GDBF, flags=["redecode", "addNoise", "thresholdAdaptation", "weightSyndromes", "outputSmoothing", "saturateSamples"],
+                          num_iterations=T, theta=-0.9, noiseScale=0.975, alpha=1.0, windowsize=8, Ymax=2.5, maxphase=1, **{"lambda": 0.988})
+    want, cnt = capi.Decoder(capi.Code(code_path("PEG")), cfg).redecode_stats(snr, R, 4711, 0, NF, NR)
+    assert np.array_equal(rows, want)
+    assert "Final result: %d bit errs in %d words" % (int(want.sum()), NF) in r.stdout
