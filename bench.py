@@ -118,6 +118,33 @@ def profiled_metric(name):
         return None
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and hence its first-touch pinned host buffers) to the CPUs nearest its GPU, as listed by
+    `nvidia-smi topo -m`.  torchrun leaves every rank free to float; with 8 ranks streaming host samples the
+    cross-socket traffic is what the e2e number then measures.  Returns the CPU list used, or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        hdr = None
+        for line in out.splitlines():
+            cols = [c.strip() for c in line.split("\t")]
+            if hdr is None and "CPU Affinity" in line:
+                hdr = [c.strip() for c in line.replace("\x1b[4m", "").replace("\x1b[0m", "").split("\t")]
+                continue
+            if hdr and cols and cols[0].replace("\x1b[4m", "").replace("\x1b[0m", "") == "GPU%d" % local_rank:
+                aff = cols[hdr.index("CPU Affinity")]
+                cpus = set()
+                for part in aff.split(","):
+                    lo, _, hi = part.partition("-")
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+                cpus &= os.sched_getaffinity(0)
+                if cpus:
+                    os.sched_setaffinity(0, cpus)
+                    return aff
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -212,6 +239,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if capi.device_count() < 1:
         raise RuntimeError("bench.py: no CUDA device visible (there is no CPU fallback)")
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -386,7 +414,7 @@ def main():
                    "profile": PROFILE_CSV,
                    "edge_updates_per_s": 2.0 * E_EDGES * WORKLOAD["T"] * F * args.steps / (kernel_ms * 1e-3) if kernel_ms > 0 else None,
                    "issue_slots_per_edge_iteration": (148 * 4 * 32 * 1.965e9) / (E_EDGES * WORKLOAD["T"] * F * args.steps / (kernel_ms * 1e-3)) if kernel_ms > 0 else None},
-        "geometry": geo, "counters": total, "ber": total["errors"] / max(1, total["totalBits"]),
+        "geometry": geo, "cpu_affinity_rank0": numa, "counters": total, "ber": total["errors"] / max(1, total["totalBits"]),
         "fer": total["wordErrors"] / max(1, total["totalWords"]),
         "clocks": clocks,
     }
