@@ -89,6 +89,10 @@ extern "C" {
 #define LDPC_GPU_DT_F64  0
 #define LDPC_GPU_DT_F32  1
 #define LDPC_GPU_DT_F16  2   /* IEEE binary16 samples in (halves the host->device bytes); out_soft is then fp32 */
+#define LDPC_GPU_DT_Q8   3   /* int8 quantiser levels in, for the min-sum family with LDPC_GPU_F_QUANTIZE_SAMPLES: the samples as a
+                              * Q-bit converter delivers them.  k = +-max(1, floor(|y| (Nq-1) / (2 Ymax))), Nq = 2^Q, with the sign of y,
+                              * +-32 for |y| > Ymax; the decoder uses k * 2 Ymax / (Nq-1) (or +-Ymax), which is what quantize()
+                              * (src/decodeMinSum.cpp:480-489) makes of y.  Needs Q <= 6.  out_soft is then fp32. */
 
 /* Length of NGDBFhw's per-frame noise buffer (src/NGDBFhw.cpp:151-152). */
 #define LDPC_GPU_HW_QBUF  2648

@@ -33,7 +33,7 @@ MACRO_FLAGS = {
 
 PREC_F64, PREC_F32, PREC_F16X2 = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
-DT_F64, DT_F32, DT_F16 = 0, 1, 2
+DT_F64, DT_F32, DT_F16, DT_Q8 = 0, 1, 2, 3
 HW_QBUF = 2648
 
 
@@ -124,3 +124,14 @@ def noise_rows_needed(cfg):
 def iter_hist_len(cfg):
     ph = cfg.maxphase if (cfg.flags & F_REDECODE and cfg.kind == KIND_GDBF and cfg.maxphase > 1) else 1
     return cfg.num_iterations * ph + 1
+
+
+def quantizer_levels(y, Ymax, Q):
+    """LDPC_GPU_DT_Q8 encoding of raw samples: what quantize() (src/decodeMinSum.cpp:480-489) makes of y, as signed levels."""
+    import numpy as np
+    y = np.asarray(y, np.float64)
+    Nq = 2.0 ** Q                      # the reference passes Nq = 2^Q and quantises to (Nq - 1) intervals (src/decodeMinSum.cpp:133,480-489)
+    a = np.abs(y)
+    L = np.floor(a * (Nq - 1.0) / (2.0 * Ymax))
+    k = np.where(a > Ymax, 32.0, np.maximum(1.0, L))
+    return np.where(y >= 0, k, -k).astype(np.int8)

@@ -90,9 +90,15 @@ LDPC_DEVINL void raw_samples4(const FrameIO &io, const DecParams &p, const CodeD
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int i = i0 + q;
-            if (i < c.N) y[q] = (io.y_dtype == LDPC_GPU_DT_F64) ? ((const double *)io.y)[(size_t)f * c.N + i]
-                              : (io.y_dtype == LDPC_GPU_DT_F32) ? (double)((const float *)io.y)[(size_t)f * c.N + i]
-                                                                : (double)__half2float(((const __half *)io.y)[(size_t)f * c.N + i]);
+            if (i < c.N) {
+                if (io.y_dtype == LDPC_GPU_DT_Q8) {                 // quantiser levels: the conditioned value itself (the launch clears the quantiser flags)
+                    const int k = (int)((const signed char *)io.y)[(size_t)f * c.N + i];
+                    y[q] = (k >= 32) ? p.Ymax : (k <= -32) ? -p.Ymax : __dmul_rn((double)k, p.ms_step);
+                } else
+                y[q] = (io.y_dtype == LDPC_GPU_DT_F64) ? ((const double *)io.y)[(size_t)f * c.N + i]
+                     : (io.y_dtype == LDPC_GPU_DT_F32) ? (double)((const float *)io.y)[(size_t)f * c.N + i]
+                                                       : (double)__half2float(((const __half *)io.y)[(size_t)f * c.N + i]);
+            }
             else y[q] = 1.0;
         }
     } else {

@@ -688,8 +688,11 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
     if (!d || !b) return set_err(LDPC_GPU_ERR_INVALID_ARG, "decoder or batch is NULL");
     if (b->n_frames < 0) return set_err(LDPC_GPU_ERR_INVALID_ARG, "n_frames < 0");
     if (b->n_frames > 0 && !b->y) return set_err(LDPC_GPU_ERR_INVALID_ARG, "batch.y is NULL");
-    if (b->y_dtype != LDPC_GPU_DT_F64 && b->y_dtype != LDPC_GPU_DT_F32 && b->y_dtype != LDPC_GPU_DT_F16) return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown y_dtype");
+    if (b->y_dtype != LDPC_GPU_DT_F64 && b->y_dtype != LDPC_GPU_DT_F32 && b->y_dtype != LDPC_GPU_DT_F16 && b->y_dtype != LDPC_GPU_DT_Q8)
+        return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown y_dtype");
     const int N = d->N, kind = d->cfg.kind;
+    if (b->y_dtype == LDPC_GPU_DT_Q8 && !(kind == LDPC_GPU_KIND_MINSUM && (d->cfg.flags & LDPC_GPU_F_QUANTIZE_SAMPLES) && d->cfg.Q >= 2 && d->cfg.Q <= 6))
+        return set_err(LDPC_GPU_ERR_INVALID_ARG, "LDPC_GPU_DT_Q8 carries quantiser levels: it needs a min-sum decoder with LDPC_GPU_F_QUANTIZE_SAMPLES and 2 <= Q <= 6");
     const int rps = rows_per_step(d->cfg.flags);
     if (kind == LDPC_GPU_KIND_GDBF && rps > 0) {
         const int ph = (d->cfg.flags & LDPC_GPU_F_REDECODE) ? std::max(1, d->cfg.maxphase) : 1;
@@ -698,12 +701,13 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
     }
     if (kind == LDPC_GPU_KIND_NGDBF_HW && !b->noise) return set_err(LDPC_GPU_ERR_INVALID_ARG, "NGDBFhw needs its per-frame noise buffer in batch.noise");
     DecParams p; int rc = channel_params(d, ch, p); if (rc) return rc;
+    if (b->y_dtype == LDPC_GPU_DT_Q8) p.flags &= ~(uint32_t)(LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES);   // the levels ARE the quantiser's output
     CU_TRY(cudaSetDevice(d->device));
     d->last_kernel_ms = 0; d->last_launches = 0;
     cudaStream_t st0 = d->slot[0].st;
     if (cnt) { if ((rc = zero_counters(d, st0))) return rc; CU_TRY(cudaStreamSynchronize(st0)); }
 
-    const size_t esz = b->y_dtype == LDPC_GPU_DT_F64 ? 8 : b->y_dtype == LDPC_GPU_DT_F32 ? 4 : 2, bpf = (size_t)(N + 7) / 8;
+    const size_t esz = b->y_dtype == LDPC_GPU_DT_F64 ? 8 : b->y_dtype == LDPC_GPU_DT_F32 ? 4 : b->y_dtype == LDPC_GPU_DT_F16 ? 2 : 1, bpf = (size_t)(N + 7) / 8;
     const size_t ssz = b->y_dtype == LDPC_GPU_DT_F64 ? 8 : 4;     // out_soft element size
     const size_t noise_pf = kind == LDPC_GPU_KIND_NGDBF_HW ? (size_t)LDPC_GPU_HW_QBUF : (kind == LDPC_GPU_KIND_GDBF && b->noise ? (size_t)b->noise_rows * N : 0);
     FrameIO io; memset(&io, 0, sizeof io);

@@ -208,6 +208,34 @@ def test_f16x2_register_resident_kernel_equals_f16x2_scheduled_kernel(variant, m
         assert np.array_equal(a.bits, b.bits) and np.array_equal(a.soft, b.soft) and a.counters == b.counters
 
 
+@pytest.mark.parametrize("prec", [abi.PREC_F64, abi.PREC_F32, abi.PREC_F16X2])
+@pytest.mark.parametrize("variant", ["decodeNormalizedMinSum", "decodeOffsetMinSum"])
+def test_quantiser_level_input_equals_raw_sample_input(variant, prec):
+    """LDPC_GPU_DT_Q8: the samples as a Q-bit converter delivers them (signed quantiser levels, one byte each).  The
+    decoder sees exactly what quantize() (src/decodeMinSum.cpp:480-489) makes of the raw double samples: same decisions,
+    iteration counts, counters and a-posteriori sums, in every instantiation."""
+    R, snr = 0.8413, 3.9
+    code = capi.Code(code_path("802_3_H"))
+    cfg = cases.cfg_for(variant, code="802_3_H", num_iterations=7, precision=prec)
+    dec = capi.Decoder(code, cfg)
+    cws = code.random_codewords(3, 4)
+    y, noise, rows, cw = cases.make_inputs(2048, cfg, snr, R, 29, 5150, cws)
+    y[0, :8] = [0.0, -0.0, 1e-9, -1e-9, cfg.Ymax, -cfg.Ymax, cfg.Ymax * (1 + 1e-12), -3 * cfg.Ymax]      # zero level, saturation edge
+    k = abi.quantizer_levels(y, cfg.Ymax, cfg.Q)
+    assert k.dtype == np.int8 and np.abs(k).min() == 1 and np.abs(k).max() == 32
+    a = dec.decode(snr, R, y, codeword=cw)
+    b = dec.decode(snr, R, k, codeword=cw, y_dtype=abi.DT_Q8)
+    assert np.array_equal(a.bits, b.bits) and np.array_equal(a.iters, b.iters) and a.counters == b.counters
+    assert b.soft.dtype == np.float32 and np.array_equal(a.soft.astype(np.float32), b.soft)
+
+
+def test_quantiser_level_input_needs_a_quantising_min_sum_decoder():
+    code = capi.Code(code_path("802_3_H"))
+    dec = capi.Decoder(code, cases.cfg_for("decodeMinSum", code="802_3_H"))
+    with pytest.raises(capi.LdpcGpuError):
+        dec.decode(4.0, 0.8413, np.ones((2, 2048), np.int8), y_dtype=abi.DT_Q8)
+
+
 def test_fp16_sample_input_equals_fp32_input_of_the_same_values():
     """LDPC_GPU_DT_F16 only changes how the samples travel: binary16 -> fp32 is exact."""
     cfg = cases.cfg_for("decodeNormalizedMinSum", precision=abi.PREC_F32)
