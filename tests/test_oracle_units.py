@@ -61,3 +61,22 @@ def test_hw_pack_unpack_table():
     for x in np.linspace(-lmax, lmax, 200):
         v = L.oracle_hw_unpack(L.oracle_hw_pack(float(x), Ymax, w))
         assert v % 2 != 0 and (v > 0) == (x > 0) and abs(v) <= 31
+
+
+def test_quantizer_levels_encode_the_reference_quantiser():
+    """abi.quantizer_levels (the LDPC_GPU_DT_Q8 encoding) against the oracle's restatement of quantize()
+    (src/decodeMinSum.cpp:480-489, pinned to the reference object code in test_oracle_vs_ref.py): level * step, +-Ymax
+    when saturated, never zero, sign of the sample (+ for +-0)."""
+    import cases
+    from ldpcsimulation_b200 import abi
+    from oracle.oracle_api import Oracle
+    for variant in ("decodeNormalizedMinSum", "decodeOffsetMinSum"):
+        cfg = cases.cfg_for(variant, code="802_3_H", num_iterations=0)
+        orc = Oracle("802_3_H")
+        y, _, _, _ = cases.make_inputs(2048, cfg, 3.0, 0.8413, 6, 99)
+        y[0, :8] = [0.0, -0.0, 1e-9, -1e-9, cfg.Ymax, -cfg.Ymax, cfg.Ymax * (1 + 1e-12), -3 * cfg.Ymax]
+        want = orc.decode(cfg, 3.0, 0.8413, y).soft                      # T = 0: the conditioned samples
+        k = abi.quantizer_levels(y, cfg.Ymax, cfg.Q)
+        step = 2 * cfg.Ymax / (2.0 ** cfg.Q - 1)
+        got = np.where(np.abs(k) == 32, np.sign(k) * cfg.Ymax, k.astype(np.float64) * step)
+        assert np.array_equal(got, want) and np.abs(k).min() >= 1
