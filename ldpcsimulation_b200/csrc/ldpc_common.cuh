@@ -154,6 +154,12 @@ LDPC_DEVINL void finish_frame(const CodeDev &c, const DecParams &p, const FrameI
     const int npad = (c.N + 31) & ~31;
     const size_t bpf = (size_t)(c.N + 7) >> 3;
     int local_err = 0;
+    if (!cw && !io.out_bits) {
+        // all-zero codeword, no decision output (the throughput entry's common case): errors = popcount of the decision
+        // words, one word per thread instead of one bit per thread (bits past N are never set)
+        for (int w = tid; w < (npad >> 5); w += nt) local_err += __popc(dbits[w]);
+        for (int o = 16; o; o >>= 1) local_err += __shfl_xor_sync(0xffffffffu, local_err, o);
+    } else
     for (int i0 = tid; i0 < npad; i0 += nt) {
         const bool valid = i0 < c.N;
         const uint32_t word = dbits[i0 >> 5];
