@@ -95,3 +95,20 @@ def test_simulate_and_misc_argument_checks():
     assert L.ldpc_gpu_decoder_destroy(None) == 0 and L.ldpc_gpu_code_destroy(None) == 0
     g = dec.geometry()
     assert g["grid"] % 148 == 0 and g["block"] % 32 == 0
+
+
+def test_redecode_stats_argument_checks():
+    L = capi.lib()
+    code = capi.Code(code_path("PEG"))
+    ch = abi.Channel(4.0, 0.5)
+    out = np.zeros((4, 3), np.int32)
+    a = abi.SimArgs(1, 0, 4, 0, 0, 0)
+    ms = capi.Decoder(code, cases.cfg_for("decodeMinSum"))
+    rc, msg = _rc(L.ldpc_gpu_redecode_stats, ms.h, C.byref(ch), C.byref(a), 3, out.ctypes.data_as(C.c_void_p), None)
+    assert rc == abi.ERR_UNSUPPORTED and "noise" in msg                     # a decoder without its own randomness has nothing to re-decode
+    ng = capi.Decoder(code, cases.cfg_for("decodeSMNGDBF", num_iterations=10))
+    assert L.ldpc_gpu_redecode_stats(ng.h, C.byref(ch), C.byref(a), 0, out.ctypes.data_as(C.c_void_p), None) == abi.ERR_INVALID_ARG
+    assert L.ldpc_gpu_redecode_stats(ng.h, C.byref(ch), C.byref(a), 3, None, None) == abi.ERR_INVALID_ARG
+    assert L.ldpc_gpu_redecode_stats(ng.h, C.byref(ch), C.byref(a), 3, out.ctypes.data_as(C.c_void_p), None) == 0     # counters are optional
+    empty = abi.SimArgs(1, 0, 0, 0, 0, 0)
+    assert L.ldpc_gpu_redecode_stats(ng.h, C.byref(ch), C.byref(empty), 3, out.ctypes.data_as(C.c_void_p), None) == 0
