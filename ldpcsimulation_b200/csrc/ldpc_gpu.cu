@@ -502,7 +502,10 @@ geometry:
     cudaFuncAttributes fa;
     CU_TRY(cudaFuncGetAttributes(&fa, (const void *)d->fn));
     const int by_regs = (65536 / std::max(1, fa.numRegs)) & ~31;      // one CTA must fit the register file
+    const int block_wanted = block;
     block = std::max(32, std::min(block, std::min(by_regs, fa.maxThreadsPerBlock & ~31)));
+    if (block != block_wanted && (d->fn == (KernelFn)ms_rc_kernel<float, 32, 6, 2048, 384, 2> || d->fn == (KernelFn)ms_rc_kernel<double, 32, 6, 2048, 384, 1>))
+        return set_err(LDPC_GPU_ERR_UNSUPPORTED, "ms_rc_kernel is written for blocks of exactly 384 threads");
     int nb = 0;
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)d->fn, block, smem));
     if (nb < 1) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "kernel does not fit on an SM");

@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
             if (have_next && gen_done < nblk) { if (gen_done + tid < nblk) gen(fnext, cwn, gen_done + tid); gen_done += nt; }
             __syncthreads();
             // ---- variable-node phase: S = y + sum_s c2v, two adjacent storage columns per thread ------
-            for (int cp = tid; cp < N / 2; cp += nt) {
+            auto vn_pair = [&](const int cp) {
                 typedef typename Vec2<Real>::type V2;
                 const int col = 2 * cp;
                 V2 sum = *reinterpret_cast<const V2 *>(&yq[col]);
@@ -297,7 +297,12 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
                         else { ((float *)io.out_soft)[(size_t)f * N + i0] = (float)sum.x; ((float *)io.out_soft)[(size_t)f * N + i1] = (float)sum.y; }
                     }
                 }
-            }
+            };
+            // compile-time trip count (the host launches this kernel with exactly NT_MAX threads): no loop control, and the
+            // loads of the rounds can overlap (22.4 -> 23.0 Gbit/s)
+            constexpr int VN_ROUNDS = (N / 2 + NT_MAX - 1) / NT_MAX;
+#pragma unroll
+            for (int rr = 0; rr < VN_ROUNDS; rr++) { const int cp = tid + rr * NT_MAX; if (cp < N / 2) vn_pair(cp); }
             if (!last) fetch_schedule();
             __syncthreads();
         }
