@@ -184,7 +184,11 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_h2rc_kernel(const CodeDev c, 
             }
             __syncthreads();
             // ---- variable-node phase: S = y + sum_s c2v, two adjacent storage columns per thread --------
-            for (int cp = tid; cp < N / 2; cp += nt) {
+            constexpr int VN_ROUNDS = (N / 2 + NT_MAX - 1) / NT_MAX;               // the host launches exactly NT_MAX threads
+#pragma unroll
+            for (int rr = 0; rr < VN_ROUNDS; rr++) {
+                const int cp = tid + rr * NT_MAX;
+                if (cp >= N / 2) break;
                 const int col = 2 * cp;
                 const uint2 y2 = *reinterpret_cast<const uint2 *>(&yq[col]);
                 __half2 s0 = h2_from(y2.x), s1 = h2_from(y2.y);
