@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_h2rc_kernel(const CodeDev c, 
         const bool have_next = prn < npairs;
         long long fna = 0, fnb = 0; if (have_next) pair_frames(prn, fna, fnb);
         const uint8_t *cwna = have_next ? codeword_row(io, c, fna) : nullptr, *cwnb = have_next ? codeword_row(io, c, fnb) : nullptr;
-        const int gen_done = 0;                                                 // the next pair is generated after this one's iterations:
-                                                                                // generating it inside the loop (as ms_rc_kernel does) costs registers the 32 c2v words need (measured 22 vs 34 Gbit/s)
+        const int gen_done = 0;                                                 // the next pair is generated after this one's iterations: generating it
+                                                                                // inside the loop (after the variable phase or after the check row) spills the 32 c2v words (measured 22-24 vs 34 Gbit/s)
         if (p.T == 0) __syncthreads();
 
         for (int it = 0; it < p.T; it++) {
