@@ -87,7 +87,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-PROFILE_CSV = "profiles/r1n_ncu_raw_ms_rc_final.csv"      # `ncu --set full` capture of the headline kernel on this workload
+PROFILE_CSV = "profiles/r1p_ncu_raw_ms_rc_final.csv"      # `ncu --set full` capture of the headline kernel on this workload
 
 
 def profiled_traffic():
