@@ -312,9 +312,11 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
             if (!last) fetch_schedule();
             __syncthreads();
         }
-        finish_frame(c, p, io, f, cw, dbits, fs, p.T, -1, 0, 0, 1, -1, tot);
-        if (have_next) for (int b = gen_done + tid; b < nblk; b += nt) gen(fnext, cwn, b);
-        __syncthreads();
+        finish_frame(c, p, io, f, cw, dbits, fs, p.T, -1, 0, 0, 1, -1, tot);      // ends with a barrier
+        if (have_next && gen_done < nblk) {                          // what the iterations did not cover (T < 2); uniform
+            for (int b = gen_done + tid; b < nblk; b += nt) gen(fnext, cwn, b);
+            __syncthreads();
+        }
     }
     if (tid == 0) tot.flush(io.counters);
 }
