@@ -283,7 +283,7 @@ def main():
     for i in range(args.warmup):
         r = step(i)
     if world > 1:                                       # first collective on a fresh communicator sets up its channels
-        capi.check(capi.lib().ldpc_gpu_allreduce_counters(r["_cnt"], code.N, cfg.num_iterations, 1))
+        capi.check(capi.lib().ldpc_gpu_allreduce_counters(r["_cnt"], code.N, C.byref(cfg)))
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -306,7 +306,7 @@ def main():
         cnt = last["_cnt"]
         for k in total:
             setattr(cnt, k, total[k])
-        capi.check(capi.lib().ldpc_gpu_allreduce_counters(cnt, code.N, cfg.num_iterations, 1))
+        capi.check(capi.lib().ldpc_gpu_allreduce_counters(cnt, code.N, C.byref(cfg)))
         total = cnt.as_dict()
     barrier()
     wall = time.perf_counter() - t0

@@ -145,7 +145,9 @@ typedef struct ldpc_gpu_counters {
     int64_t smoothingUsed;
     int64_t undetectedWords;        /* e>0 with all checks satisfied ("All checks satisfied.", decodeGDBF.cpp:383-387) */
     int64_t *error_weight_hist;     /* [N]              error_weight_hist[e-1]++          */
-    int64_t *iter_hist;             /* [T+1]            iterations used per frame (itdist source, NGDBFhw.cpp:420-421) */
+    int64_t *iter_hist;             /* [ldpc_gpu_iter_hist_len(cfg)] iterations used per frame (itdist source, NGDBFhw.cpp:420-421):
+                                       T+1 entries, or T*maxphase+1 for the GDBF family with LDPC_GPU_F_REDECODE and maxphase > 1
+                                       (RNGDBF.cpp:394 adds `it` per phase) */
     int64_t *phase_hist;            /* [maxphase]       phase_hist[phase-1]++ (RNGDBF.cpp:403) */
 } ldpc_gpu_counters;
 
@@ -209,6 +211,8 @@ int  ldpc_gpu_code_random_codewords(ldpc_gpu_code *code, uint64_t seed, int64_t 
 
 /* ---- decoder ------------------------------------------------------------ */
 int  ldpc_gpu_decoder_cfg_default(int kind, ldpc_gpu_decoder_cfg *cfg);
+/* Number of entries a caller-owned ldpc_gpu_counters.iter_hist must hold for this configuration. */
+int  ldpc_gpu_iter_hist_len(const ldpc_gpu_decoder_cfg *cfg);
 int  ldpc_gpu_decoder_create(const ldpc_gpu_code *code, const ldpc_gpu_decoder_cfg *cfg, int device,
                              ldpc_gpu_decoder **out);
 int  ldpc_gpu_decoder_destroy(ldpc_gpu_decoder *dec);
@@ -261,7 +265,9 @@ int  ldpc_gpu_decoder_geometry(const ldpc_gpu_decoder *dec, int *grid, int *bloc
 int  ldpc_gpu_comm_unique_id(uint8_t id[128]);
 int  ldpc_gpu_comm_init(const uint8_t id[128], int rank, int nranks, int device);
 int  ldpc_gpu_comm_destroy(void);
-int  ldpc_gpu_allreduce_counters(ldpc_gpu_counters *counters, int N, int T, int maxphase);
+/* Lengths are taken from the decoder configuration the counters were filled under:
+ * error_weight_hist [N], iter_hist [ldpc_gpu_iter_hist_len(cfg)], phase_hist [max(1, cfg->maxphase)]. */
+int  ldpc_gpu_allreduce_counters(ldpc_gpu_counters *counters, int N, const ldpc_gpu_decoder_cfg *cfg);
 
 #ifdef __cplusplus
 }

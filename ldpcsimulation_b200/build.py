@@ -35,9 +35,8 @@ def build_library(force=False, verbose=False):
     os.makedirs(OUT, exist_ok=True)
     if not force and _newer(LIB, sources()):
         return LIB
-    extra = os.environ.get("LDPC_EXTRA_NVCC_FLAGS", "").split()
     out = os.environ.get("LDPC_GPU_LIB_OUT", LIB)
-    cmd = [NVCC] + NVCC_FLAGS + extra + [os.path.join(CSRC, "ldpc_gpu.cu"), "-o", out, "-ldl"]
+    cmd = [NVCC] + NVCC_FLAGS + [os.path.join(CSRC, "ldpc_gpu.cu"), "-o", out, "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     with open(os.path.join(OUT, "ptxas.log"), "w") as f:
         f.write(r.stdout + r.stderr)

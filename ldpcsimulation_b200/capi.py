@@ -19,7 +19,7 @@ EXPORTS = [
     "ldpc_gpu_version", "ldpc_gpu_last_error", "ldpc_gpu_init", "ldpc_gpu_shutdown", "ldpc_gpu_device_count",
     "ldpc_gpu_code_create", "ldpc_gpu_code_load_alist", "ldpc_gpu_code_dims", "ldpc_gpu_code_destroy",
     "ldpc_gpu_code_random_codewords",
-    "ldpc_gpu_decoder_cfg_default", "ldpc_gpu_decoder_create", "ldpc_gpu_decoder_destroy",
+    "ldpc_gpu_decoder_cfg_default", "ldpc_gpu_iter_hist_len", "ldpc_gpu_decoder_create", "ldpc_gpu_decoder_destroy",
     "ldpc_gpu_decoder_set_codewords", "ldpc_gpu_decode_batch", "ldpc_gpu_simulate", "ldpc_gpu_redecode_stats", "ldpc_gpu_channel_dump",
     "ldpc_gpu_philox4x32", "ldpc_gpu_last_timing", "ldpc_gpu_decoder_geometry",
     "ldpc_gpu_comm_unique_id", "ldpc_gpu_comm_init", "ldpc_gpu_comm_destroy", "ldpc_gpu_allreduce_counters",
@@ -64,7 +64,8 @@ def lib():
         L.ldpc_gpu_init.argtypes = [C.c_void_p, C.c_int]
         L.ldpc_gpu_comm_unique_id.argtypes = [C.c_void_p]
         L.ldpc_gpu_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
-        L.ldpc_gpu_allreduce_counters.argtypes = [C.POINTER(abi.Counters), C.c_int, C.c_int, C.c_int]
+        L.ldpc_gpu_allreduce_counters.argtypes = [C.POINTER(abi.Counters), C.c_int, C.POINTER(abi.DecoderCfg)]
+        L.ldpc_gpu_iter_hist_len.argtypes = [C.POINTER(abi.DecoderCfg)]
         _lib = L
     return _lib
 

@@ -572,6 +572,7 @@ __global__ void hw_kernel(const CodeDev c, const DecParams p, const FrameIO io)
         __syncthreads();
 
         int qpointer = io.qpointer0 ? io.qpointer0[f] : 0;
+        qpointer = ((qpointer % (QB - N)) + (QB - N)) % (QB - N);      // the window start lives in [0, QBUF - N) (:356-358); host batches are validated
         int leastIterations = T, leastErrors = N, satisfied = 1, it = 0;
         for (int phase = 0; phase < maxPhases; phase++) {             // :280-373
             for (int w = tid; w < nwords; w += nt) dbits[w] = rbits[w];

@@ -293,6 +293,8 @@ static int iter_hist_len(const ldpc_gpu_decoder_cfg &c)
     return c.num_iterations * ph + 1;
 }
 
+extern "C" int ldpc_gpu_iter_hist_len(const ldpc_gpu_decoder_cfg *c) { return c ? iter_hist_len(*c) : 0; }
+
 extern "C" int ldpc_gpu_decoder_cfg_default(int kind, ldpc_gpu_decoder_cfg *c)
 {
     if (!c) return set_err(LDPC_GPU_ERR_INVALID_ARG, "cfg is NULL");
@@ -540,7 +542,9 @@ static int validate_cfg(const ldpc_gpu_decoder_cfg &c)
     if ((c.kind == LDPC_GPU_KIND_MINSUM && (c.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES))) || c.kind == LDPC_GPU_KIND_DDBMP)
         if (!(c.Ymax > 0) || (((c.flags & LDPC_GPU_F_QUANTIZE_SAMPLES) || c.kind == LDPC_GPU_KIND_DDBMP) && (c.Q < 1 || c.Q > 30)))
             return set_err(LDPC_GPU_ERR_INVALID_ARG, "quantiser needs Ymax > 0 and 1 <= Q <= 30");
-    if (c.kind == LDPC_GPU_KIND_MINSUM && (c.flags & LDPC_GPU_F_NORMALIZED_MS) && c.alpha == 0) return set_err(LDPC_GPU_ERR_INVALID_ARG, "alpha = 0");
+    if (c.kind == LDPC_GPU_KIND_MINSUM && (c.flags & LDPC_GPU_F_NORMALIZED_MS) && !(c.alpha > 0)) return set_err(LDPC_GPU_ERR_INVALID_ARG, "normalised min-sum needs alpha > 0");
+    if (c.kind == LDPC_GPU_KIND_MINSUM && (c.flags & LDPC_GPU_F_OFFSET_MS) && !(c.delta >= 0))
+        return set_err(LDPC_GPU_ERR_INVALID_ARG, "offset min-sum needs delta >= 0 (the kernels implement sgn(m) max(|m| - delta, 0), src/decodeMinSum.cpp:503-515, in forms that assume it)");
     return LDPC_GPU_OK;
 }
 
@@ -603,7 +607,9 @@ extern "C" int ldpc_gpu_decoder_create(const ldpc_gpu_code *code, const ldpc_gpu
         if (code & 16) p.hw_theta = -p.hw_theta;
         p.hw_Smult = (int)round(NL / lmax);
     }
-    p.inv_alpha_f = (float)(1.0 / cfg->alpha);
+    p.inv_alpha_f = cfg->alpha != 0 ? (float)(1.0 / (double)(float)cfg->alpha) : 0.0f;
+    { int ex; const bool pow2 = cfg->alpha > 0 && frexp(cfg->alpha, &ex) == 0.5;
+      p.alpha_div_f = ((cfg->flags & LDPC_GPU_F_NORMALIZED_MS) && !pow2 && !getenv("LDPC_GPU_NO_FDIV")) ? (float)cfg->alpha : 0.0f; }
     p.ms_scale_f = (float)((Nq - 1) / (2.0 * cfg->Ymax)); p.ms_step_f = (float)p.ms_step; p.Ymax_f = (float)cfg->Ymax;
     p.iter_hist_len = iter_hist_len(*cfg);
     p.rows_per_step = rows_per_step(cfg->flags);
@@ -703,6 +709,10 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
         if (b->noise_rows < (int64_t)d->cfg.num_iterations * ph * rps) return set_err(LDPC_GPU_ERR_INVALID_ARG, "batch.noise_rows is smaller than T * phases * rows-per-step");
     }
     if (kind == LDPC_GPU_KIND_NGDBF_HW && !b->noise) return set_err(LDPC_GPU_ERR_INVALID_ARG, "NGDBFhw needs its per-frame noise buffer in batch.noise");
+    if (kind == LDPC_GPU_KIND_NGDBF_HW && b->qpointer0 && b->mem == LDPC_GPU_MEM_HOST)
+        for (int64_t f = 0; f < b->n_frames; f++)
+            if (b->qpointer0[f] < 0 || b->qpointer0[f] >= LDPC_GPU_HW_QBUF - N)
+                return set_err(LDPC_GPU_ERR_INVALID_ARG, "batch.qpointer0 outside [0, LDPC_GPU_HW_QBUF - N): the noise window wraps there (src/NGDBFhw.cpp:356-358)");
     DecParams p; int rc = channel_params(d, ch, p); if (rc) return rc;
     if (b->y_dtype == LDPC_GPU_DT_Q8) p.flags &= ~(uint32_t)(LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES);   // the levels ARE the quantiser's output
     CU_TRY(cudaSetDevice(d->device));
@@ -736,7 +746,8 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
         chunk = std::max<long long>(chunk, 16ll * d->grid_full * d->frames_per_cta);
         chunk = std::min<long long>(chunk, std::max<long long>(1, (b->n_frames + 1) / 2));
         if (b->n_frames <= 2 * (long long)d->grid_full) chunk = std::max<long long>(1, b->n_frames);
-        std::vector<std::pair<int, bool>> pending;       // slots with a timing pair outstanding
+        // any failure inside the loop must not leave async copies in flight on the caller's buffers
+        auto run_chunks = [&]() -> int {
         int c = 0;
         for (long long f0 = 0; f0 < b->n_frames; f0 += chunk, c++) {
             const long long nf = std::min<long long>(chunk, b->n_frames - f0);
@@ -780,10 +791,19 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
             if (b->out_errors) CU_TRY(cudaMemcpyAsync(b->out_errors + f0, s.errs.p, 4 * (size_t)nf, cudaMemcpyDeviceToHost, s.st));
             if (b->out_flags)  CU_TRY(cudaMemcpyAsync(b->out_flags + f0, s.flags.p, (size_t)nf, cudaMemcpyDeviceToHost, s.st));
         }
+        return LDPC_GPU_OK;
+        };
+        rc = run_chunks();
+        if (rc) {                                         // drain both slots, keep the first error's message
+            const std::string msg = g_err;
+            for (Slot &s : d->slot) { cudaStreamSynchronize(s.st); s.used = false; }
+            cudaGetLastError();
+            return set_err(rc, msg);
+        }
         for (Slot &s : d->slot) if (s.used) {
+            s.used = false;
             CU_TRY(cudaStreamSynchronize(s.st));
             float ms = 0; cudaEventElapsedTime(&ms, s.k0, s.k1); d->last_kernel_ms += ms;
-            s.used = false;
         }
     } else return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown batch.mem");
     if (cnt) return fetch_counters(d, cnt, st0);
@@ -862,7 +882,7 @@ extern "C" int ldpc_gpu_redecode_stats(ldpc_gpu_decoder *d, const ldpc_gpu_chann
     io.seed = a->seed; io.cw_table = d->d_cwtab; io.n_cw = d->n_cw;
     io.counters = d->d_counters; io.ew_hist = d->d_ew; io.it_hist = d->d_it; io.ph_hist = d->d_ph;
     io.out_errors = d_err;
-    CU_TRY(cudaEventRecord(d->slot[0].k0, st));
+    if (cudaEventRecord(d->slot[0].k0, st) != cudaSuccess) { cudaFree(d_err); return set_err(LDPC_GPU_ERR_CUDA, "cudaEventRecord failed"); }
     for (long long done = 0; done < a->n_frames && !rc; done += per_launch) {
         const long long nf = std::min<long long>(per_launch, a->n_frames - done);
         io.n_frames = nf; io.frame_begin = a->frame_begin + done;
@@ -1020,12 +1040,13 @@ extern "C" int ldpc_gpu_comm_destroy(void)
     if (g_comm_stream) { cudaStreamDestroy(g_comm_stream); g_comm_stream = nullptr; }
     return LDPC_GPU_OK;
 }
-extern "C" int ldpc_gpu_allreduce_counters(ldpc_gpu_counters *c, int N, int T, int maxphase)
+extern "C" int ldpc_gpu_allreduce_counters(ldpc_gpu_counters *c, int N, const ldpc_gpu_decoder_cfg *cfg)
 {
-    if (!c) return set_err(LDPC_GPU_ERR_INVALID_ARG, "counters is NULL");
+    if (!c || !cfg) return set_err(LDPC_GPU_ERR_INVALID_ARG, "counters or cfg is NULL");
+    const int maxphase = cfg->maxphase;
     if (!g_comm) return set_err(LDPC_GPU_ERR_COMM, "communicator not initialised");
     CU_TRY(cudaSetDevice(g_comm_dev));
-    const size_t n_ew = c->error_weight_hist ? (size_t)N : 0, n_it = c->iter_hist ? (size_t)T + 1 : 0, n_ph = c->phase_hist ? (size_t)std::max(1, maxphase) : 0;
+    const size_t n_ew = c->error_weight_hist ? (size_t)N : 0, n_it = c->iter_hist ? (size_t)iter_hist_len(*cfg) : 0, n_ph = c->phase_hist ? (size_t)std::max(1, maxphase) : 0;
     std::vector<int64_t> h(8 + n_ew + n_it + n_ph);
     int64_t *q = h.data();
     q[0] = c->errors; q[1] = c->uncodedErrors; q[2] = c->totalBits; q[3] = c->totalWords; q[4] = c->wordErrors;

@@ -166,7 +166,7 @@ __global__ void mp_kernel(const CodeDev c, const DecParams p, const FrameIO io)
                                 const Real mag = (k == idx) ? m2 : m1;
                                 const bool ng = pneg ^ (bool)((signs >> k) & 1ull);
                                 Real out = ng ? -mag : mag;           // prod*minMag*sgn(msg)
-                                if (normalized) out = (sizeof(Real) == 8) ? out / alpha : out * (Real)p.inv_alpha_f;   // :494-499
+                                if (normalized) out = out / alpha;                                // :494-499
                                 if (offset) {                         // :503-515
                                     const Real mg = absr(out) - delta;
                                     out = (mg > 0) ? (neg_ge(out) ? -mg : mg) : (Real)0;

@@ -140,8 +140,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_fast_kernel(const CodeDev c, 
                 }
                 Real o1 = m1, o2 = m2;
                 if (normalized) {
-                    if (sizeof(Real) == 8) { o1 = o1 / alpha; o2 = o2 / alpha; }
-                    else { o1 = o1 * (Real)p.inv_alpha_f; o2 = o2 * (Real)p.inv_alpha_f; }
+                    o1 = o1 / alpha; o2 = o2 / alpha;                       // IEEE division in every precision, once per row (src/decodeMinSum.cpp:494-499)
                 }
                 if (offset) { o1 = o1 - delta; o1 = (o1 > 0) ? o1 : (Real)0; o2 = o2 - delta; o2 = (o2 > 0) ? o2 : (Real)0; }
                 const Real s1 = SignOps<Real>::presign(o1, sg), s2 = SignOps<Real>::presign(o2, sg);
@@ -313,7 +312,6 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
             const bool last = (it == p.T - 1);
             if (last) for (int w = tid; w < nwords; w += nt) dbits[w] = 0u;          // re-filled below, in true variable order
             // ---- check-node phase ----------------------------------------------------------------
-#ifndef LDPC_EXPERIMENT_SKIP_CN
             for (int j = tid; j < M; j += nt) {
                 if (ALGO == ALGO_BP) {
                     Real t[DC];                                       // phi(|v_k|) carrying the sign of v_k
@@ -365,8 +363,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
                 }
                 Real o1 = m1, o2 = m2;
                 if (normalized) {
-                    if (sizeof(Real) == 8) { o1 = o1 / alpha; o2 = o2 / alpha; }
-                    else { o1 = o1 * (Real)p.inv_alpha_f; o2 = o2 * (Real)p.inv_alpha_f; }
+                    o1 = o1 / alpha; o2 = o2 / alpha;                       // IEEE division in every precision, once per row (src/decodeMinSum.cpp:494-499)
                 }
                 if (offset) { o1 = o1 - delta; o1 = (o1 > 0) ? o1 : (Real)0; o2 = o2 - delta; o2 = (o2 > 0) ? o2 : (Real)0; }
                 const Real s1 = SignOps<Real>::presign(o1, sg), s2 = SignOps<Real>::presign(o2, sg);
@@ -382,13 +379,11 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
                     }
                 }
             }
-#endif
             __syncthreads();
             // ---- variable-node phase (storage columns) --------------------------------------------
             // Two adjacent columns per thread, moved as 8/16-byte vectors: same bytes and layout, half the
             // LDS/STS instructions.  The kernel is bound by the SM-wide issue rate of memory instructions
             // (profiles/r1_summary.md), not by shared-memory bytes.
-#ifndef LDPC_EXPERIMENT_SKIP_VN
             for (int cp = tid; cp < N / 2; cp += nt) {
                 typedef typename Vec2<Real>::type V2;
                 const int col = 2 * cp;
@@ -415,7 +410,6 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
                     }
                 }
             }
-#endif
             if (have_next && gen_done < nblk) {                       // idle threads stage the next frame
                 if (gen_id >= 0 && gen_done + gen_id < nblk) gen(fnext, cwn, gen_done + gen_id);
                 gen_done += gen_threads;

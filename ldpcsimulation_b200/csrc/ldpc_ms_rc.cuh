@@ -67,8 +67,7 @@ LDPC_DEVINL void rc_check_row(unsigned char *msgb, const int slot, const uint4 *
     }
     Real o1 = m1, o2 = m2;
     if (normalized) {
-        if (sizeof(Real) == 8) { o1 = o1 / alpha; o2 = o2 / alpha; }
-        else { o1 = o1 * inv_alpha; o2 = o2 * inv_alpha; }
+        o1 = o1 / alpha; o2 = o2 / alpha;
     }
     if (offset) { o1 = o1 - delta; o1 = (o1 > 0) ? o1 : (Real)0; o2 = o2 - delta; o2 = (o2 > 0) ? o2 : (Real)0; }
     const Real s1 = SignOps<Real>::presign(o1, sg), s2 = SignOps<Real>::presign(o2, sg);
@@ -112,7 +111,7 @@ LDPC_DEVINL float min_xorsign_abs(float a, float b)
 //           FSETP + FSEL + LOP3 on the ALU pipe, which is the pipe that bounds this phase.
 template <int DC, int DV, int NB>
 LDPC_DEVINL void rc_check_row_f32(unsigned char *msgb, const int slot, const uint4 (&sw)[RC_NPRE], const uint4 *__restrict__ sched, const int M, const int j, float (&v)[DC],
-                                  const bool normalized, const bool offset, const float inv_alpha, const float delta)
+                                  const bool normalized, const bool offset, const float inv_alpha, const float delta, const float alpha_div)
 {
     constexpr int NG = DC / 4;
     float m1 = real_inf<float>(), m2 = real_inf<float>();
@@ -139,9 +138,13 @@ LDPC_DEVINL void rc_check_row_f32(unsigned char *msgb, const int slot, const uin
     m1 = fabsf(m1);
     const uint32_t K = __float_as_uint(m1) + __float_as_uint(m2);
     const float mult = SignOps<float>::presign(normalized ? inv_alpha : 1.0f, sg);
+    // alpha_div != 0: alpha is not a power of two, so m * (1/alpha) is not always the correctly rounded m / alpha the
+    // reference computes (src/decodeMinSum.cpp:494-499).  q' = fma(fma(-q, alpha, m), 1/alpha, q) with q = m * RN(1/alpha) is
+    // (Markstein's correction step; no overflow / underflow at message magnitudes): two more FMA-pipe instructions per edge.
+    const float nalpha = SignOps<float>::presign(-alpha_div, sg);
     // the offset variant is a separate copy of the loop: a per-edge `if (offset)` costs a branch per edge (0.35
     // branches per edge in the r1n capture) in the phase that is bound by issue slots
-    auto second_pass = [&](auto with_offset) {
+    auto second_pass = [&](auto with_offset, auto with_div) {
 #pragma unroll
         for (int g = 0; g < NG; g++) {
             const uint4 w = (g < RC_NPRE) ? sw[g] : __ldg(&sched[(size_t)g * M + j]);
@@ -153,6 +156,7 @@ LDPC_DEVINL void rc_check_row_f32(unsigned char *msgb, const int slot, const uin
                 uint32_t rb;
                 asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(rb) : "r"(__float_as_uint(ts)), "r"(K));   // K - bits(ts), FMA pipe
                 float o = __fmul_rn(__uint_as_float(rb), mult);
+                if (decltype(with_div)::value) o = __fmaf_rn(__fmaf_rn(o, nalpha, __uint_as_float(rb)), mult, o);
                 // offset min-sum: sgn(o) max(|o| - delta, 0) = o - clamp(o, -delta, +delta), and the clamp is
                 // min.xorsign.abs(o, delta): the same subtraction of the same operands as the reference's, sign-symmetric
                 if (decltype(with_offset)::value) o = __fadd_rn(o, -min_xorsign_abs(o, delta));
@@ -161,7 +165,9 @@ LDPC_DEVINL void rc_check_row_f32(unsigned char *msgb, const int slot, const uin
             }
         }
     };
-    if (offset) second_pass(std::true_type()); else second_pass(std::false_type());
+    if (alpha_div != 0.0f) { if (offset) second_pass(std::true_type(), std::true_type()); else second_pass(std::false_type(), std::true_type()); }
+    else if (offset) second_pass(std::true_type(), std::false_type());
+    else second_pass(std::false_type(), std::false_type());
 }
 
 template <typename Real, int DC, int DV, int NFIX, int NT_MAX, int MINB>
@@ -246,8 +252,10 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
     };
     for (long long f = blockIdx.x; f < io.n_frames; f += gridDim.x) {
         const uint8_t *cw = codeword_row(io, c, f);
-        if (tid == 0) { fs->uncoded = *unc_next; fs->errors = 0; fs->flag = 0; }
-        for (int w = tid; w < nwords; w += nt) dbits[w] = rnext[w];
+        // the staging words are cleared by the thread that consumes them, before the barrier that precedes the
+        // next frame's generator (which accumulates into them with atomics)
+        if (tid == 0) { fs->uncoded = *unc_next; *unc_next = 0; fs->errors = 0; fs->flag = 0; }
+        for (int w = tid; w < nwords; w += nt) { dbits[w] = rnext[w]; rnext[w] = 0u; }
         for (int cp = tid; cp < N / 2; cp += nt) {
             typedef typename Vec2<Real>::type V2;
             const V2 vr = *reinterpret_cast<const V2 *>(&ybuf[2 * cp]);
@@ -264,8 +272,6 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
         for (int k = 0; k < DC; k++) v[k] = (Real)0;
         fetch_schedule();
         __syncthreads();
-        for (int w = tid; w < nwords; w += nt) rnext[w] = 0u;
-        if (tid == 0) *unc_next = 0;
         const long long fnext = f + gridDim.x;
         const bool have_next = fnext < io.n_frames;
         const uint8_t *cwn = have_next ? codeword_row(io, c, fnext) : nullptr;
@@ -277,7 +283,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
             if (last) for (int w = tid; w < nwords; w += nt) dbits[w] = 0u;
             // ---- check-node phase: one row per thread ------------------------------------------------
             if (has_row) {
-                if constexpr (sizeof(Real) == 4) rc_check_row_f32<DC, DV, NB>(msgb, slot, sw, c.sched, M, tid, v, normalized, offset, inv_alpha, delta);
+                if constexpr (sizeof(Real) == 4) rc_check_row_f32<DC, DV, NB>(msgb, slot, sw, c.sched, M, tid, v, normalized, offset, inv_alpha, delta, p.alpha_div_f);
                 else rc_check_row<Real, DC, DV, NB>(msgb, slot, c.sched, M, tid, v, normalized, offset, alpha, inv_alpha, delta);
             }
             // next frame's channel samples, one block per thread, right after the thread's row: the generator is a long

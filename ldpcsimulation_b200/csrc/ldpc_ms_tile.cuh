@@ -134,8 +134,7 @@ __global__ void __launch_bounds__(NT_MAX, 1) ms_tile_kernel(const CodeDev c, con
                     }
                     Real o1 = m1, o2 = m2;
                     if (normalized) {
-                        if (sizeof(Real) == 8) { o1 = o1 / alpha; o2 = o2 / alpha; }
-                        else { o1 = o1 * (Real)p.inv_alpha_f; o2 = o2 * (Real)p.inv_alpha_f; }
+                        o1 = o1 / alpha; o2 = o2 / alpha;                       // IEEE division in every precision, once per row (src/decodeMinSum.cpp:494-499)
                     }
                     if (offset) { o1 = o1 - delta; o1 = (o1 > 0) ? o1 : (Real)0; o2 = o2 - delta; o2 = (o2 > 0) ? o2 : (Real)0; }
                     s1[q] = SignOps<Real>::presign(o1, sg); s2[q] = SignOps<Real>::presign(o2, sg); mm[q] = m1;

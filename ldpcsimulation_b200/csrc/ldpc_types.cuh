@@ -50,7 +50,8 @@ struct DecParams {
     int      hw_theta, hw_Smult;                      // :175-176
     double   sigma, N0, noiseSigma;                   // decodeMinSum.cpp:146-147, decodeGDBF.cpp:296
     double   uni_scale;     // (sqrt(3)*noiseSigma)*2.0                   decodeGDBF.cpp:322
-    float    inv_alpha_f;   // fp32 instantiation: multiply instead of divide
+    float    inv_alpha_f;   // fp32 instantiation: RN(1/alpha)
+    float    alpha_div_f;   // (float)alpha when the fp32 normalisation needs the division-correction step (alpha not a power of two), else 0
     float    ms_scale_f, ms_step_f, Ymax_f;   // fp32 front end (fp32 instantiation fed by the Philox channel or fp32 samples)
     int      iter_hist_len;
     int      rows_per_step; // GDBF noise rows consumed per flip step

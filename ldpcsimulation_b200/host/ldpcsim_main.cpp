@@ -319,7 +319,7 @@ int main(int argc, char *argv[])
       while (getline(ss, t, ',')) if (!t.empty()) devs.push_back(atoi(t.c_str())); }
     if (ldpc_gpu_init(devs.data(), (int)devs.size())) { cerr << "ldpc_gpu_init: " << ldpc_gpu_last_error() << endl; return 1; }
     const int T = cfg.num_iterations;
-    const int ith_len = T * (((f & RD) && cfg.maxphase > 1) ? cfg.maxphase : 1) + 1;
+    const int ith_len = ldpc_gpu_iter_hist_len(&cfg);
     vector<Shard> sh(devs.size());
     for (size_t g = 0; g < devs.size(); g++) {
         sh[g].device = devs[g];

@@ -80,7 +80,8 @@ def test_decode_batch_argument_checks():
 def test_simulate_and_misc_argument_checks():
     L = capi.lib()
     code = capi.Code(code_path("PEG"))
-    dec = capi.Decoder(code, cases.cfg_for("decodeMinSum"))
+    cfg = cases.cfg_for("decodeMinSum")
+    dec = capi.Decoder(code, cfg)
     ch = abi.Channel(3.0, 0.5)
     cnt = abi.Counters()
     a = abi.SimArgs(1, 0, -5, 0, 0, 0)
@@ -89,7 +90,7 @@ def test_simulate_and_misc_argument_checks():
     assert L.ldpc_gpu_simulate(dec.h, C.byref(ch), C.byref(a), None) == abi.ERR_INVALID_ARG
     assert L.ldpc_gpu_simulate(dec.h, C.byref(ch), C.byref(a), C.byref(cnt)) == 0 and cnt.totalWords == 10
     assert L.ldpc_gpu_simulate(dec.h, C.byref(ch), C.byref(a), C.byref(cnt)) == 0 and cnt.totalWords == 20   # counters are ADDED
-    assert L.ldpc_gpu_allreduce_counters(C.byref(cnt), code.N, 10, 1) == abi.ERR_COMM                        # no communicator
+    assert L.ldpc_gpu_allreduce_counters(C.byref(cnt), code.N, C.byref(cfg)) == abi.ERR_COMM                        # no communicator
     assert L.ldpc_gpu_init((C.c_int * 1)(42), 1) == abi.ERR_INVALID_ARG
     assert L.ldpc_gpu_init(None, 0) == 0
     assert L.ldpc_gpu_decoder_destroy(None) == 0 and L.ldpc_gpu_code_destroy(None) == 0
