@@ -81,6 +81,12 @@ extern "C" {
                                    binary16 pair, v2c clamped to +-512.  NOT the reference's arithmetic: decisions
                                    match on converging frames, BER/FER within confidence intervals */
 
+/* ---- on-device noise generator (Philox4x32-10 keyed by (seed, frame id) either way) ---- */
+#define LDPC_GPU_CHANNEL_EXACT 0   /* Box-Muller in explicitly rounded fp32 polynomials: reproducible bit for bit on a CPU (oracle/) */
+#define LDPC_GPU_CHANNEL_FAST  1   /* Box-Muller on the SFU approximations (lg2 / sqrt / sin / cos .approx) and y = x fma(sigma, n, 1) in
+                                      fp32: deterministic per GPU architecture, ~5x cheaper; the samples are available through
+                                      ldpc_gpu_channel_dump only */
+
 /* ---- where a caller buffer lives --------------------------------------- */
 #define LDPC_GPU_MEM_HOST    0
 #define LDPC_GPU_MEM_DEVICE  1
@@ -119,7 +125,7 @@ typedef struct ldpc_gpu_decoder_cfg {
     int32_t  windowsize;      /* output smoothing window                              */
     int32_t  maxphase;        /* RNGDBF maxphase / NGDBFhw maxPhases                  */
     int32_t  Tswitch;         /* mode-switching start (decodeGDBF.cpp:51), default 0  */
-    int32_t  reserved0;
+    int32_t  channel_mode;    /* LDPC_GPU_CHANNEL_*: noise generator of ldpc_gpu_simulate / _channel_dump / _redecode_stats */
     double   w;               /* NGDBFhw syndrome weight (NGDBFhw.cpp:50)             */
     double   theta0;          /* NGDBFhw threshold before quantisation (:57)          */
     double   MAXLLR;          /* BP message clip (decodeBP.cpp:58), default 20        */
@@ -254,6 +260,10 @@ int  ldpc_gpu_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t 
 /* Timing of the last decode/simulate call on this decoder: kernel time from
  * CUDA events on the launching stream, and the number of kernel launches. */
 int  ldpc_gpu_last_timing(const ldpc_gpu_decoder *dec, double *kernel_ms, int64_t *launches);
+/* LDPC_GPU_PREC_F16X2 on an exact lattice (csrc/ldpc_ms_x2.cuh): *exact_lattice = 1 when the decoder runs the certified
+ * two-frames-per-lane kernel, and *redo_frames = frames (since creation) it could not certify and handed to the fp64
+ * instantiation.  Both optional. */
+int  ldpc_gpu_decoder_stats(const ldpc_gpu_decoder *dec, int64_t *redo_frames, int32_t *exact_lattice);
 /* Launch geometry the library chose (for DESIGN/roofline reporting). */
 int  ldpc_gpu_decoder_geometry(const ldpc_gpu_decoder *dec, int *grid, int *block, int *smem_bytes,
                                int *frames_per_cta);

@@ -32,6 +32,7 @@ MACRO_FLAGS = {
 }
 
 PREC_F64, PREC_F32, PREC_F16X2 = 0, 1, 2
+CHANNEL_EXACT, CHANNEL_FAST = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 DT_F64, DT_F32, DT_F16, DT_Q8 = 0, 1, 2, 3
 HW_QBUF = 2648
@@ -43,7 +44,7 @@ class DecoderCfg(C.Structure):
         ("Ymax", C.c_double), ("Q", C.c_int32), ("NQ", C.c_int32),
         ("alpha", C.c_double), ("delta", C.c_double), ("theta", C.c_double), ("lambda_", C.c_double),
         ("noiseScale", C.c_double), ("windowsize", C.c_int32), ("maxphase", C.c_int32),
-        ("Tswitch", C.c_int32), ("reserved0", C.c_int32),
+        ("Tswitch", C.c_int32), ("channel_mode", C.c_int32),
         ("w", C.c_double), ("theta0", C.c_double), ("MAXLLR", C.c_double),
     ]
 

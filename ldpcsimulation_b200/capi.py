@@ -21,7 +21,7 @@ EXPORTS = [
     "ldpc_gpu_code_random_codewords",
     "ldpc_gpu_decoder_cfg_default", "ldpc_gpu_iter_hist_len", "ldpc_gpu_decoder_create", "ldpc_gpu_decoder_destroy",
     "ldpc_gpu_decoder_set_codewords", "ldpc_gpu_decode_batch", "ldpc_gpu_simulate", "ldpc_gpu_redecode_stats", "ldpc_gpu_channel_dump",
-    "ldpc_gpu_philox4x32", "ldpc_gpu_last_timing", "ldpc_gpu_decoder_geometry",
+    "ldpc_gpu_philox4x32", "ldpc_gpu_last_timing", "ldpc_gpu_decoder_stats", "ldpc_gpu_decoder_geometry",
     "ldpc_gpu_comm_unique_id", "ldpc_gpu_comm_init", "ldpc_gpu_comm_destroy", "ldpc_gpu_allreduce_counters",
 ]
 
@@ -60,6 +60,7 @@ def lib():
                                             C.c_void_p, C.c_void_p, C.c_int64]
         L.ldpc_gpu_philox4x32.argtypes = [C.c_void_p] * 3
         L.ldpc_gpu_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        L.ldpc_gpu_decoder_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
         L.ldpc_gpu_decoder_geometry.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
         L.ldpc_gpu_init.argtypes = [C.c_void_p, C.c_int]
         L.ldpc_gpu_comm_unique_id.argtypes = [C.c_void_p]
@@ -136,6 +137,12 @@ class Decoder:
         v = [C.c_int() for _ in range(4)]
         check(lib().ldpc_gpu_decoder_geometry(self.h, *[C.byref(x) for x in v]))
         return dict(zip(("grid", "block", "smem_bytes", "ctas_per_sm"), [x.value for x in v]))
+
+    def stats(self):
+        """(exact_lattice, redo_frames) of the LDPC_GPU_PREC_F16X2 lattice kernel (csrc/ldpc_ms_x2.cuh)."""
+        r, x = C.c_int64(), C.c_int32()
+        check(lib().ldpc_gpu_decoder_stats(self.h, C.byref(r), C.byref(x)))
+        return bool(x.value), r.value
 
     def last_timing(self):
         ms, n = C.c_double(), C.c_int64()

@@ -81,6 +81,13 @@ LDPC_DEVINL const uint8_t *codeword_row(const FrameIO &io, const CodeDev &c, lon
     return nullptr;
 }
 
+// LDPC_GPU_CHANNEL_FAST: y = x (1 + sigma n) in fp32, one FFMA (the sign flip is exact)
+LDPC_DEVINL float fast_channel_sample(const DecParams &p, const uint8_t *cw, int i, int N, float n)
+{
+    const float y = __fmaf_rn(p.sigma_f, n, 1.0f);
+    return (cw && i < N && cw[i]) ? -y : y;
+}
+
 // a2: four raw channel samples y = x(1 + sigma n) of block b (src/decodeMinSum.cpp:216), from the
 // caller's array or from the Philox channel.
 LDPC_DEVINL void raw_samples4(const FrameIO &io, const DecParams &p, const CodeDev &c, long long f, const uint8_t *cw, int b, double y[4])
@@ -101,6 +108,11 @@ LDPC_DEVINL void raw_samples4(const FrameIO &io, const DecParams &p, const CodeD
             }
             else y[q] = 1.0;
         }
+    } else if (p.channel_mode == LDPC_GPU_CHANNEL_FAST) {
+        float n[4];
+        normal4_fast(io.seed, (unsigned long long)(io.frame_begin + f), (uint32_t)b, 0u, STREAM_CHANNEL, n);
+#pragma unroll
+        for (int q = 0; q < 4; q++) y[q] = (double)fast_channel_sample(p, cw, i0 + q, c.N, n[q]);
     } else {
         float n[4];
         normal4(io.seed, (unsigned long long)(io.frame_begin + f), (uint32_t)b, 0u, STREAM_CHANNEL, n);

@@ -26,6 +26,7 @@
 #include "ldpc_ms_tile.cuh"
 #include "ldpc_ms_h2.cuh"
 #include "ldpc_ms_h2rc.cuh"
+#include "ldpc_ms_x2.cuh"
 #include "ldpc_bf_kernels.cuh"
 
 using namespace ldpc;
@@ -284,7 +285,32 @@ struct ldpc_gpu_decoder {
     uint8_t *d_cwtab = nullptr; long long n_cw = 0;
     double last_kernel_ms = 0; long long last_launches = 0;
     int N = 0, M = 0;
+    // exact-lattice packed kernel (ldpc_ms_x2.cuh): frames it cannot certify are decoded by an fp64 decoder on the same stream
+    bool x2 = false; float x2_cap = 0, x2_m0 = 0;
+    ldpc_gpu_decoder *redo = nullptr;
+    long long *d_redo_list = nullptr; size_t redo_cap = 0;
+    unsigned int *d_redo_count = nullptr; unsigned long long *d_redo_total = nullptr;
 };
+
+// Does the configuration put plain / offset min-sum on a lattice binary16 holds exactly (ldpc_ms_x2.cuh)?
+// u = Ymax / (2^Q - 1) = step / 2 must be a power of two, delta a multiple of u, and the c2v cap C must leave room on both
+// sides: |S| <= Ymax + dv_max C <= 2047 u, and (dv_min - 1) C - Ymax >= m0, the stable-state bound of the lemma.
+static bool x2_lattice(const ldpc_gpu_decoder_cfg &c, int dv_min, int dv_max, float *cap, float *m0)
+{
+    if (c.kind != LDPC_GPU_KIND_MINSUM || !(c.flags & LDPC_GPU_F_QUANTIZE_SAMPLES) || (c.flags & LDPC_GPU_F_NORMALIZED_MS)) return false;
+    if (c.Q < 2 || c.Q > 8 || !(c.Ymax > 0) || dv_min < 3) return false;
+    const double Yu = pow(2.0, c.Q) - 1.0, u = c.Ymax / Yu;
+    int ex;
+    if (frexp(u, &ex) != 0.5 || ex - 1 < -14 || ex - 1 > 4) return false;
+    const double du = (c.flags & LDPC_GPU_F_OFFSET_MS) ? c.delta / u : 0.0;
+    if (du < 0 || du != floor(du) || du > 64) return false;
+    double cap_u = floor((2047.0 - Yu) / dv_max);
+    if (const char *e = getenv("LDPC_GPU_X2_CAP_UNITS")) cap_u = std::min(cap_u, (double)atoi(e));   // test hook: a low cap exercises the redo path
+    const double m0_u = ceil((Yu + (dv_min - 1) * du) / (dv_min - 2));
+    if ((dv_min - 1) * cap_u - Yu < m0_u || cap_u < m0_u) return false;
+    *cap = (float)(cap_u * u); *m0 = (float)(m0_u * u);
+    return true;
+}
 
 static int rows_per_step(uint32_t fl) { return ((fl & LDPC_GPU_F_ADDNOISE) ? 1 : 0) + ((fl & LDPC_GPU_F_QUANTIZEPROBABILITIES) ? 1 : 0); }
 static int iter_hist_len(const ldpc_gpu_decoder_cfg &c)
@@ -409,6 +435,14 @@ static int pick_kernel(ldpc_gpu_decoder *d)
             if (v.row_slot && !getenv("LDPC_GPU_NO_RC")) {                 // c2v pairs resident in registers (ldpc_ms_h2rc.cuh)
                 d->fn = (KernelFn)ms_h2rc_kernel<32, 6, 2048, 384, 2>;
                 smem = ms_h2rc_smem_bytes(v);
+                // exact lattice: decisions certified identical to the reference's, fp64 redo of the rest (ldpc_ms_x2.cuh)
+                if (!getenv("LDPC_GPU_NO_X2") && v.M == 384 && x2_lattice(d->cfg, 6, 6, &d->x2_cap, &d->x2_m0)) {
+                    d->x2 = true;
+                    const char *xv = getenv("LDPC_GPU_X2_VARIANT");   // A/B switch: offsets kept in registers | re-read, 2 or 3 CTAs per SM
+                    const int variant = xv ? atoi(xv) : 1;
+                    d->fn = variant == 0 ? (KernelFn)ms_x2_kernel<32, 6, 2048, 384, 2, true> : (KernelFn)ms_x2_kernel<32, 6, 2048, 384, 2, false>;
+                    smem = ms_x2_smem_bytes(v);
+                }
             }
             goto geometry;
         }
@@ -527,6 +561,7 @@ static int validate_cfg(const ldpc_gpu_decoder_cfg &c)
     if (c.num_iterations < 0) return set_err(LDPC_GPU_ERR_INVALID_ARG, "num_iterations < 0");
     if (c.precision != LDPC_GPU_PREC_F64 && c.precision != LDPC_GPU_PREC_F32 && c.precision != LDPC_GPU_PREC_F16X2)
         return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown precision");
+    if (c.channel_mode != LDPC_GPU_CHANNEL_EXACT && c.channel_mode != LDPC_GPU_CHANNEL_FAST) return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown channel_mode");
     if (c.precision == LDPC_GPU_PREC_F16X2 && c.kind != LDPC_GPU_KIND_MINSUM)
         return set_err(LDPC_GPU_ERR_UNSUPPORTED, "LDPC_GPU_PREC_F16X2 exists for the min-sum family only");
     if (c.kind == LDPC_GPU_KIND_GDBF) {
@@ -558,6 +593,10 @@ extern "C" int ldpc_gpu_decoder_destroy(ldpc_gpu_decoder *d)
         if (s.k0) cudaEventDestroy(s.k0); if (s.k1) cudaEventDestroy(s.k1);
         if (s.st) cudaStreamDestroy(s.st);
     }
+    if (d->redo) ldpc_gpu_decoder_destroy(d->redo);
+    if (d->d_redo_list) cudaFree(d->d_redo_list);
+    if (d->d_redo_count) cudaFree(d->d_redo_count);
+    if (d->d_redo_total) cudaFree(d->d_redo_total);
     if (d->d_counters) cudaFree(d->d_counters);
     if (d->d_ws) cudaFree(d->d_ws);
     if (d->d_cwtab) cudaFree(d->d_cwtab);
@@ -580,6 +619,12 @@ extern "C" int ldpc_gpu_decoder_create(const ldpc_gpu_code *code, const ldpc_gpu
         ((cfg->kind == LDPC_GPU_KIND_MINSUM || (cfg->kind == LDPC_GPU_KIND_BP && cfg->precision != LDPC_GPU_PREC_F64)) &&
          (rc = build_schedule(d, code, cfg->precision == LDPC_GPU_PREC_F64 ? 8 : 4))) ||
         (rc = pick_kernel(d))) { ldpc_gpu_decoder_destroy(d); return rc; }
+    if (d->x2) {
+        ldpc_gpu_decoder_cfg c64 = *cfg; c64.precision = LDPC_GPU_PREC_F64;
+        if ((rc = ldpc_gpu_decoder_create(code, &c64, device, &d->redo))) { ldpc_gpu_decoder_destroy(d); return rc; }
+        if (cudaMalloc(&d->d_redo_count, 2 * sizeof(unsigned int)) != cudaSuccess || cudaMalloc(&d->d_redo_total, sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMemset(d->d_redo_total, 0, sizeof(unsigned long long)) != cudaSuccess) { ldpc_gpu_decoder_destroy(d); return set_err(LDPC_GPU_ERR_NOMEM, "redo-list allocation failed"); }
+    }
     for (Slot &s : d->slot) {
         if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&s.k0) != cudaSuccess ||
             cudaEventCreate(&s.k1) != cudaSuccess) { ldpc_gpu_decoder_destroy(d); return set_err(LDPC_GPU_ERR_CUDA, "stream/event creation failed"); }
@@ -613,6 +658,12 @@ extern "C" int ldpc_gpu_decoder_create(const ldpc_gpu_code *code, const ldpc_gpu
     p.ms_scale_f = (float)((Nq - 1) / (2.0 * cfg->Ymax)); p.ms_step_f = (float)p.ms_step; p.Ymax_f = (float)cfg->Ymax;
     p.iter_hist_len = iter_hist_len(*cfg);
     p.rows_per_step = rows_per_step(cfg->flags);
+    p.channel_mode = cfg->channel_mode;
+    {
+        auto h2 = [](float x) { const __half h = __float2half_rn(x); unsigned short b; memcpy(&b, &h, 2); return (uint32_t)b | ((uint32_t)b << 16); };
+        p.x2_delta2 = h2((cfg->flags & LDPC_GPU_F_OFFSET_MS) ? (float)cfg->delta : 0.0f);
+        p.x2_cap2 = h2(d->x2_cap); p.x2_m02 = h2(d->x2_m0);
+    }
     *out = d;
     return LDPC_GPU_OK;
 }
@@ -643,6 +694,23 @@ extern "C" int ldpc_gpu_last_timing(const ldpc_gpu_decoder *d, double *ms, int64
     return LDPC_GPU_OK;
 }
 
+extern "C" int ldpc_gpu_decoder_stats(const ldpc_gpu_decoder *d, int64_t *redo_frames, int32_t *exact_lattice)
+{
+    if (!d) return set_err(LDPC_GPU_ERR_INVALID_ARG, "decoder is NULL");
+    if (exact_lattice) *exact_lattice = d->x2 ? 1 : 0;
+    if (redo_frames) {
+        *redo_frames = 0;
+        if (d->x2) {
+            unsigned long long h = 0;
+            CU_TRY(cudaSetDevice(d->device));
+            CU_TRY(cudaDeviceSynchronize());
+            CU_TRY(cudaMemcpy(&h, d->d_redo_total, sizeof h, cudaMemcpyDeviceToHost));
+            *redo_frames = (int64_t)h;
+        }
+    }
+    return LDPC_GPU_OK;
+}
+
 // per-call channel constants, with the reference's expressions (decodeMinSum.cpp:146-147)
 static int channel_params(const ldpc_gpu_decoder *d, const ldpc_gpu_channel *ch, DecParams &p)
 {
@@ -652,6 +720,7 @@ static int channel_params(const ldpc_gpu_decoder *d, const ldpc_gpu_channel *ch,
     p.sigma = sqrt(p.N0 / 2.0);
     p.noiseSigma = p.sigma * p.noiseScale;                        // decodeGDBF.cpp:296
     p.uni_scale = sqrt(3) * p.noiseSigma * 2.0;                   // decodeGDBF.cpp:322
+    p.sigma_f = (float)p.sigma;
     return LDPC_GPU_OK;
 }
 
@@ -683,9 +752,31 @@ static int launch(ldpc_gpu_decoder *d, const DecParams &p, const FrameIO &io, cu
     const long long want = std::min<long long>((io.n_frames + d->frames_per_cta - 1) / d->frames_per_cta, d->grid_full);
     if (want <= 0) return LDPC_GPU_OK;
     FrameIO io2 = io; io2.workspace = d->d_ws; io2.ws_stride = d->ws_stride;
+    if (d->x2) {
+        if ((size_t)io.n_frames > d->redo_cap) {          // grows only (streams of this decoder may still read the old list: drain them)
+            for (Slot &s : d->slot) if (s.st) CU_TRY(cudaStreamSynchronize(s.st));
+            if (d->d_redo_list) cudaFree(d->d_redo_list);
+            d->d_redo_list = nullptr; d->redo_cap = 0;
+            const size_t cap = std::max<size_t>((size_t)io.n_frames, 1 << 16);
+            CU_TRY(cudaMalloc(&d->d_redo_list, 2 * cap * sizeof(long long)));      // one half per pipeline slot
+            d->redo_cap = cap;
+        }
+        const int half = (st == d->slot[1].st) ? 1 : 0;
+        io2.redo_list = d->d_redo_list + (size_t)half * d->redo_cap;
+        io2.redo_count = d->d_redo_count + half;
+        io2.redo_total = d->d_redo_total;
+        CU_TRY(cudaMemsetAsync(io2.redo_count, 0, sizeof(unsigned int), st));
+    }
     d->fn<<<(unsigned)want, d->block, d->smem, st>>>(d->dev, p, io2);
     CU_TRY(cudaGetLastError());
     d->last_launches++;
+    if (d->x2) {                                          // the frames the packed kernel could not certify, fp64, same stream, no host round trip
+        FrameIO io3 = io; io3.frame_list = io2.redo_list; io3.n_frames_dev = io2.redo_count;
+        ldpc_gpu_decoder *r = d->redo;
+        r->fn<<<(unsigned)std::min<long long>(io.n_frames, r->grid_full), r->block, r->smem, st>>>(r->dev, p, io3);
+        CU_TRY(cudaGetLastError());
+        d->last_launches++;
+    }
     return LDPC_GPU_OK;
 }
 

@@ -228,12 +228,17 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
         if (unc) atomicAdd(unc_next, unc);
     };
 
-    if ((long long)blockIdx.x < io.n_frames) {
+    // redo launches of the exact-lattice packed kernel (ldpc_ms_x2.cuh): the launch's frames are the batch frames
+    // frame_list[0 .. *n_frames_dev)
+    const long long n_launch = io.n_frames_dev ? min((long long)*io.n_frames_dev, io.n_frames) : io.n_frames;
+    auto frame_of = [&](long long q) -> long long { return io.frame_list ? io.frame_list[q] : q; };
+    if ((long long)blockIdx.x < n_launch) {
         for (int w = tid; w < nwords; w += nt) rnext[w] = 0u;
         if (tid == 0) *unc_next = 0;
         __syncthreads();
-        const uint8_t *cw0 = codeword_row(io, c, blockIdx.x);
-        for (int b = tid; b < nblk; b += nt) gen(blockIdx.x, cw0, b);
+        const long long f0 = frame_of(blockIdx.x);
+        const uint8_t *cw0 = codeword_row(io, c, f0);
+        for (int b = tid; b < nblk; b += nt) gen(f0, cw0, b);
         __syncthreads();
     }
 
@@ -250,7 +255,8 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
             }
         }
     };
-    for (long long f = blockIdx.x; f < io.n_frames; f += gridDim.x) {
+    for (long long fq = blockIdx.x; fq < n_launch; fq += gridDim.x) {
+        const long long f = frame_of(fq);
         const uint8_t *cw = codeword_row(io, c, f);
         // the staging words are cleared by the thread that consumes them, before the barrier that precedes the
         // next frame's generator (which accumulates into them with atomics)
@@ -272,8 +278,8 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
         for (int k = 0; k < DC; k++) v[k] = (Real)0;
         fetch_schedule();
         __syncthreads();
-        const long long fnext = f + gridDim.x;
-        const bool have_next = fnext < io.n_frames;
+        const bool have_next = fq + gridDim.x < n_launch;
+        const long long fnext = have_next ? frame_of(fq + gridDim.x) : 0;
         const uint8_t *cwn = have_next ? codeword_row(io, c, fnext) : nullptr;
         int gen_done = 0;
         if (p.T == 0) __syncthreads();

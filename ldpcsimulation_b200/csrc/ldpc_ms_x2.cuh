@@ -1,0 +1,342 @@
+// ldpc_ms_x2.cuh -- min-sum / offset min-sum on an EXACT LATTICE, two frames per lane, decisions certified
+// identical to the reference's (LDPC_GPU_PREC_F16X2 when the configuration admits it; else ms_h2rc_kernel).
+//
+// Lattice.  With `quantizeSamples` the channel values are k * step, step = 2 Ymax / (2^Q - 1), or +-Ymax
+// (quantize(), src/decodeMinSum.cpp:480-489).  When u = step / 2 is a power of two (e.g. Ymax = 1.9375, Q = 5:
+// u = 1/16) and delta is a multiple of u, every message and every sum of plain / offset min-sum
+// (src/decodeMinSum.cpp:410-476, :503-515) is an integer multiple of u, in the reference's doubles as well.
+// binary16 holds the integers up to 2048 exactly, so as long as every |value| <= 2047 u the packed-half
+// arithmetic below (HADD2 / HMNMX2 on the same edge of two frames) IS the reference's arithmetic: no rounding
+// happens anywhere, the operation order is irrelevant.
+//
+// Growth.  The reference's messages are unbounded: once a frame has converged they grow about (dv - 1)-fold per
+// iteration (measured: 1e5 u and more at T = 10), while frames that have not converged stay small (max |c2v| about
+// 22 u at 3.6 - 4.0 dB on the 802.3an code).  The kernel caps c2v magnitudes at C (`cap`), chosen so that
+// |S| <= Ymax + dv C <= 2047 u, and PROVES per frame that the cap cannot have changed a decision:
+//
+//   Lemma (stable state).  Let x be a codeword (as +-1), dvm = min column weight >= 3, and suppose that before a
+//   check phase every v2c on an edge of variable i has sign x_i and magnitude >= m, with
+//   m >= m0 = (Ymax + (dvm - 1) delta) / (dvm - 2).  Then every c2v is x_i max(min_others - delta, 0) (min-sum with
+//   all parities satisfied), of magnitude >= m - delta, so the next v2c = y_i + sum_{others} c2v has sign x_i and
+//   magnitude >= (dvm - 1)(m - delta) - Ymax >= m, and S_i = y_i + sum c2v has sign x_i.  By induction every later
+//   decision vector equals x.  The same induction holds when c2v magnitudes are capped at any C with
+//   (dvm - 1) C - Ymax >= m0 (the bound becomes min(m, (dvm - 1) C - Ymax) >= m0).  So from a stable state on, the
+//   capped and the uncapped decoder output the same decisions, x, at every iteration.
+//
+//   Certificate.  While the cap has never engaged the frame's arithmetic is exact (state EXACT).  Every check phase of such a
+//   frame also verifies the lemma's premise on its (exact) inputs -- every row has an even number of negative v2c and
+//   min |v2c| >= m0, and every v2c has the sign of its variable's a-posteriori sum (one LOP3 per edge) -- and the frame
+//   becomes CERTIFIED as soon as all rows agree; from then on the cap is harmless.  If the cap engages in a check phase whose
+//   inputs do not satisfy the premise, the frame is UNCERTIFIED: it is not reported from here but appended to a redo list, and
+//   the host library decodes the listed frames with the fp64 parity instantiation (ms_rc_kernel<double>) on the same stream.
+//   Either way every reported decision vector is the reference's, bit for bit; a-posteriori sums (out_soft) are the
+//   reference's only while the cap has not engaged (they saturate near Ymax + dv C afterwards) -- callers that need the
+//   sums of converged frames use fp32 / fp64.
+//
+// Kernel structure: ms_h2rc_kernel's (one CTA per frame pair, one thread per check row, the row's 32 c2v words
+// resident in registers, a-posteriori sums published through shared memory), with the check row rewritten around the
+// per-row constants: o1 / o2 (offset and cap applied once per row), second pass = HSET2 + 2 LOP3 per edge.
+#pragma once
+#include "ldpc_ms_h2rc.cuh"
+
+namespace ldpc {
+
+enum { X2_EXACT = 0, X2_CERT = 2, X2_UNCERT = 3 };
+
+// lattice constants derived on the host (ldpc_gpu.cu: x2_lattice); all in LLR units (multiples of u)
+// (binary16 pairs, both halves equal; kept in DecParams = the constant bank, so they cost no registers)
+
+static inline size_t ms_x2_smem_bytes(const CodeDev &c)
+{
+    return ((size_t)64 + 4 * ((size_t)c.dvN + 2 * (size_t)c.N) + 8 * (size_t)((c.N + 31) / 32) + 15) & ~(size_t)15;
+}
+
+// schedule word of step group g of row j.  The second pass re-reads the row's words through the `volatile` form: ptxas
+// otherwise keeps the first pass's 32 offsets alive (merging the loads) and spills them around the 32 c2v registers.
+LDPC_DEVINL uint4 x2_sched(const uint4 *p)
+{
+    uint4 r;
+    asm("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+LDPC_DEVINL uint4 x2_sched_again(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// (a & b) ^ c as ONE LOP3 (NVVM re-associates the XOR chain into three otherwise)
+LDPC_DEVINL uint32_t x2_and_xor(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// One check row of a frame pair.  KEEP: the row's 32 schedule offsets stay in registers between the passes instead of being
+// read again.  Returns the row's flag word: bit 0 / 16 = premise violated (frame a / b), bit 1 / 17 = cap engaged.
+template <int DC, int DV, int NB, int M, bool KEEP>
+LDPC_DEVINL uint32_t x2_check_row(unsigned char *msgb, const int slot, const uint4 *__restrict__ sched, const int j,
+                                  uint32_t (&v)[DC], const DecParams &k)
+{
+    constexpr int NG = DC / 4;
+    const uint32_t INF2 = 0x7bff7bffu;                                             // 65504, 65504
+    uint32_t m1 = INF2, m2 = INF2, acc = 0u;
+    uint32_t offk[KEEP ? DC : 1];
+    // the schedule words are read in order, one group ahead (`volatile` keeps ptxas from hoisting all eight loads -- 32 live
+    // offsets next to the 32 c2v registers -- and from merging the two passes' loads)
+    uint4 wn = KEEP ? x2_sched(&sched[j]) : x2_sched_again(&sched[j]);
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+        const uint4 w = wn;
+        if (g + 1 < NG) wn = KEEP ? x2_sched(&sched[(size_t)(g + 1) * M + j]) : x2_sched_again(&sched[(size_t)(g + 1) * M + j]);
+        const uint32_t off[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int e = g * 4 + q;
+            if (KEEP) offk[e] = off[q];
+            uint32_t so;
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(so) : "r"((uint32_t)slot), "r"((uint32_t)-NB), "r"(off[q]));
+            const uint32_t s = *reinterpret_cast<const uint32_t *>(msgb + DV * NB + so);
+            v[e] = h2_bits(__hsub2(h2_from(s), h2_from(v[e])));                    // v2c = sum - c2v (exact)
+            acc |= v[e] ^ s;                                            // bit 15 / 31: sign(v2c) != sign(S)
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q += 2) {
+            const uint32_t a = v[g * 4 + q], b = v[g * 4 + q + 1];
+            const uint32_t lo = h2_min_xorsign_abs(a, b);
+            const __half2 hi = __hmax2(__habs2(h2_from(a)), __habs2(h2_from(b)));
+            const __half2 t = __hmax2(__habs2(h2_from(m1)), __habs2(h2_from(lo)));
+            m2 = h2_bits(__hmin2(__hmin2(t, h2_from(m2)), hi));
+            m1 = h2_min_xorsign_abs(m1, lo);
+        }
+    }
+    const uint32_t sg = m1 & 0x80008000u;                                          // the rows' sign products (both frames)
+    const uint32_t m1a = m1 & 0x7fff7fffu;
+    const __half2 zero2 = h2_from(0u);
+    // offset (:503-515; delta = 0 for plain min-sum) and cap, once per row
+    const __half2 t1 = __hmax2(__hsub2(h2_from(m1a), h2_from(k.x2_delta2)), zero2);
+    const __half2 t2 = __hmax2(__hsub2(h2_from(m2), h2_from(k.x2_delta2)), zero2);
+    const __half2 o1 = __hmin2(t1, h2_from(k.x2_cap2)), o2 = __hmin2(t2, h2_from(k.x2_cap2));
+    const uint32_t eng = __hgt2_mask(t2, h2_from(k.x2_cap2));                         // t2 >= t1
+    const uint32_t bad = ~__hge2_mask(h2_from(m1a), h2_from(k.x2_m02)) | sg | acc;       // bit 15 / 31 of each half
+    const uint32_t flags = ((eng & 0x00010001u) << 1) | ((bad >> 15) & 0x00010001u);
+    uint32_t s1 = h2_bits(o1) ^ sg, d12 = h2_bits(o1) ^ h2_bits(o2);
+    asm("" : "+r"(s1), "+r"(d12));                                              // keep the two row constants as they are: two LOP3 per edge below
+    const uint4 *sched2 = sched + k.zero;                                        // == sched, but ptxas cannot merge the second pass's loads with the first's
+    if (!KEEP) wn = x2_sched_again(&sched2[j]);
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+        const uint4 w = wn;
+        if (!KEEP && g + 1 < NG) wn = x2_sched_again(&sched2[(size_t)(g + 1) * M + j]);
+        const uint32_t off[4] = { KEEP ? offk[4 * g] : w.x, KEEP ? offk[4 * g + 1] : w.y, KEEP ? offk[4 * g + 2] : w.z, KEEP ? offk[4 * g + 3] : w.w };
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int e = g * 4 + q;
+            const uint32_t eq = __heq2_mask(__habs2(h2_from(v[e])), h2_from(m1a));  // 0xffff where this edge attains the row minimum
+            const uint32_t o = x2_and_xor(eq, d12, x2_and_xor(v[e], 0x80008000u, s1));   // sign(v) s1, or sign(v) s2 on the argmin edge
+            v[e] = o;                                                              // c2v, kept for the next iteration
+            *reinterpret_cast<uint32_t *>(msgb + off[q]) = o;
+        }
+    }
+    return flags;
+}
+
+// Lean channel front ends of the min-sum family (fp32 conditioning): the sample source is a launch constant,
+// so each source gets its own straight-line code instead of raw_samples4's per-sample dispatch through doubles.
+enum { SRC_PHILOX = 0, SRC_PHILOX_FAST = 1, SRC_Q8 = 2, SRC_OTHER = 3 };
+
+template <int SRC>
+LDPC_DEVINL void ms_cond4_f32(const FrameIO &io, const DecParams &p, const CodeDev &c, const long long f, const uint8_t *cw, const int b,
+                              const uint32_t qflags, const bool fcond, float (&vf)[4])
+{
+    const int i0 = 4 * b;
+    if (SRC == SRC_PHILOX) {                                   // same values as raw_samples4 + condition_ms_f32, bit for bit
+        float n[4];
+        normal4(io.seed, (unsigned long long)(io.frame_begin + f), (uint32_t)b, 0u, STREAM_CHANNEL, n);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const double x = (cw && cw[i0 + q]) ? -1.0 : 1.0;
+            vf[q] = condition_ms_f32((float)__dmul_rn(x, __dadd_rn(1.0, __dmul_rn(p.sigma, (double)n[q]))), p, qflags);
+        }
+    } else if (SRC == SRC_PHILOX_FAST) {
+        float n[4];
+        normal4_fast(io.seed, (unsigned long long)(io.frame_begin + f), (uint32_t)b, 0u, STREAM_CHANNEL, n);
+#pragma unroll
+        for (int q = 0; q < 4; q++) vf[q] = condition_ms_f32(fast_channel_sample(p, cw, i0 + q, c.N, n[q]), p, qflags);
+    } else if (SRC == SRC_Q8) {                                // four quantiser levels in one 32-bit load (N % 4 == 0, base 4-byte aligned)
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(io.y) + (((size_t)f * c.N) >> 2) + b);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = (int)(signed char)((w >> (8 * q)) & 0xffu);
+            vf[q] = (k >= 32) ? p.Ymax_f : (k <= -32) ? -p.Ymax_f : (float)__dmul_rn((double)k, p.ms_step);
+        }
+    } else {
+        double y4[4];
+        raw_samples4(io, p, c, f, cw, b, y4);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (fcond) vf[q] = condition_ms_f32((float)y4[q], p, qflags);
+            else {
+                double d = y4[q];
+                if (qflags & LDPC_GPU_F_QUANTIZE_SAMPLES) d = quantize_ms(d, p);
+                if (qflags & LDPC_GPU_F_SATURATE_SAMPLES) d = fmin(fmax(d, -p.Ymax), p.Ymax);
+                vf[q] = (float)d;
+            }
+        }
+    }
+}
+
+LDPC_DEVINL int ms_sample_source(const FrameIO &io, const DecParams &p, const int N)
+{
+    if (!io.y) return p.channel_mode == LDPC_GPU_CHANNEL_FAST ? SRC_PHILOX_FAST : SRC_PHILOX;
+    if (io.y_dtype == LDPC_GPU_DT_Q8 && (N & 3) == 0 && ((size_t)io.y & 3) == 0) return SRC_Q8;
+    return SRC_OTHER;
+}
+
+template <int DC, int DV, int NFIX, int NT_MAX, int MINB, bool KEEP>
+__global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, const DecParams p, const FrameIO io)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int N = NFIX, nwords = (N + 31) >> 5, nblk = (N + 3) >> 2, NB = N * 4;
+    FrameScratch *fs = reinterpret_cast<FrameScratch *>(smem_raw);                 // [2]
+    int *st = reinterpret_cast<int *>(smem_raw + 32);                             // [0..1] certificate state, [2] flags of this check phase
+    uint32_t *msg = reinterpret_cast<uint32_t *>(smem_raw + 64);                  // [DV*N] c2v pairs
+    uint32_t *S = msg + DV * N;                                                   // [N] a-posteriori sums
+    uint32_t *yq = S + N;                                                         // [N]
+    uint32_t *dbits = yq + N;                                                     // [2][nwords]
+    unsigned char *msgb = reinterpret_cast<unsigned char *>(msg);
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, M = c.M;
+    const uint32_t qflags = p.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES);
+    const bool fcond = !io.y || io.y_dtype != LDPC_GPU_DT_F64;
+    const int src = ms_sample_source(io, p, N);
+    const bool has_row = tid < M;
+    const int slot = has_row ? (int)__ldg(&c.row_slot[tid]) : 0;
+    const long long npairs = (io.n_frames + 1) / 2;
+    CtaTotals tot; tot.clear();
+    uint32_t v[DC];                                                               // this thread's row: c2v of the previous iteration
+
+    // channel front end of a frame pair, straight into yq / S (the iteration state of the previous pair is dead by then)
+    auto gen_pair = [&](auto srct, const long long fa, const long long fb, const uint8_t *cwa, const uint8_t *cwb) {
+        constexpr int SRC = decltype(srct)::value;
+        int unca = 0, uncb = 0;
+        for (int b = tid; b < nblk; b += nt) {
+            float va[4], vb[4];
+            ms_cond4_f32<SRC>(io, p, c, fa, cwa, b, qflags, fcond, va);
+            ms_cond4_f32<SRC>(io, p, c, fb, cwb, b, qflags, fcond, vb);
+            const uint2 cc = __ldg(reinterpret_cast<const uint2 *>(c.col_of_var) + b);
+            uint32_t niba = 0, nibb = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = 4 * b + q;
+                const bool na = !(va[q] > 0.0f), nb = !(vb[q] > 0.0f);
+                unca += (int)(na != ((cwa ? cwa[i] : 0) != 0)); uncb += (int)(nb != ((cwb ? cwb[i] : 0) != 0));
+                niba |= (uint32_t)na << q; nibb |= (uint32_t)nb << q;
+                const uint32_t w = h2_bits(__floats2half2_rn(va[q], vb[q]));      // exact: lattice points
+                const int col = (int)(((q < 2 ? cc.x : cc.y) >> (16 * (q & 1))) & 0xffffu);
+                yq[col] = w; S[col] = w;
+                if (io.out_soft && p.T == 0) {                                    // T = 0: the conditioned samples themselves
+                    if (io.y_dtype == LDPC_GPU_DT_F64) { ((double *)io.out_soft)[(size_t)fa * N + i] = va[q]; if (fb != fa) ((double *)io.out_soft)[(size_t)fb * N + i] = vb[q]; }
+                    else { ((float *)io.out_soft)[(size_t)fa * N + i] = va[q]; if (fb != fa) ((float *)io.out_soft)[(size_t)fb * N + i] = vb[q]; }
+                }
+            }
+            if (p.T == 0) {                                                       // otherwise the decisions come from the last iteration
+                if (niba) atomicOr(&dbits[(4 * b) >> 5], niba << ((4 * b) & 31));
+                if (nibb) atomicOr(&dbits[nwords + ((4 * b) >> 5)], nibb << ((4 * b) & 31));
+            }
+        }
+        unca = __reduce_add_sync(0xffffffffu, unca); uncb = __reduce_add_sync(0xffffffffu, uncb);
+        if (lane == 0) { if (unca) atomicAdd(&fs[0].uncoded, unca); if (uncb) atomicAdd(&fs[1].uncoded, uncb); }
+    };
+
+    for (long long pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
+        const long long fa = 2 * pr, fb = (2 * pr + 1 < io.n_frames) ? 2 * pr + 1 : 2 * pr;   // a dead lane replays frame fa, unreported
+        const bool live_b = 2 * pr + 1 < io.n_frames;
+        const uint8_t *cwa = codeword_row(io, c, fa), *cwb = codeword_row(io, c, fb);
+        if (tid < 2) { fs[tid].uncoded = 0; fs[tid].errors = 0; fs[tid].flag = 0; st[tid] = X2_EXACT; }
+        if (tid == 2) st[2] = 0;
+        if (p.T == 0) for (int w = tid; w < 2 * nwords; w += nt) dbits[w] = 0u;
+        __syncthreads();
+        switch (src) {                                                            // launch constant
+        case SRC_PHILOX:      gen_pair(std::integral_constant<int, SRC_PHILOX>(), fa, fb, cwa, cwb); break;
+        case SRC_PHILOX_FAST: gen_pair(std::integral_constant<int, SRC_PHILOX_FAST>(), fa, fb, cwa, cwb); break;
+        case SRC_Q8:          gen_pair(std::integral_constant<int, SRC_Q8>(), fa, fb, cwa, cwb); break;
+        default:              gen_pair(std::integral_constant<int, SRC_OTHER>(), fa, fb, cwa, cwb); break;
+        }
+#pragma unroll
+        for (int e = 0; e < DC; e++) v[e] = 0u;                                   // c2v = 0, S = y: the first v2c is the channel value (:364-370)
+        __syncthreads();
+
+        for (int it = 0; it < p.T; it++) {
+            const bool last = (it == p.T - 1);
+            if (last) for (int w = tid; w < 2 * nwords; w += nt) dbits[w] = 0u;
+            const int sa = st[0], sb = st[1];                                     // block-uniform: written before the previous barrier
+            // ---- check-node phase: one row per thread, both frames -----------------------------------
+            uint32_t flags = 0u;
+            if (has_row) {
+                flags = x2_check_row<DC, DV, NB, NT_MAX, KEEP>(msgb, slot, c.sched, tid, v, p);
+            }
+            if (sa < X2_CERT || sb < X2_CERT) {                                   // somebody still needs this phase's flags
+                flags = __reduce_or_sync(0xffffffffu, flags);
+                if (lane == 0 && flags) atomicOr(reinterpret_cast<unsigned int *>(&st[2]), flags);
+            }
+            __syncthreads();
+            if (tid == 0) {                                                       // certificate state machine of both frames; the flag word is
+                const uint32_t all = (uint32_t)st[2];                             // consumed and cleared between this phase's barrier and the next
+                st[2] = 0;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t fl = all >> (16 * h);
+                    int s = h ? sb : sa;
+                    if (s == X2_EXACT) { if (!(fl & 1u)) s = X2_CERT; else if (fl & 2u) s = X2_UNCERT; }
+                    st[h] = s;
+                }
+            }
+            // ---- variable-node phase: S = y + sum_s c2v, two adjacent storage columns per thread --------
+            constexpr int VN_ROUNDS = (N / 2 + NT_MAX - 1) / NT_MAX;               // the host launches exactly NT_MAX threads
+#pragma unroll
+            for (int rr = 0; rr < VN_ROUNDS; rr++) {
+                const int cp = tid + rr * NT_MAX;
+                if (cp >= N / 2) break;
+                const int col = 2 * cp;
+                const uint2 y2 = *reinterpret_cast<const uint2 *>(&yq[col]);
+                __half2 s0 = h2_from(y2.x), s1 = h2_from(y2.y);
+#pragma unroll
+                for (int s = 0; s < DV; s++) {
+                    const uint2 cm = *reinterpret_cast<const uint2 *>(&msg[s * N + col]);
+                    s0 = __hadd2(s0, h2_from(cm.x)); s1 = __hadd2(s1, h2_from(cm.y));
+                }
+                *reinterpret_cast<uint2 *>(&S[col]) = make_uint2(h2_bits(s0), h2_bits(s1));
+                if (last) {
+                    const unsigned vv = __ldg(reinterpret_cast<const unsigned *>(c.var_of_col) + cp);
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int i = h ? (int)(vv >> 16) : (int)(vv & 0xffffu);
+                        const __half2 sum = h ? s1 : s0;
+                        const float xa = __low2float(sum), xb = __high2float(sum);
+                        if (!(xa > 0.0f)) atomicOr(&dbits[i >> 5], 1u << (i & 31));
+                        if (!(xb > 0.0f)) atomicOr(&dbits[nwords + (i >> 5)], 1u << (i & 31));
+                        if (io.out_soft) {
+                            if (io.y_dtype == LDPC_GPU_DT_F64) { ((double *)io.out_soft)[(size_t)fa * N + i] = xa; if (live_b) ((double *)io.out_soft)[(size_t)fb * N + i] = xb; }
+                            else { ((float *)io.out_soft)[(size_t)fa * N + i] = xa; if (live_b) ((float *)io.out_soft)[(size_t)fb * N + i] = xb; }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // frames whose decisions are not certified go to the redo list instead of being reported
+        const int enda = st[0], endb = st[1];
+        if (tid == 0) {
+            if (enda == X2_UNCERT) { const unsigned q = atomicAdd(io.redo_count, 1u); io.redo_list[q] = fa; atomicAdd(io.redo_total, 1ull); }
+            if (live_b && endb == X2_UNCERT) { const unsigned q = atomicAdd(io.redo_count, 1u); io.redo_list[q] = fb; atomicAdd(io.redo_total, 1ull); }
+        }
+        if (enda != X2_UNCERT) finish_frame(c, p, io, fa, cwa, dbits, &fs[0], p.T, -1, 0, 0, 1, -1, tot);
+        if (live_b && endb != X2_UNCERT) finish_frame(c, p, io, fb, cwb, dbits + nwords, &fs[1], p.T, -1, 0, 0, 1, -1, tot);
+        __syncthreads();
+    }
+    if (tid == 0) tot.flush(io.counters);
+}
+
+} // namespace ldpc

@@ -53,6 +53,10 @@ struct DecParams {
     float    inv_alpha_f;   // fp32 instantiation: RN(1/alpha)
     float    alpha_div_f;   // (float)alpha when the fp32 normalisation needs the division-correction step (alpha not a power of two), else 0
     float    ms_scale_f, ms_step_f, Ymax_f;   // fp32 front end (fp32 instantiation fed by the Philox channel or fp32 samples)
+    uint32_t x2_delta2, x2_cap2, x2_m02;   // exact-lattice packed kernel (ldpc_ms_x2.cuh), binary16 pairs: offset (0 for plain min-sum), c2v cap, stable-state bound
+    int      channel_mode;  // LDPC_GPU_CHANNEL_*
+    int      zero;          // always 0: an offset the compiler cannot see through (ldpc_ms_x2.cuh)
+    float    sigma_f;       // fast channel: (float)sigma
     int      iter_hist_len;
     int      rows_per_step; // GDBF noise rows consumed per flip step
 };
@@ -83,6 +87,14 @@ struct FrameIO {
                                   // draws rows r * rows_per_decode ... (ldpc_gpu_redecode_stats)
     unsigned char *workspace;     // device, gridDim.x * ws_stride bytes: per-CTA frame state of the HBM-resident
     size_t         ws_stride;     //   instantiations (codes whose state exceeds one SM's shared memory)
+    // exact-lattice packed kernel: frames whose decisions it cannot certify (batch-relative indices), decoded by the fp64 kernel
+    long long     *redo_list;
+    unsigned int  *redo_count;
+    unsigned long long *redo_total; // running total over the decoder's life (statistics)
+    // frame indirection of the redo launch: frame f of the launch is frame frame_list[f] of the batch; the launch size is read
+    // on the device so that no host synchronisation sits between the two kernels
+    const long long *frame_list;
+    const unsigned int *n_frames_dev;
     // channel_dump outputs
     double       *dump_y;
     double       *dump_noise;
