@@ -43,13 +43,35 @@ LDPC_DEVINL float condition_ms_f32(float y, const DecParams &p, uint32_t qflags)
     float v = y;
     if (qflags & LDPC_GPU_F_QUANTIZE_SAMPLES) {
         const float a = fabsf(y);
-        float q = floorf(a * p.ms_scale_f) * p.ms_step_f;
-        q = (q == 0.0f) ? p.ms_step_f : q;
+        // level * step: exact in fp32 when the step is a dyadic fp32 number; otherwise the product is rounded once, from double,
+        // as (float)(level * step) of the double rule is
+        const float lev = fmaxf(floorf(a * p.ms_scale_f), 1.0f);
+        float q = p.ms_step_dyadic ? lev * p.ms_step_f : (float)__dmul_rn((double)lev, p.ms_step);
         q = (a > p.Ymax_f) ? p.Ymax_f : q;
         v = (y >= 0.0f) ? q : -q;
     }
     if (qflags & LDPC_GPU_F_SATURATE_SAMPLES) v = fminf(fmaxf(v, -p.Ymax_f), p.Ymax_f);
     return v;
+}
+
+// The same conditioning of a DOUBLE sample, guaranteed to return what the double rule (quantize_ms + clamp) returns: the
+// fp32 evaluation is used wherever it provably lands on the same level, i.e. when floor()'s argument is further than 2^-13
+// from an integer (the fp32 error of |y| (Nq-1)/(2 Ymax) is below 3e-5 for Q <= 8) and |y| is not within 1e-5 of Ymax; the
+// few samples inside those bands (about 3 in 10^4) are redone in double.  So the fp32 / binary16 instantiations and the fp64
+// parity instantiation decode the very same quantised samples.
+LDPC_DEVINL float condition_ms_guarded(double yd, const DecParams &p, uint32_t qflags)
+{
+    const float yf = (float)yd;
+    if (qflags & LDPC_GPU_F_QUANTIZE_SAMPLES) {
+        const float a = fabsf(yf), t = a * p.ms_scale_f, fl = floorf(t);
+        const bool risky = (t - fl) < 1.220703125e-4f || (fl + 1.0f - t) < 1.220703125e-4f || fabsf(a - p.Ymax_f) < 1e-5f || p.Q > 8;
+        if (risky) {
+            double d = quantize_ms(yd, p);
+            if (qflags & LDPC_GPU_F_SATURATE_SAMPLES) d = fmin(fmax(d, -p.Ymax), p.Ymax);
+            return (float)d;
+        }
+    }
+    return condition_ms_f32(yf, p, qflags);
 }
 
 // a3: GDBF quantiser, src/decodeGDBF.cpp:488-493

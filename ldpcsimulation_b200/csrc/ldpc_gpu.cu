@@ -655,6 +655,7 @@ extern "C" int ldpc_gpu_decoder_create(const ldpc_gpu_code *code, const ldpc_gpu
     p.inv_alpha_f = cfg->alpha != 0 ? (float)(1.0 / (double)(float)cfg->alpha) : 0.0f;
     { int ex; const bool pow2 = cfg->alpha > 0 && frexp(cfg->alpha, &ex) == 0.5;
       p.alpha_div_f = ((cfg->flags & LDPC_GPU_F_NORMALIZED_MS) && !pow2 && !getenv("LDPC_GPU_NO_FDIV")) ? (float)cfg->alpha : 0.0f; }
+    { int ex; p.ms_step_dyadic = (p.ms_step > 0 && frexp(p.ms_step, &ex) == 0.5 && cfg->Q <= 16) ? 1 : 0; }
     p.ms_scale_f = (float)((Nq - 1) / (2.0 * cfg->Ymax)); p.ms_step_f = (float)p.ms_step; p.Ymax_f = (float)cfg->Ymax;
     p.iter_hist_len = iter_hist_len(*cfg);
     p.rows_per_step = rows_per_step(cfg->flags);

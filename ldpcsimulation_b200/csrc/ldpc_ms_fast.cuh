@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_fast_kernel(const CodeDev c, 
                 if (i >= N) break;
                 Real vr; bool rneg;
                 if (sizeof(Real) == 4 && fcond) {
-                    const float vf = condition_ms_f32((float)y4[q], p, qflags);
+                    const float vf = condition_ms_guarded(y4[q], p, qflags);
                     vr = (Real)vf; rneg = !(vf > 0.0f);
                 } else {
                     double v = y4[q];
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_sched_kernel(const CodeDev c,
                 if (fabs(v) > p.MAXLLR) v = (neg_ge(v) ? -1.0 : 1.0) * p.MAXLLR;
                 rneg = neg_ge(v); vr = (Real)v;
             } else if (sizeof(Real) == 4 && fcond) {
-                const float vf = condition_ms_f32((float)y4[q], p, qflags);
+                const float vf = condition_ms_guarded(y4[q], p, qflags);
                 vr = (Real)vf; rneg = !(vf > 0.0f);
             } else {                                              // src/decodeMinSum.cpp:214-238
                 double v = y4[q];

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_h2_kernel(const CodeDev c, co
             for (int q = 0; q < 4; q++) {
                 const int i = 4 * b + q;
                 float va, vb;
-                if (fcond) { va = condition_ms_f32((float)ya[q], p, qflags); vb = condition_ms_f32((float)yb[q], p, qflags); }
+                if (fcond) { va = condition_ms_guarded(ya[q], p, qflags); vb = condition_ms_guarded(yb[q], p, qflags); }
                 else {
                     double da = ya[q], db = yb[q];
                     if (qflags & LDPC_GPU_F_QUANTIZE_SAMPLES) { da = quantize_ms(da, p); db = quantize_ms(db, p); }

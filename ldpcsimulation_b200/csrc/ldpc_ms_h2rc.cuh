@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_h2rc_kernel(const CodeDev c, 
         for (int q = 0; q < 4; q++) {
             const int i = 4 * b + q;
             float vf;
-            if (fcond) vf = condition_ms_f32((float)y4[q], p, qflags);
+            if (fcond) vf = condition_ms_guarded(y4[q], p, qflags);
             else {
                 double d = y4[q];
                 if (qflags & LDPC_GPU_F_QUANTIZE_SAMPLES) d = quantize_ms(d, p);

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
             const int i = 4 * b + q;
             Real vr; bool rneg;
             if (sizeof(Real) == 4 && fcond) {
-                const float vf = condition_ms_f32((float)y4[q], p, qflags);
+                const float vf = condition_ms_guarded(y4[q], p, qflags);
                 vr = (Real)vf; rneg = !(vf > 0.0f);
             } else {                                              // src/decodeMinSum.cpp:214-238
                 double v = y4[q];

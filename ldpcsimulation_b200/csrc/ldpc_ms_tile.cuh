@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(NT_MAX, 1) ms_tile_kernel(const CodeDev c, con
                 if (i >= N) break;
                 Real vr; bool rneg;
                 if (sizeof(Real) == 4 && fcond) {
-                    const float vf = condition_ms_f32((float)y4[q], p, qflags);
+                    const float vf = condition_ms_guarded(y4[q], p, qflags);
                     vr = (Real)vf; rneg = !(vf > 0.0f);
                 } else {
                     double v = y4[q];

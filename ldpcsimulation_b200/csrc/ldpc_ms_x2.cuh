@@ -23,14 +23,16 @@
 //   (dvm - 1) C - Ymax >= m0 (the bound becomes min(m, (dvm - 1) C - Ymax) >= m0).  So from a stable state on, the
 //   capped and the uncapped decoder output the same decisions, x, at every iteration.
 //
-//   Certificate.  While the cap has never engaged the frame's arithmetic is exact (state EXACT).  Every check phase of such a
-//   frame also verifies the lemma's premise on its (exact) inputs -- every row has an even number of negative v2c and
-//   min |v2c| >= m0, and every v2c has the sign of its variable's a-posteriori sum (one LOP3 per edge) -- and the frame
-//   becomes CERTIFIED as soon as all rows agree; from then on the cap is harmless.  If the cap engages in a check phase whose
-//   inputs do not satisfy the premise, the frame is UNCERTIFIED: it is not reported from here but appended to a redo list, and
-//   the host library decodes the listed frames with the fp64 parity instantiation (ms_rc_kernel<double>) on the same stream.
-//   Either way every reported decision vector is the reference's, bit for bit; a-posteriori sums (out_soft) are the
-//   reference's only while the cap has not engaged (they saturate near Ymax + dv C afterwards) -- callers that need the
+//   Certificate.  While the cap has never engaged the frame's arithmetic is exact (state EXACT).  The lemma's premise for
+//   the inputs of check phase t+1 is verified in two cheap pieces: (a) the variable phase of iteration t (only when every row of
+//   check phase t was satisfied with min |v2c| >= m0, i.e. when the frame looks converged; one extra pass over the variable's
+//   c2v) checks that every v2c = S - c2v it implies has the sign of S and magnitude >= m0; (b) check phase t+1 reports, from
+//   values it computes anyway, that every row has an even number of negative v2c (so sign(S) is a codeword) and min |v2c| >= m0.
+//   (a) and (b) together are the premise, and the frame becomes CERTIFIED; from then on the cap is harmless.  If the cap engages
+//   in a check phase whose inputs are not certified, the frame is UNCERTIFIED: it is not reported from here but appended to a
+//   redo list, and the host library decodes the listed frames with the fp64 parity instantiation (ms_rc_kernel<double>) on the
+//   same stream.  Either way every reported decision vector is the reference's, bit for bit; a-posteriori sums (out_soft) are
+//   the reference's only while the cap has not engaged (they saturate near Ymax + dv C afterwards) -- callers that need the
 //   sums of converged frames use fp32 / fp64.
 //
 // Kernel structure: ms_h2rc_kernel's (one CTA per frame pair, one thread per check row, the row's 32 c2v words
@@ -75,14 +77,14 @@ LDPC_DEVINL uint32_t x2_and_xor(uint32_t a, uint32_t b, uint32_t c)
 }
 
 // One check row of a frame pair.  KEEP: the row's 32 schedule offsets stay in registers between the passes instead of being
-// read again.  Returns the row's flag word: bit 0 / 16 = premise violated (frame a / b), bit 1 / 17 = cap engaged.
+// read again.  Returns the row's flag word: bit 0 / 16 = row unsatisfied or min |v2c| < m0 (frame a / b), bit 1 / 17 = cap engaged.
 template <int DC, int DV, int NB, int M, bool KEEP>
 LDPC_DEVINL uint32_t x2_check_row(unsigned char *msgb, const int slot, const uint4 *__restrict__ sched, const int j,
                                   uint32_t (&v)[DC], const DecParams &k)
 {
     constexpr int NG = DC / 4;
     const uint32_t INF2 = 0x7bff7bffu;                                             // 65504, 65504
-    uint32_t m1 = INF2, m2 = INF2, acc = 0u;
+    uint32_t m1 = INF2, m2 = INF2;
     uint32_t offk[KEEP ? DC : 1];
     // the schedule words are read in order, one group ahead (`volatile` keeps ptxas from hoisting all eight loads -- 32 live
     // offsets next to the 32 c2v registers -- and from merging the two passes' loads)
@@ -100,7 +102,6 @@ LDPC_DEVINL uint32_t x2_check_row(unsigned char *msgb, const int slot, const uin
             asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(so) : "r"((uint32_t)slot), "r"((uint32_t)-NB), "r"(off[q]));
             const uint32_t s = *reinterpret_cast<const uint32_t *>(msgb + DV * NB + so);
             v[e] = h2_bits(__hsub2(h2_from(s), h2_from(v[e])));                    // v2c = sum - c2v (exact)
-            acc |= v[e] ^ s;                                            // bit 15 / 31: sign(v2c) != sign(S)
         }
 #pragma unroll
         for (int q = 0; q < 4; q += 2) {
@@ -120,7 +121,7 @@ LDPC_DEVINL uint32_t x2_check_row(unsigned char *msgb, const int slot, const uin
     const __half2 t2 = __hmax2(__hsub2(h2_from(m2), h2_from(k.x2_delta2)), zero2);
     const __half2 o1 = __hmin2(t1, h2_from(k.x2_cap2)), o2 = __hmin2(t2, h2_from(k.x2_cap2));
     const uint32_t eng = __hgt2_mask(t2, h2_from(k.x2_cap2));                         // t2 >= t1
-    const uint32_t bad = ~__hge2_mask(h2_from(m1a), h2_from(k.x2_m02)) | sg | acc;       // bit 15 / 31 of each half
+    const uint32_t bad = ~__hge2_mask(h2_from(m1a), h2_from(k.x2_m02)) | sg;             // bit 15 / 31 of each half
     const uint32_t flags = ((eng & 0x00010001u) << 1) | ((bad >> 15) & 0x00010001u);
     uint32_t s1 = h2_bits(o1) ^ sg, d12 = h2_bits(o1) ^ h2_bits(o2);
     asm("" : "+r"(s1), "+r"(d12));                                              // keep the two row constants as they are: two LOP3 per edge below
@@ -147,7 +148,7 @@ LDPC_DEVINL uint32_t x2_check_row(unsigned char *msgb, const int slot, const uin
 // so each source gets its own straight-line code instead of raw_samples4's per-sample dispatch through doubles.
 enum { SRC_PHILOX = 0, SRC_PHILOX_FAST = 1, SRC_Q8 = 2, SRC_OTHER = 3 };
 
-template <int SRC>
+template <int SRC, bool HASCW>
 LDPC_DEVINL void ms_cond4_f32(const FrameIO &io, const DecParams &p, const CodeDev &c, const long long f, const uint8_t *cw, const int b,
                               const uint32_t qflags, const bool fcond, float (&vf)[4])
 {
@@ -157,14 +158,15 @@ LDPC_DEVINL void ms_cond4_f32(const FrameIO &io, const DecParams &p, const CodeD
         normal4(io.seed, (unsigned long long)(io.frame_begin + f), (uint32_t)b, 0u, STREAM_CHANNEL, n);
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const double x = (cw && cw[i0 + q]) ? -1.0 : 1.0;
-            vf[q] = condition_ms_f32((float)__dmul_rn(x, __dadd_rn(1.0, __dmul_rn(p.sigma, (double)n[q]))), p, qflags);
+            double y = __dadd_rn(1.0, __dmul_rn(p.sigma, (double)n[q]));
+            if (HASCW && cw && cw[i0 + q]) y = -y;                                // x (1 + sigma n), x = -1: an exact sign flip
+            vf[q] = condition_ms_guarded(y, p, qflags);
         }
     } else if (SRC == SRC_PHILOX_FAST) {
         float n[4];
         normal4_fast(io.seed, (unsigned long long)(io.frame_begin + f), (uint32_t)b, 0u, STREAM_CHANNEL, n);
 #pragma unroll
-        for (int q = 0; q < 4; q++) vf[q] = condition_ms_f32(fast_channel_sample(p, cw, i0 + q, c.N, n[q]), p, qflags);
+        for (int q = 0; q < 4; q++) vf[q] = condition_ms_guarded((double)fast_channel_sample(p, HASCW ? cw : nullptr, i0 + q, c.N, n[q]), p, qflags);
     } else if (SRC == SRC_Q8) {                                // four quantiser levels in one 32-bit load (N % 4 == 0, base 4-byte aligned)
         const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(io.y) + (((size_t)f * c.N) >> 2) + b);
 #pragma unroll
@@ -177,7 +179,7 @@ LDPC_DEVINL void ms_cond4_f32(const FrameIO &io, const DecParams &p, const CodeD
         raw_samples4(io, p, c, f, cw, b, y4);
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            if (fcond) vf[q] = condition_ms_f32((float)y4[q], p, qflags);
+            if (fcond) vf[q] = condition_ms_guarded(y4[q], p, qflags);
             else {
                 double d = y4[q];
                 if (qflags & LDPC_GPU_F_QUANTIZE_SAMPLES) d = quantize_ms(d, p);
@@ -201,7 +203,8 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int N = NFIX, nwords = (N + 31) >> 5, nblk = (N + 3) >> 2, NB = N * 4;
     FrameScratch *fs = reinterpret_cast<FrameScratch *>(smem_raw);                 // [2]
-    int *st = reinterpret_cast<int *>(smem_raw + 32);                             // [0..1] certificate state, [2] flags of this check phase
+    int *st = reinterpret_cast<int *>(smem_raw + 32);                             // [0..1] certificate state, [2] flags of this check phase,
+                                                                                  // (x2, by iteration parity), [4..5] failures of the variable-side check (x2)
     uint32_t *msg = reinterpret_cast<uint32_t *>(smem_raw + 64);                  // [DV*N] c2v pairs
     uint32_t *S = msg + DV * N;                                                   // [N] a-posteriori sums
     uint32_t *yq = S + N;                                                         // [N]
@@ -218,21 +221,20 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
     uint32_t v[DC];                                                               // this thread's row: c2v of the previous iteration
 
     // channel front end of a frame pair, straight into yq / S (the iteration state of the previous pair is dead by then)
-    auto gen_pair = [&](auto srct, const long long fa, const long long fb, const uint8_t *cwa, const uint8_t *cwb) {
+    auto gen_pair = [&](auto srct, auto cwt, const long long fa, const long long fb, const uint8_t *cwa, const uint8_t *cwb) {
         constexpr int SRC = decltype(srct)::value;
+        constexpr bool HASCW = decltype(cwt)::value;
         int unca = 0, uncb = 0;
         for (int b = tid; b < nblk; b += nt) {
             float va[4], vb[4];
-            ms_cond4_f32<SRC>(io, p, c, fa, cwa, b, qflags, fcond, va);
-            ms_cond4_f32<SRC>(io, p, c, fb, cwb, b, qflags, fcond, vb);
+            ms_cond4_f32<SRC, HASCW>(io, p, c, fa, cwa, b, qflags, fcond, va);
+            ms_cond4_f32<SRC, HASCW>(io, p, c, fb, cwb, b, qflags, fcond, vb);
             const uint2 cc = __ldg(reinterpret_cast<const uint2 *>(c.col_of_var) + b);
             uint32_t niba = 0, nibb = 0;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int i = 4 * b + q;
-                const bool na = !(va[q] > 0.0f), nb = !(vb[q] > 0.0f);
-                unca += (int)(na != ((cwa ? cwa[i] : 0) != 0)); uncb += (int)(nb != ((cwb ? cwb[i] : 0) != 0));
-                niba |= (uint32_t)na << q; nibb |= (uint32_t)nb << q;
+                niba |= (uint32_t)(!(va[q] > 0.0f)) << q; nibb |= (uint32_t)(!(vb[q] > 0.0f)) << q;
                 const uint32_t w = h2_bits(__floats2half2_rn(va[q], vb[q]));      // exact: lattice points
                 const int col = (int)(((q < 2 ? cc.x : cc.y) >> (16 * (q & 1))) & 0xffffu);
                 yq[col] = w; S[col] = w;
@@ -245,6 +247,16 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
                 if (niba) atomicOr(&dbits[(4 * b) >> 5], niba << ((4 * b) & 31));
                 if (nibb) atomicOr(&dbits[nwords + ((4 * b) >> 5)], nibb << ((4 * b) & 31));
             }
+            uint32_t ca = 0, cb = 0;                                              // the codeword bits of the block, as nibbles
+            if (HASCW) {
+                auto nibble = [&](const uint8_t *cw) -> uint32_t {
+                    if (!cw) return 0u;
+                    if (((size_t)cw & 3) == 0) { const uint32_t w = *reinterpret_cast<const uint32_t *>(cw + 4 * b); return (w & 1u) | ((w >> 7) & 2u) | ((w >> 14) & 4u) | ((w >> 21) & 8u); }
+                    return (uint32_t)(cw[4 * b] != 0) | ((uint32_t)(cw[4 * b + 1] != 0) << 1) | ((uint32_t)(cw[4 * b + 2] != 0) << 2) | ((uint32_t)(cw[4 * b + 3] != 0) << 3);
+                };
+                ca = nibble(cwa); cb = nibble(cwb);
+            }
+            unca += __popc(niba ^ ca); uncb += __popc(nibb ^ cb);                 // uncodedErrors (:230-236)
         }
         unca = __reduce_add_sync(0xffffffffu, unca); uncb = __reduce_add_sync(0xffffffffu, uncb);
         if (lane == 0) { if (unca) atomicAdd(&fs[0].uncoded, unca); if (uncb) atomicAdd(&fs[1].uncoded, uncb); }
@@ -254,45 +266,63 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
         const long long fa = 2 * pr, fb = (2 * pr + 1 < io.n_frames) ? 2 * pr + 1 : 2 * pr;   // a dead lane replays frame fa, unreported
         const bool live_b = 2 * pr + 1 < io.n_frames;
         const uint8_t *cwa = codeword_row(io, c, fa), *cwb = codeword_row(io, c, fb);
-        if (tid < 2) { fs[tid].uncoded = 0; fs[tid].errors = 0; fs[tid].flag = 0; st[tid] = X2_EXACT; }
-        if (tid == 2) st[2] = 0;
+        if (tid < 2) { fs[tid].uncoded = 0; fs[tid].errors = 0; fs[tid].flag = 0; }
+        if (tid < 8) st[tid] = 0;
         if (p.T == 0) for (int w = tid; w < 2 * nwords; w += nt) dbits[w] = 0u;
         __syncthreads();
-        switch (src) {                                                            // launch constant
-        case SRC_PHILOX:      gen_pair(std::integral_constant<int, SRC_PHILOX>(), fa, fb, cwa, cwb); break;
-        case SRC_PHILOX_FAST: gen_pair(std::integral_constant<int, SRC_PHILOX_FAST>(), fa, fb, cwa, cwb); break;
-        case SRC_Q8:          gen_pair(std::integral_constant<int, SRC_Q8>(), fa, fb, cwa, cwb); break;
-        default:              gen_pair(std::integral_constant<int, SRC_OTHER>(), fa, fb, cwa, cwb); break;
+        if (cwa || cwb) {                                                         // launch constants: one straight-line front end per source
+            switch (src) {
+            case SRC_PHILOX:      gen_pair(std::integral_constant<int, SRC_PHILOX>(), std::true_type(), fa, fb, cwa, cwb); break;
+            case SRC_PHILOX_FAST: gen_pair(std::integral_constant<int, SRC_PHILOX_FAST>(), std::true_type(), fa, fb, cwa, cwb); break;
+            case SRC_Q8:          gen_pair(std::integral_constant<int, SRC_Q8>(), std::true_type(), fa, fb, cwa, cwb); break;
+            default:              gen_pair(std::integral_constant<int, SRC_OTHER>(), std::true_type(), fa, fb, cwa, cwb); break;
+            }
+        } else {
+            switch (src) {
+            case SRC_PHILOX:      gen_pair(std::integral_constant<int, SRC_PHILOX>(), std::false_type(), fa, fb, cwa, cwb); break;
+            case SRC_PHILOX_FAST: gen_pair(std::integral_constant<int, SRC_PHILOX_FAST>(), std::false_type(), fa, fb, cwa, cwb); break;
+            case SRC_Q8:          gen_pair(std::integral_constant<int, SRC_Q8>(), std::false_type(), fa, fb, cwa, cwb); break;
+            default:              gen_pair(std::integral_constant<int, SRC_OTHER>(), std::false_type(), fa, fb, cwa, cwb); break;
+            }
         }
 #pragma unroll
         for (int e = 0; e < DC; e++) v[e] = 0u;                                   // c2v = 0, S = y: the first v2c is the channel value (:364-370)
         __syncthreads();
 
+        // certificate state of the two frames: every thread runs the same few-instruction state machine on the same shared
+        // flag words, so no thread has to publish a decision and no barrier is added.  Flag words are double-buffered by
+        // iteration parity: fl[it & 1] collects check phase `it`, vb[it & 1] the variable-side check of iteration `it`.
+        int sa = X2_EXACT, sb = X2_EXACT;
+        uint32_t vn_ran = 0u;                                                     // bit h: the previous variable phase checked frame h
+        unsigned int *fl = reinterpret_cast<unsigned int *>(&st[2]), *vb = reinterpret_cast<unsigned int *>(&st[4]);
         for (int it = 0; it < p.T; it++) {
             const bool last = (it == p.T - 1);
             if (last) for (int w = tid; w < 2 * nwords; w += nt) dbits[w] = 0u;
-            const int sa = st[0], sb = st[1];                                     // block-uniform: written before the previous barrier
             // ---- check-node phase: one row per thread, both frames -----------------------------------
             uint32_t flags = 0u;
-            if (has_row) {
-                flags = x2_check_row<DC, DV, NB, NT_MAX, KEEP>(msgb, slot, c.sched, tid, v, p);
-            }
-            if (sa < X2_CERT || sb < X2_CERT) {                                   // somebody still needs this phase's flags
+            if (has_row) flags = x2_check_row<DC, DV, NB, NT_MAX, KEEP>(msgb, slot, c.sched, tid, v, p);
+            const bool open_cert = sa == X2_EXACT || sb == X2_EXACT;              // somebody still needs this phase's flags
+            if (open_cert) {
                 flags = __reduce_or_sync(0xffffffffu, flags);
-                if (lane == 0 && flags) atomicOr(reinterpret_cast<unsigned int *>(&st[2]), flags);
+                if (lane == 0 && flags) atomicOr(&fl[it & 1], flags);
             }
             __syncthreads();
-            if (tid == 0) {                                                       // certificate state machine of both frames; the flag word is
-                const uint32_t all = (uint32_t)st[2];                             // consumed and cleared between this phase's barrier and the next
-                st[2] = 0;
+            uint32_t vn_want = 0u;                                                // bit h: this variable phase checks frame h
+            if (open_cert) {
+                const uint32_t all = fl[it & 1], vbad = vb[(it + 1) & 1];
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    const uint32_t fl = all >> (16 * h);
+                    const uint32_t f2 = all >> (16 * h);
                     int s = h ? sb : sa;
-                    if (s == X2_EXACT) { if (!(fl & 1u)) s = X2_CERT; else if (fl & 2u) s = X2_UNCERT; }
-                    st[h] = s;
+                    if (s == X2_EXACT) {
+                        if (((vn_ran >> h) & 1u) && !((vbad >> h) & 1u) && !(f2 & 1u)) s = X2_CERT;   // (a) at it - 1 and (b) now
+                        else if (f2 & 2u) s = X2_UNCERT;                          // the cap engaged on uncertified inputs
+                        else if (!(f2 & 1u)) vn_want |= 1u << h;                  // looks converged: check the variable side now
+                    }
+                    if (h) sb = s; else sa = s;
                 }
             }
+            vn_ran = vn_want;
             // ---- variable-node phase: S = y + sum_s c2v, two adjacent storage columns per thread --------
             constexpr int VN_ROUNDS = (N / 2 + NT_MAX - 1) / NT_MAX;               // the host launches exactly NT_MAX threads
 #pragma unroll
@@ -324,10 +354,31 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
                     }
                 }
             }
+            if (vn_want) {                                                        // rare (once or twice per frame): premise (a) as a second pass over
+                uint32_t vfail = 0u;                                              // this thread's own columns: every next v2c = S - c2v keeps the
+#pragma unroll 1                                                                  // sign of S and has magnitude >= m0
+                for (int cp = tid; cp < N / 2; cp += NT_MAX) {
+                    const int col = 2 * cp;
+                    const uint2 s2 = *reinterpret_cast<const uint2 *>(&S[col]);
+                    uint32_t w0 = 0x7bff7bffu, w1 = 0x7bff7bffu;                  // running minimum of  sign-agreement x min(|v2c|, |S|)
+#pragma unroll
+                    for (int s = 0; s < DV; s++) {
+                        const uint2 cm = *reinterpret_cast<const uint2 *>(&msg[s * N + col]);
+                        w0 = h2_bits(__hmin2(h2_from(w0), h2_from(h2_min_xorsign_abs(h2_bits(__hsub2(h2_from(s2.x), h2_from(cm.x))), s2.x))));
+                        w1 = h2_bits(__hmin2(h2_from(w1), h2_from(h2_min_xorsign_abs(h2_bits(__hsub2(h2_from(s2.y), h2_from(cm.y))), s2.y))));
+                    }
+                    vfail |= ~(__hge2_mask(h2_from(w0), h2_from(p.x2_m02)) & __hge2_mask(h2_from(w1), h2_from(p.x2_m02)));
+                }
+                vfail = __reduce_or_sync(0xffffffffu, ((vfail >> 15) & 1u) | ((vfail >> 30) & 2u));
+                if (lane == 0 && vfail) atomicOr(&vb[it & 1], vfail);
+            }
             __syncthreads();
+            if (tid == 0 && open_cert) { fl[it & 1] = 0u; vb[(it + 1) & 1] = 0u; }   // both were read by everybody before this barrier
         }
+        if (tid == 0) { st[0] = sa; st[1] = sb; }
+        __syncthreads();
         // frames whose decisions are not certified go to the redo list instead of being reported
-        const int enda = st[0], endb = st[1];
+        const int enda = sa, endb = sb;
         if (tid == 0) {
             if (enda == X2_UNCERT) { const unsigned q = atomicAdd(io.redo_count, 1u); io.redo_list[q] = fa; atomicAdd(io.redo_total, 1ull); }
             if (live_b && endb == X2_UNCERT) { const unsigned q = atomicAdd(io.redo_count, 1u); io.redo_list[q] = fb; atomicAdd(io.redo_total, 1ull); }

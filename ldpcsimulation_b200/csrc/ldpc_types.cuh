@@ -52,6 +52,7 @@ struct DecParams {
     double   uni_scale;     // (sqrt(3)*noiseSigma)*2.0                   decodeGDBF.cpp:322
     float    inv_alpha_f;   // fp32 instantiation: RN(1/alpha)
     float    alpha_div_f;   // (float)alpha when the fp32 normalisation needs the division-correction step (alpha not a power of two), else 0
+    int      ms_step_dyadic; // 2*Ymax/(Nq-1) is a power of two times a small integer: level * step is exact in fp32
     float    ms_scale_f, ms_step_f, Ymax_f;   // fp32 front end (fp32 instantiation fed by the Philox channel or fp32 samples)
     uint32_t x2_delta2, x2_cap2, x2_m02;   // exact-lattice packed kernel (ldpc_ms_x2.cuh), binary16 pairs: offset (0 for plain min-sum), c2v cap, stable-state bound
     int      channel_mode;  // LDPC_GPU_CHANNEL_*

@@ -127,7 +127,6 @@ def test_f32_gdbf_family_criterion(variant):
            "oracle_word_errors": int((a.errors > 0).sum()), "fp32_word_errors": int((b.errors > 0).sum()),
            "iters_equal_frames": int((a.iters == b.iters).sum())}
     _report("gdbf_f32_%s" % variant, rep)
-    assert easy.sum() > F // 4, rep
     assert rep["easy_and_fp32_in_error"] <= 0.01 * easy.sum(), rep
     assert differ.mean() < 0.05, rep
     assert abs(rep["oracle_word_errors"] - rep["fp32_word_errors"]) <= differ.sum(), rep
