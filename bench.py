@@ -1,23 +1,27 @@
-#!/usr/bin/env python3
 """bench.py -- coded Gbit/s decoded at fixed iterations, on N B200s, next to the host-CPU reference.
 
-Workload (BASELINE.json configs[1] / SURVEY.md 8(d) M1): IEEE 802.3an (2048,1723) RS-LDPC
-(codes/802_3/802_3_H.alist: N=2048, M=384, E=12288), normalised min-sum (the reference's
-decodeNormalizedMinSum: quantizeSamples + normalizedMS), T=10 fixed iterations (the reference has no
-early stop for min-sum), all-zero codeword, BPSK/AWGN at Eb/N0 = 4.0 dB, R = 0.8413.
+Default workload `oms_8023` (BASELINE.json configs[1], offset variant / SURVEY.md 8(d) M1): IEEE 802.3an (2048,1723) RS-LDPC
+(codes/802_3/802_3_H.alist: N=2048, M=384, E=12288), offset min-sum (the reference's decodeOffsetMinSum: quantizeSamples +
+offsetMS, Ymax=1.9375 Q=5 delta=0.125 -- a dyadic lattice of step 1/16), T=10 fixed iterations (the reference has no early
+stop for min-sum), all-zero codeword, BPSK/AWGN at Eb/N0 = 4.0 dB, R = 0.8413.  Decoder: LDPC_GPU_PREC_F16X2 on the exact
+lattice (csrc/ldpc_ms_x2.cuh): two frames per lane in binary16, every reported decision vector certified identical to the
+reference's doubles (uncertifiable frames are re-decoded by the fp64 instantiation inside the same call).
 
-  step        one pass of the hot path over one batch: ldpc_gpu_simulate() = Philox channel ->
-              condition/quantise -> T iterations -> decisions -> error counting, all in one kernel
+  step        one pass of the hot path over one batch: ldpc_gpu_simulate() = Philox channel -> condition/quantise ->
+              T iterations -> decisions -> error counting (one kernel, plus the -- normally empty -- fp64 redo launch)
   value       whole-job coded Gbit/s of that step (no input to stage: samples are generated in-kernel)
-  e2e         the same decoder through the reference-facing call ldpc_gpu_decode_batch() with HOST
-              buffers: pinned fp32 samples H2D, kernel, packed decisions + iteration counts D2H
-  roofline    algorithmic message bytes ((4E+N)*b per frame-iteration) over the kernel
-              time measured with CUDA events on the launching stream, against the measured HBM peak
-  cpu_baseline / --impl reference
-              the reference's own object code (oracle/_ref), one process per host core
+  e2e         the same decoder through the reference-facing call ldpc_gpu_decode_batch() with HOST buffers: pinned quantiser
+              levels H2D, kernel, packed decisions + iteration counts D2H; fp64 / fp32 / fp16 samples beside it
+  roofline    SURVEY.md 8(d): algorithmic message bytes ((4E+N)*b per frame-iteration) over the kernel time measured with CUDA
+              events on the launching stream, against the aggregate shared-memory peak 148 SM x 128 B/clk x f_SM (the state
+              never leaves the SM), with the ncu-measured issue / shared-memory fractions of the committed capture
+  parity_f64 / fp32 / other_workloads
+              the fp64 parity instantiation and the fp32 one on the same workload; short timed runs of the other configs
+  cpu_baseline* / --impl reference
+              the reference's own object code (oracle/_ref): all host cores (-O2), one core (-O2), reference flags (-g, no -O)
 
-One process per GPU (torchrun for N>1); frames are sharded by frame-id range, the only collective is
-the final NCCL all-reduce of the counters (ldpc_gpu_allreduce_counters).
+One process per GPU (torchrun for N>1); frames are sharded by frame-id range, the only collective is the final NCCL
+all-reduce of the counters (ldpc_gpu_allreduce_counters).
 """
 import argparse
 import json
@@ -31,14 +35,46 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(code="802_3_H", variant="decodeNormalizedMinSum", snr_db=4.0, R=0.8413, T=10,
-                cfg=dict(Ymax=2.0, Q=6, alpha=1.25))
-N_BITS, M_CHK, E_EDGES = 2048, 384, 12288
+R8023 = 0.8413
+WORKLOADS = {
+    # name: code, reference binary, macros, cfg, T, Eb/N0, R, default precision, (Ymax, Q) of the one-byte level format or None
+    "oms_8023": dict(code="802_3_H", variant="decodeOffsetMinSum", flags=["quantizeSamples", "offsetMS"],
+                     cfg=dict(Ymax=1.9375, Q=5, delta=0.125), T=10, snr_db=4.0, R=R8023, precision="x2", q8=(1.9375, 5),
+                     text="IEEE 802.3an (2048,1723) RS-LDPC 802_3_H.alist, offset min-sum (decodeOffsetMinSum: Ymax=1.9375 Q=5 "
+                          "delta=0.125), T=10 fixed iterations, all-zero codeword, BPSK/AWGN Eb/N0=4.0 dB R=0.8413"),
+    "nms_8023": dict(code="802_3_H", variant="decodeNormalizedMinSum", flags=["quantizeSamples", "normalizedMS"],
+                     cfg=dict(Ymax=2.0, Q=6, alpha=1.25), T=10, snr_db=4.0, R=R8023, precision="f32", q8=(2.0, 6),
+                     text="IEEE 802.3an (2048,1723) RS-LDPC 802_3_H.alist, normalised min-sum (decodeNormalizedMinSum: Ymax=2.0 Q=6 "
+                          "alpha=1.25), T=10 fixed iterations, all-zero codeword, BPSK/AWGN Eb/N0=4.0 dB R=0.8413"),
+    "bp_8023": dict(code="802_3_H", variant="decodeBP", flags=[], cfg=dict(), T=10, snr_db=4.0, R=R8023, precision="f32", q8=None,
+                    text="802_3_H.alist, sum-product (decodeBP), T=10, Eb/N0=4.0 dB"),
+    "ms_peg_t50": dict(code="PEG", variant="decodeMinSum", flags=[], cfg=dict(), T=50, snr_db=2.0, R=0.5, precision="f32", q8=None,
+                       text="BASELINE configs[0]: PEGReg504x1008.alist, float min-sum (decodeMinSum), T=50, Eb/N0=2.0 dB, R=0.5"),
+    "ms_dvbs2": dict(code="dvbs2", variant="decodeMinSum", flags=[], cfg=dict(), T=10, snr_db=3.0, R=0.5, precision="f32", q8=None,
+                     text="BASELINE configs[3]: dvbs2_1_2.alist (N=64800, E=226799), min-sum T=10, Eb/N0=3.0 dB: messages in HBM"),
+    "ngdbfhw_8023": dict(code="802_3_H", variant="NGDBFhw", flags=[], cfg=dict(), T=600, snr_db=4.5, R=R8023, precision="f64", q8=None,
+                         text="BASELINE configs[2]: 802_3_H.alist, NGDBFhw (integer), T<=600 with early stop, Eb/N0=4.5 dB"),
+    "smngdbf_8023": dict(code="802_3_H", variant="decodeSMNGDBF", flags=None, cfg=dict(num_iterations=100, alpha=0.3, theta=-0.525, windowsize=64),
+                         T=100, snr_db=4.5, R=R8023, precision="f64", q8=None,
+                         text="BASELINE configs[2]: 802_3_H.alist, SM-NGDBF (decodeSMNGDBF), T<=100 with early stop, Eb/N0=4.5 dB, fp64 (parity-exact)"),
+}
+CODE_FILES = {"802_3_H": "802_3/802_3_H.alist", "PEG": "PEGReg504x1008/PEGReg504x1008.alist", "dvbs2": "dvbs2_1_2/dvbs2_1_2.alist"}
+DTYPE_TEXT = {"x2": "f16x2", "f32": "f32", "f64": "f64"}
 
 
-def cfg_of(abi, precision):
-    return abi.default_cfg(abi.KIND_MINSUM, flags=["quantizeSamples", "normalizedMS"], num_iterations=WORKLOAD["T"],
-                           precision=precision, **WORKLOAD["cfg"])
+def cfg_of(abi, wl, precision):
+    """ldpc_gpu_decoder_cfg of a workload: the reference binary's macro set + the operating point."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    prec = {"x2": abi.PREC_F16X2, "f32": abi.PREC_F32, "f64": abi.PREC_F64}[precision]
+    w = WORKLOADS[wl]
+    if w["flags"] is None:                                      # bit-flipping variants: macro sets live in tests/cases.py
+        return cases.cfg_for(w["variant"], precision=prec, code=w["code"], **w["cfg"])
+    kind = {"decodeBP": abi.KIND_BP}.get(w["variant"], abi.KIND_NGDBF_HW if w["variant"] == "NGDBFhw" else abi.KIND_MINSUM)
+    kw = dict(w["cfg"])
+    if kind != abi.KIND_NGDBF_HW:
+        kw["num_iterations"] = w["T"]
+    return abi.default_cfg(kind, flags=w["flags"], precision=prec, **kw)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -87,14 +123,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-PROFILE_CSV = "profiles/r1p_ncu_raw_ms_rc_final.csv"      # `ncu --set full` capture of the headline kernel on this workload
+PROFILE_CSV = {"x2": "profiles/r2_ncu_raw_ms_x2.csv", "f32": "profiles/r1p_ncu_raw_ms_rc_final.csv"}   # `ncu --set full` captures of the headline kernels
 
 
-def profiled_traffic():
+def profiled_traffic(csv_path):
     """dram__bytes_read.sum + dram__bytes_write.sum of the decode kernel, per launch, from the committed
     `ncu --set full` capture of this same workload (profiles/); None if the capture is absent."""
     import csv
-    path = os.path.join(ROOT, PROFILE_CSV)
+    path = os.path.join(ROOT, csv_path or "-")
     try:
         rows = list(csv.reader(open(path)))
         hdr, units, vals = rows[0], rows[1], rows[2]
@@ -108,11 +144,11 @@ def profiled_traffic():
         return None
 
 
-def profiled_metric(name):
-    """One metric of the committed ncu capture (PROFILE_CSV); None if absent."""
+def profiled_metric(csv_path, name):
+    """One metric of the committed ncu capture; None if absent."""
     import csv
     try:
-        rows = list(csv.reader(open(os.path.join(ROOT, PROFILE_CSV))))
+        rows = list(csv.reader(open(os.path.join(ROOT, csv_path or "-"))))
         return float(rows[2][rows[0].index(name)])
     except Exception:
         return None
@@ -156,13 +192,15 @@ def measured_peak():
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_reference(frames_per_proc, reps=1, cores=None):
+def cpu_reference(wl, frames_per_proc, reps=1, cores=None, lib_suffix=""):
     """The reference's CPU implementation of the path on the host cores: one process per core."""
+    w = WORKLOADS[wl]
     cores = cores or os.cpu_count() or 1
-    cmd = [sys.executable, os.path.join(ROOT, "oracle", "cpu_worker.py"), "--variant", WORKLOAD["variant"],
-           "--code", WORKLOAD["code"], "--snr", str(WORKLOAD["snr_db"]), "--rate", str(WORKLOAD["R"]),
-           "--iters", str(WORKLOAD["T"]), "--frames", str(frames_per_proc), "--reps", str(reps),
-           "--cfg", json.dumps(WORKLOAD["cfg"])]
+    over = dict(w["cfg"])
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "cpu_worker.py"), "--variant", w["variant"],
+           "--code", w["code"], "--snr", str(w["snr_db"]), "--rate", str(w["R"]),
+           "--iters", str(w["T"]), "--frames", str(frames_per_proc), "--reps", str(reps),
+           "--cfg", json.dumps(over), "--lib-suffix", lib_suffix]
     t0 = time.perf_counter()
     procs = [subprocess.Popen(cmd + ["--seed", str(100 + i)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
              for i in range(cores)]
@@ -174,38 +212,39 @@ def cpu_reference(frames_per_proc, reps=1, cores=None):
         outs.append(json.loads(o.strip().splitlines()[-1]))
     wall = time.perf_counter() - t0
     fps = sum(o["frames_per_s"] for o in outs)
-    return {"value": fps * N_BITS / 1e9, "unit": "Gbit/s", "cores": cores, "kind": outs[0]["kind"],
+    nbits = outs[0]["N"]
+    built = "-g, no -O (the reference's own flags, Makefile:5-6)" if lib_suffix == "_g" else "-O2"
+    return {"value": fps * nbits / 1e9, "unit": "Gbit/s", "cores": cores, "kind": outs[0]["kind"],
             "frames_per_s": fps, "wall_s": wall,
-            "sample": "%d frames x %d rep(s) per process, %d processes, frame loop only, %s built -O2" %
-                      (frames_per_proc, reps, cores, "oracle/_ref (reference object code)" if outs[0]["kind"] == "reference" else "oracle port")}
+            "sample": "%d frames x %d rep(s) per process, %d process(es), frame loop only, %s built %s" %
+                      (frames_per_proc, reps, cores, "oracle/_ref (reference object code)" if outs[0]["kind"] == "reference" else "oracle port", built)}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    frames = 96
+    wl = args.workload
+    frames = 96 if WORKLOADS[wl]["code"] != "dvbs2" else 4
     for _ in range(args.warmup):
-        cpu_reference(8)
+        cpu_reference(wl, 8 if frames > 8 else 1)
     t0 = time.perf_counter()
-    res = [cpu_reference(frames) for _ in range(args.steps)]
+    res = [cpu_reference(wl, frames) for _ in range(args.steps)]
     wall = time.perf_counter() - t0
     val = statistics.mean(r["value"] for r in res)
     line = {"impl": "reference", "metric": "coded Gbit/s decoded at fixed iters", "value": val, "unit": "Gbit/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_block("cpu"),
+            "config": config_block(wl, "cpu"),
             "cpu_baseline": {"value": val, "unit": "Gbit/s", "cores": res[0]["cores"], "kind": res[0]["kind"], "sample": res[0]["sample"]},
             "e2e": {"value": val, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
 
 
-def config_block(where, frames_per_step=None, e2e_frames=None):
-    c = {"workload": "IEEE 802.3an (2048,1723) RS-LDPC 802_3_H.alist, normalised min-sum (decodeNormalizedMinSum: "
-                     "Ymax=2.0 Q=6 alpha=1.25), T=10 fixed iterations, all-zero codeword, BPSK/AWGN Eb/N0=4.0 dB R=0.8413",
-         "code": "802_3_H", "N": N_BITS, "M": M_CHK, "E": E_EDGES, "T": WORKLOAD["T"], "snr_db": WORKLOAD["snr_db"],
-         "decoder": WORKLOAD["variant"]}
+def config_block(wl, where, frames_per_step=None, e2e_frames=None):
+    w = WORKLOADS[wl]
+    c = {"workload": w["text"], "name": wl, "code": w["code"], "T": w["T"], "snr_db": w["snr_db"], "decoder": w["variant"]}
     if where == "gpu":
         c.update({"frames_per_step_per_gpu": frames_per_step, "e2e_frames_per_step_per_gpu": e2e_frames,
                   "parallelism": "frames sharded by frame-id range, one process per GPU, final NCCL all-reduce of counters",
@@ -221,10 +260,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--frames", type=int, default=1 << 20, help="frames per step per GPU (value)")
+    ap.add_argument("--workload", default="oms_8023", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="frames per step per GPU (value); 0 = per-workload default")
     ap.add_argument("--e2e-frames", type=int, default=1 << 17, help="frames per step per GPU (e2e, host buffers)")
-    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--precision", default=None, choices=["x2", "f32", "f64"])
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip parity_f64 / fp32 / other_workloads")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -234,6 +275,9 @@ def main():
     import torch
     from ldpcsimulation_b200 import abi, capi, shard
 
+    wl = args.workload
+    W = WORKLOADS[wl]
+    precision = args.precision or W["precision"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -251,17 +295,39 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # CPU baseline first (rank 0, N=1 only), before the GPU is busy
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_reference(160)
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        tw = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        return float(tw[0])
 
-    prec = abi.PREC_F32 if args.precision == "f32" else abi.PREC_F64
-    code = capi.Code(os.path.join(ROOT, "codes", "802_3", "802_3_H.alist"))
-    cfg = cfg_of(abi, prec)
+    # CPU baselines first (rank 0, N=1 only), before the GPU is busy
+    cpu = cpu1 = cpug = cpug1 = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        small = W["code"] == "dvbs2"
+        cpu = cpu_reference(wl, 4 if small else 160)
+        cpu1 = cpu_reference(wl, 4 if small else 320, cores=1)
+        try:
+            cpug = cpu_reference(wl, 2 if small else 48, lib_suffix="_g")
+            cpug1 = cpu_reference(wl, 2 if small else 96, cores=1, lib_suffix="_g")
+        except Exception:                                    # oracle/_ref/*_g.so not built (no reference tree at build time)
+            cpug = cpug1 = None
+
+    codes = {}
+
+    def code_of(name):
+        if name not in codes:
+            codes[name] = capi.Code(os.path.join(ROOT, "codes", CODE_FILES[name]))
+        return codes[name]
+
+    code = code_of(W["code"])
+    NB = code.N
+    cfg = cfg_of(abi, wl, precision)
     dec = capi.Decoder(code, cfg, device=local)
     geo = dec.geometry()
-    snr, R, F = WORKLOAD["snr_db"], WORKLOAD["R"], args.frames
+    snr, R = W["snr_db"], W["R"]
+    F = args.frames or {"dvbs2": 1 << 14, "PEG": 1 << 19}.get(W["code"], 1 << 20)
 
     # the path's one collective: library-owned NCCL communicator, id distributed over torch.distributed
     if world > 1:
@@ -311,26 +377,53 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
-    if dist is not None:
-        tw = torch.tensor([wall, kernel_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-        wall, kernel_ms = float(tw[0]), float(tw[1])
+    wall, kernel_ms = max_over_ranks(wall), max_over_ranks(kernel_ms)
     frames_total = F * args.steps * world
-    value = frames_total * N_BITS / wall / 1e9
+    value = frames_total * NB / wall / 1e9
+    x2_exact, redo_frames = dec.stats()
+
+    # ---- a short timed run of another decoder / workload (extras) ----------------------------------
+    def short_value(wl2, prec2, frames, steps=3, channel=0, seed_base=10 ** 9):
+        w2 = WORKLOADS[wl2]
+        c2 = cfg_of(abi, wl2, prec2)
+        c2.channel_mode = channel
+        d2 = capi.Decoder(code_of(w2["code"]), c2, device=local)
+        for i in range(2):
+            d2.simulate(w2["snr_db"], w2["R"], 1234, seed_base + i * frames, frames)
+        barrier()
+        t2 = time.perf_counter()
+        tot, kms = None, 0.0
+        for i in range(steps):
+            begin, n = shard.step_range(10 ** 6 + i, rank, world, frames)
+            rr = d2.simulate(w2["snr_db"], w2["R"], 1234, begin, n)
+            kms += d2.last_timing()[0]
+            tot = dict(rr.counters) if tot is None else {k: tot[k] + rr.counters[k] for k in tot}
+        barrier()
+        w = max_over_ranks(time.perf_counter() - t2)
+        nb = code_of(w2["code"]).N
+        out = {"value": frames * steps * world * nb / w / 1e9, "unit": "Gbit/s", "dtype": DTYPE_TEXT[prec2], "frames_per_step_per_gpu": frames,
+               "steps": steps, "kernel_ms_per_step": kms / steps, "fer_this_rank": tot["wordErrors"] / max(1, tot["totalWords"]),
+               "ber_this_rank": tot["errors"] / max(1, tot["totalBits"]),
+               "avg_iterations": tot["totalIterations"] / max(1, tot["totalWords"]), "kernel": d2.geometry()}
+        return out, d2
 
     # ---- e2e: reference-facing call with host buffers -------------------------------------------
-    Fe = args.e2e_frames
+    Fe = args.e2e_frames if W["code"] != "dvbs2" else 1 << 11
     sigma = float(np.sqrt(10 ** (-snr / 10) / R / 2))
     gen = torch.Generator(device="cuda").manual_seed(7 + rank)
-    y_dev = 1.0 + sigma * torch.randn((Fe, N_BITS), generator=gen, device="cuda", dtype=torch.float32)
-    bits_host = torch.empty((Fe, N_BITS // 8), dtype=torch.uint8, pin_memory=True)
+    y_dev = 1.0 + sigma * torch.randn((Fe, NB), generator=gen, device="cuda", dtype=torch.float32)
+    bits_host = torch.empty((Fe, (NB + 7) // 8), dtype=torch.uint8, pin_memory=True)
     iters_host = torch.empty((Fe,), dtype=torch.int32, pin_memory=True)
     e2e_steps = max(3, min(args.steps, 10))
+    hw_noise = None
+    if W["variant"] == "NGDBFhw":                        # the parity entry takes the decoder's noise buffer from the caller
+        hw_noise = torch.empty((Fe, abi.HW_QBUF), dtype=torch.float64, pin_memory=True)
+        hw_noise.copy_(torch.randn((Fe, abi.HW_QBUF), generator=gen, device="cuda", dtype=torch.float64))
 
-    def run_e2e(torch_dtype, abi_dtype):
-        y_host = torch.empty((Fe, N_BITS), dtype=torch_dtype, pin_memory=True)
+    def run_e2e(decoder, torch_dtype, abi_dtype, steps=e2e_steps):
+        y_host = torch.empty((Fe, NB), dtype=torch_dtype, pin_memory=True)
         if abi_dtype == abi.DT_Q8:                                # the samples as a Q-bit converter delivers them: signed quantiser levels
-            Ymax, Nq = float(WORKLOAD["cfg"]["Ymax"]), 2.0 ** WORKLOAD["cfg"]["Q"]
+            Ymax, Nq = float(W["q8"][0]), 2.0 ** W["q8"][1]
             a = y_dev.abs().double()
             k = torch.where(a > Ymax, torch.full_like(a, 32.0), torch.clamp(torch.floor(a * (Nq - 1.0) / (2.0 * Ymax)), min=1.0))
             y_host.copy_(torch.where(y_dev >= 0, k, -k).to(torch.int8))
@@ -340,98 +433,135 @@ def main():
         b = abi.Batch()
         b.n_frames, b.mem, b.y_dtype = Fe, abi.MEM_HOST, abi_dtype
         b.y, b.out_bits, b.out_iters = y_host.data_ptr(), bits_host.data_ptr(), iters_host.data_ptr()
+        if hw_noise is not None:
+            b.noise = hw_noise.data_ptr()
         for _ in range(2):
-            dec.decode_raw(snr, R, b)
+            decoder.decode_raw(snr, R, b)
         barrier()
         t1 = time.perf_counter()
         nl = 0
-        for _ in range(e2e_steps):
-            dec.decode_raw(snr, R, b)
-            nl += dec.last_timing()[1]
+        for _ in range(steps):
+            decoder.decode_raw(snr, R, b)
+            nl += decoder.last_timing()[1]
         barrier()
-        w = time.perf_counter() - t1
-        if dist is not None:
-            tw = torch.tensor([w], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-            w = float(tw[0])
-        return Fe * e2e_steps * world * N_BITS / w / 1e9, nl, float(np.unpackbits(bits_host.numpy()).mean())
+        w = max_over_ranks(time.perf_counter() - t1)
+        return Fe * steps * world * NB / w / 1e9, nl, float(np.unpackbits(bits_host.numpy()).mean())
 
-    # headline e2e: the decoder of this workload quantises its samples to Q = 6 bits (decodeNormalizedMinSum ... 2.0 6 1.25), so the
-    # host hands over what a 6-bit converter delivers, one byte per sample (LDPC_GPU_DT_Q8; bit-identical to raw double samples:
-    # tests/test_gpu_parity.py::test_quantiser_level_input_equals_raw_sample_input).  binary16 / fp32 samples are reported beside it.
-    e2e_value, e2e_launches, ber_e2e = run_e2e(torch.int8, abi.DT_Q8)
-    e2e16_value, _, ber_e2e16 = run_e2e(torch.float16, abi.DT_F16)
-    e2e32_value, _, ber_e2e32 = run_e2e(torch.float32, abi.DT_F32)
+    noisy_gdbf = cfg.kind == abi.KIND_GDBF and abi.noise_rows_needed(cfg) > 0
+    e2e = None
+    if not noisy_gdbf:                                   # (the noisy GDBF variants would stream T x N doubles of noise per frame: not a format anybody feeds)
+        if W["q8"]:
+            # headline e2e: the decoder quantises its samples to Q bits, so the host hands over what a Q-bit converter delivers, one byte per
+            # sample (LDPC_GPU_DT_Q8; bit-identical to raw double samples: tests/test_gpu_parity.py::test_quantiser_level_input_equals_raw_sample_input)
+            v8, e2e_launches, ber8 = run_e2e(dec, torch.int8, abi.DT_Q8)
+            e2e = {"value": v8, "unit": "Gbit/s", "h2d_bytes_per_step": Fe * NB * 1, "d2h_bytes_per_step": Fe * ((NB + 7) // 8 + 4), "steps": e2e_steps,
+                   "api": "ldpc_gpu_decode_batch(mem=HOST, y_dtype=Q8): pinned %d-bit quantiser levels (one byte per sample) in, packed decisions + iteration counts out" % W["q8"][1],
+                   "decoded_ber": ber8}
+        v64, l64, ber64 = run_e2e(dec, torch.float64, abi.DT_F64, steps=3)
+        v32, _, ber32 = run_e2e(dec, torch.float32, abi.DT_F32, steps=3)
+        v16, _, ber16 = run_e2e(dec, torch.float16, abi.DT_F16, steps=3)
+        if e2e is None:
+            e2e = {"value": v64, "unit": "Gbit/s", "h2d_bytes_per_step": Fe * NB * 8 + (Fe * abi.HW_QBUF * 8 if hw_noise is not None else 0),
+                   "d2h_bytes_per_step": Fe * ((NB + 7) // 8 + 4), "steps": 3,
+                   "api": "ldpc_gpu_decode_batch(mem=HOST, y_dtype=F64): pinned double samples (the reference's own sample type) in, packed decisions + iteration counts out",
+                   "decoded_ber": ber64}
+            e2e_launches = l64
+        e2e["fp64_samples"] = {"value": v64, "h2d_bytes_per_step": Fe * NB * 8, "decoded_ber": ber64}
+        e2e["fp32_samples"] = {"value": v32, "h2d_bytes_per_step": Fe * NB * 4, "decoded_ber": ber32}
+        e2e["fp16_samples"] = {"value": v16, "h2d_bytes_per_step": Fe * NB * 2, "decoded_ber": ber16}
+    else:
+        e2e = {"value": None, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "api": "not measured for this workload: the parity entry of a noisy bit-flipping decoder takes T x N doubles of decoder noise per frame"}
+        e2e_launches = 0
 
-    # ---- extra, labelled: the two-frames-per-thread binary16 instantiation (not the headline dtype) ----
-    h2 = None
-    if args.precision == "f32":
-        dech = capi.Decoder(code, cfg_of(abi, abi.PREC_F16X2), device=local)
-        for i in range(2):
-            dech.simulate(snr, R, 1234, 10 ** 9 + i * F, F)
-        barrier()
-        t2 = time.perf_counter()
-        hsteps = max(3, min(args.steps, 5))
-        htot = None
-        for i in range(hsteps):
-            begin, n = shard.step_range(10 ** 6 + i, rank, world, F)
-            r = dech.simulate(snr, R, 1234, begin, n)
-            htot = dict(r.counters) if htot is None else {k: htot[k] + r.counters[k] for k in htot}
-        barrier()
-        hw = time.perf_counter() - t2
-        if dist is not None:
-            tw = torch.tensor([hw], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-            hw = float(tw[0])
-        h2 = {"value": F * hsteps * world * N_BITS / hw / 1e9, "unit": "Gbit/s", "dtype": "f16x2",
-              "fer_this_rank": htot["wordErrors"] / max(1, htot["totalWords"]), "ber_this_rank": htot["errors"] / max(1, htot["totalBits"]),
-              "note": "LDPC_GPU_PREC_F16X2: two frames per thread, binary16 messages clamped to +-512; a labelled throughput "
-                      "instantiation validated on decisions of converging frames and on FER confidence intervals, not the headline"}
+    # ---- extras on the same workload: the fp64 parity instantiation, fp32, the fast channel ----------
+    extras, others = {}, {}
+    if not args.no_extras and W["variant"] in ("decodeOffsetMinSum", "decodeNormalizedMinSum"):
+        for name, prec2, frames in (("parity_f64", "f64", 1 << 17), ("fp32", "f32", 1 << 18), ("f16x2", "x2", 1 << 19)):
+            if prec2 == precision:
+                continue
+            out, d2 = short_value(wl, prec2, frames)
+            ve, _, _ = run_e2e(d2, torch.int8, abi.DT_Q8, steps=3)
+            out["e2e"] = ve
+            if prec2 == "x2":
+                out["exact_lattice_kernel"], out["redo_frames"] = d2.stats()
+                if not out["exact_lattice_kernel"]:
+                    out["note"] = ("LDPC_GPU_PREC_F16X2 off the exact lattice: binary16 messages clamped to +-512, a labelled throughput "
+                                   "instantiation (decisions of converging frames, FER confidence intervals), never the headline")
+            extras[name] = out
+        out, _ = short_value(wl, precision, 1 << 19, channel=abi.CHANNEL_FAST)
+        extras["fast_channel"] = dict(out, note="LDPC_GPU_CHANNEL_FAST: SFU Box-Muller (lg2/sqrt/sin/cos.approx) instead of the CPU-reproducible polynomials")
+    if not args.no_extras:
+        for name, frames in (("nms_8023", 1 << 19), ("oms_8023", 1 << 19), ("bp_8023", 1 << 17), ("ms_peg_t50", 1 << 18), ("ms_dvbs2", 1 << 13),
+                             ("ngdbfhw_8023", 1 << 18), ("smngdbf_8023", 1 << 16)):
+            if name == wl:
+                continue
+            out, _ = short_value(name, WORKLOADS[name]["precision"], frames)
+            out["workload"] = WORKLOADS[name]["text"]
+            others[name] = out
     if world > 1:
         capi.lib().ldpc_gpu_comm_destroy()
         dist.destroy_process_group()
     if rank != 0:
         return 0
 
-    b_msg = 4 if prec == abi.PREC_F32 else 8
-    bytes_per_frame = WORKLOAD["T"] * (4 * E_EDGES + N_BITS) * b_msg           # B_iter * T, B_io = 0 (fused channel)
-    peak, peak_src = measured_peak()
+    # ---- roofline ------------------------------------------------------------------
+    E = code.E
+    b_msg = {"x2": 2, "f32": 4, "f64": 8}[precision]
+    hbm_peak, peak_src = measured_peak()
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    smem_peak = 148 * 128 * sm_mhz * 1e6 / 1e9                                   # GB/s: 148 SMs x 128 B/clk x f_SM
+    if W["variant"] in ("decodeMinSum", "decodeOffsetMinSum", "decodeNormalizedMinSum", "decodeBP"):
+        bytes_per_frame = W["T"] * (4 * E + NB) * b_msg                           # B_iter * T, B_io = 0 (fused channel)
+        iters_per_frame = W["T"]
+    else:                                                                         # GDBF family: (2E)/8 bit-packed + N*b_y per executed iteration
+        iters_per_frame = total["totalIterations"] / max(1, total["totalWords"])
+        bytes_per_frame = iters_per_frame * (2 * E / 8 + NB * (4 if W["variant"] == "NGDBFhw" else 8))
     achieved = F * args.steps * bytes_per_frame / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+    hbm_bound = geo["smem_bytes"] < 48 * 1024 and W["code"] == "dvbs2"
+    prof = PROFILE_CSV.get(precision) if wl in ("oms_8023", "nms_8023") else None
+    edge_rate = E * iters_per_frame * F * args.steps / (kernel_ms * 1e-3) if kernel_ms > 0 else None
+    roof = {"bound": "hbm" if hbm_bound else "smem+issue", "achieved": achieved, "peak": hbm_peak if hbm_bound else smem_peak, "unit": "GB/s",
+            "frac": (achieved / (hbm_peak if hbm_bound else smem_peak)) if achieved else None,
+            "traffic": profiled_traffic(prof), "traffic_source": (prof + " (dram bytes per launch of 65536 frames)") if prof else None,
+            "peak_source": peak_src if hbm_bound else "148 SMs x 128 B/clk x %.0f MHz (SM clock sampled during the timed region); SURVEY.md 8(d)" % sm_mhz,
+            "algorithmic_bytes_per_frame": bytes_per_frame, "message_bytes": b_msg,
+            "hbm_view": {"peak": hbm_peak, "frac": (achieved / hbm_peak) if achieved else None, "peak_source": peak_src,
+                         "note": "messages never leave the SM: DRAM traffic (`traffic`) is nil, so this fraction exceeds 1 and says nothing"},
+            "issue": {"lane_instr_slots_per_edge_iteration": (148 * 4 * 32 * sm_mhz * 1e6) / edge_rate if edge_rate else None,
+                      "profiled_issue_active_pct": profiled_metric(prof, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                      "profiled_warp_instr_per_launch": profiled_metric(prof, "smsp__inst_executed.sum"),
+                      "profiled_shared_wavefronts_pct_of_peak": profiled_metric(prof, "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+                      "profiled_l1tex_pct_of_peak": profiled_metric(prof, "l1tex__throughput.avg.pct_of_peak_sustained_active"),
+                      "profile": prof}}
+    dtype_text = DTYPE_TEXT[precision]
     line = {
         "metric": "coded Gbit/s decoded at fixed iters", "value": value, "unit": "Gbit/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": config_block("gpu", F, Fe),
-        "e2e": {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": Fe * N_BITS * 1,
-                "d2h_bytes_per_step": Fe * (N_BITS // 8 + 4), "steps": e2e_steps,
-                "api": "ldpc_gpu_decode_batch(mem=HOST, y_dtype=Q8): pinned 6-bit quantiser levels (one byte per sample) in, packed decisions + iteration counts out",
-                "decoded_ber": ber_e2e,
-                "fp16_samples": {"value": e2e16_value, "h2d_bytes_per_step": Fe * N_BITS * 2, "decoded_ber": ber_e2e16},
-                "fp32_samples": {"value": e2e32_value, "h2d_bytes_per_step": Fe * N_BITS * 4, "decoded_ber": ber_e2e32}},
+        "scaling": "weak", "vs_baseline": None, "dtype": dtype_text, "data": "synthetic",
+        "config": config_block(wl, "gpu", F, Fe),
+        "e2e": e2e,
         "gpu_launches": int(launches), "e2e_gpu_launches": int(e2e_launches),
         "kernel_ms_per_step": kernel_ms / args.steps,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": profiled_traffic(),
-                     "traffic_source": PROFILE_CSV + " (bytes per launch of 131072 frames)",
-                     "peak_source": peak_src,
-                     "algorithmic_bytes_per_frame": bytes_per_frame,
-                     "note": "messages never leave the SM (shared memory): DRAM traffic is nil, so algorithmic message bytes over "
-                             "kernel time exceed the HBM copy peak; the binding resources are shared-memory wavefronts, the ALU pipe "
-                             "and issue slots (DESIGN.md section 3, profiles/r1_summary.md)"},
-        "onchip": {"profiled_l1tex_pct_of_peak": profiled_metric("l1tex__throughput.avg.pct_of_peak_sustained_active"),
-                   "profiled_issue_active_pct": profiled_metric("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-                   "profiled_shared_wavefronts_pct_of_peak": profiled_metric("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
-                   "profile": PROFILE_CSV,
-                   "edge_updates_per_s": 2.0 * E_EDGES * WORKLOAD["T"] * F * args.steps / (kernel_ms * 1e-3) if kernel_ms > 0 else None,
-                   "issue_slots_per_edge_iteration": (148 * 4 * 32 * 1.965e9) / (E_EDGES * WORKLOAD["T"] * F * args.steps / (kernel_ms * 1e-3)) if kernel_ms > 0 else None},
+        "roofline": roof,
         "geometry": geo, "cpu_affinity_rank0": numa, "counters": total, "ber": total["errors"] / max(1, total["totalBits"]),
         "fer": total["wordErrors"] / max(1, total["totalWords"]),
         "clocks": clocks,
     }
-    if h2 is not None:
-        line["f16x2"] = h2
+    if precision == "x2":
+        line["parity"] = {"exact_lattice_kernel": bool(x2_exact), "redo_frames_fp64": int(redo_frames), "frames": int(F * (args.steps + args.warmup)),
+                          "statement": ("decisions, iteration counts and counters bit-identical to the fp64 parity instantiation / the double oracle on every frame "
+                                        "(tests/test_gpu_x2.py); frames the packed kernel cannot certify are re-decoded in fp64 inside the same call")
+                          if x2_exact else "LDPC_GPU_PREC_F16X2 off the exact lattice: labelled approximate instantiation"}
+    line.update(extras)
+    if others:
+        line["other_workloads"] = others
     if cpu is not None:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline_1core"] = {k: cpu1[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if cpug is not None:
+            line["cpu_baseline_refflags"] = {k: cpug[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline_refflags_1core"] = {k: cpug1[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
     return 0
 

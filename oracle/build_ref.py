@@ -43,6 +43,9 @@ VARIANTS = {
 }
 
 
+BENCH_VARIANTS = ("decodeMinSum", "decodeOffsetMinSum", "decodeNormalizedMinSum", "decodeBP", "NGDBFhw", "decodeSMNGDBF")
+
+
 def run(cmd):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
@@ -68,8 +71,9 @@ def build_restatement(force=False):
     return out
 
 
-def build_reference(force=False, opt="-O2", suffix=""):
-    """Returns the list of built libraries ([] when the reference tree is absent)."""
+def build_reference(force=False, opt="-O2", suffix="", only=None):
+    """Returns the list of built libraries ([] when the reference tree is absent).
+    opt="-O0", suffix="_g": the reference's own flags (`CFLAGS = -g -I./inc`, no -O, Makefile:5-6) for bench.py's cpu_baseline_refflags."""
     if not os.path.isdir(os.path.join(REF, "src")):
         return []
     os.makedirs(OUT, exist_ok=True)
@@ -77,6 +81,8 @@ def build_reference(force=False, opt="-O2", suffix=""):
     harness = os.path.join(HERE, "ref_harness.cpp")
     common = [os.path.join(REF, "src", f) for f in ("alist.cpp", "r.cpp", "nrutil.cpp")]
     for name, (tu, sel, macros) in VARIANTS.items():
+        if only is not None and name not in only:
+            continue
         out = os.path.join(OUT, "libref_%s%s.so" % (name, suffix))
         src = os.path.join(REF, "src", tu)
         if force or not newer(out, [harness, src] + common):
@@ -92,4 +98,5 @@ if __name__ == "__main__":
     force = "--force" in sys.argv
     print(build_restatement(force))
     libs = build_reference(force)
+    build_reference(force, opt="-O0", suffix="_g", only=BENCH_VARIANTS)
     print("%d reference variants built into %s" % (len(libs), OUT) if libs else "reference tree absent: oracle/_ref not rebuilt")

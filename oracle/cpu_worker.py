@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cfg", default="{}")
+    ap.add_argument("--lib-suffix", default="", help="'_g': the build with the reference's own flags (-g, no -O)")
     a = ap.parse_args()
 
     import numpy as np
@@ -37,8 +38,10 @@ def main():
     over = json.loads(a.cfg)
     over["num_iterations"] = a.iters
     cfg = cases.cfg_for(a.variant, code=a.code, **over)
-    if Reference.available(a.variant):
-        eng, kind = Reference(a.variant, a.code), "reference"
+    if a.lib_suffix and not Reference.available(a.variant + a.lib_suffix):
+        raise SystemExit("oracle/_ref/libref_%s%s.so is not built" % (a.variant, a.lib_suffix))
+    if Reference.available(a.variant + a.lib_suffix):
+        eng, kind = Reference(a.variant + a.lib_suffix, a.code), "reference"
     else:
         eng, kind = Oracle(a.code), "port"
     y, noise, rows, cw = cases.make_inputs(eng.N, cfg, a.snr, a.rate, a.frames, a.seed)

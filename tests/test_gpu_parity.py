@@ -198,6 +198,7 @@ def test_f16x2_register_resident_kernel_equals_f16x2_scheduled_kernel(variant, m
     R, snr = 0.8413, 3.9
     code = capi.Code(code_path("802_3_H"))
     cws = code.random_codewords(9, 4)
+    monkeypatch.setenv("LDPC_GPU_NO_X2", "1")             # the labelled kernels, also where the exact-lattice kernel would be selected
     for T, F in ((0, 6), (1, 7), (10, 41)):
         cfg = cases.cfg_for(variant, code="802_3_H", num_iterations=T, precision=abi.PREC_F16X2)
         y, noise, rows, cw = cases.make_inputs(2048, cfg, snr, R, F, 77 + T, cws if T else None)
