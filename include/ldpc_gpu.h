@@ -74,6 +74,10 @@ extern "C" {
 #define LDPC_GPU_F_REDECODE               (1u << 13)  /* -D redecode: RNGDBF.cpp conventions
                                                          (phase loop, w = alpha*Ymax/dv, clip y before copy) */
 
+#define LDPC_GPU_F_CERT_STOP              (1u << 14)  /* no reference macro.  LDPC_GPU_PREC_F16X2 on an exact lattice only (csrc/ldpc_ms_x2.cuh):
+                                                         stop iterating a frame once its decisions are certified final -- the reported decisions,
+                                                         iteration counts (T) and counters are still those of T full iterations; out_soft is refused */
+
 /* ---- arithmetic of the message / metric path --------------------------- */
 #define LDPC_GPU_PREC_F64   0   /* parity instantiation: IEEE double, the reference's operation order */
 #define LDPC_GPU_PREC_F32   1   /* throughput instantiation: fp32 messages, same dataflow */

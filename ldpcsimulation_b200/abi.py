@@ -20,6 +20,7 @@ F_UNIFORMNOISE = 1 << 10
 F_NOISESHAPING = 1 << 11
 F_QUANTIZEPROBABILITIES = 1 << 12
 F_REDECODE = 1 << 13
+F_CERT_STOP = 1 << 14
 
 # reference -D macro name -> flag bit (C_implementations/Makefile:24-71)
 MACRO_FLAGS = {
@@ -29,6 +30,7 @@ MACRO_FLAGS = {
     "weightSyndromes": F_WEIGHTSYNDROMES, "outputSmoothing": F_OUTPUTSMOOTHING,
     "thresholdAdaptation": F_THRESHOLDADAPTATION, "uniformNoise": F_UNIFORMNOISE,
     "noiseShaping": F_NOISESHAPING, "quantizeProbabilities": F_QUANTIZEPROBABILITIES, "redecode": F_REDECODE,
+    "certStop": F_CERT_STOP,
 }
 
 PREC_F64, PREC_F32, PREC_F16X2 = 0, 1, 2

@@ -268,6 +268,8 @@ struct Slot {                    // one in-flight chunk of a host-memory batch
     cudaStream_t st = nullptr; cudaEvent_t k0 = nullptr, k1 = nullptr;
     DevBuf y, noise, cw, qp, bits, iters, soft, errs, flags;
     bool used = false;
+    ldpc::FrameIO io;            // the chunk in flight (for the redo launch of the exact-lattice kernel)
+    long long f0 = 0, nf = 0;
 };
 
 struct ldpc_gpu_decoder {
@@ -290,6 +292,7 @@ struct ldpc_gpu_decoder {
     ldpc_gpu_decoder *redo = nullptr;
     long long *d_redo_list = nullptr; size_t redo_cap = 0;
     unsigned int *d_redo_count = nullptr; unsigned long long *d_redo_total = nullptr;
+    unsigned int *h_redo = nullptr;          // pinned [2]: the two slots' redo counts, copied back behind every launch
 };
 
 // Does the configuration put plain / offset min-sum on a lattice binary16 holds exactly (ldpc_ms_x2.cuh)?
@@ -440,7 +443,8 @@ static int pick_kernel(ldpc_gpu_decoder *d)
                     d->x2 = true;
                     const char *xv = getenv("LDPC_GPU_X2_VARIANT");   // A/B switch: offsets kept in registers | re-read, 2 or 3 CTAs per SM
                     const int variant = xv ? atoi(xv) : 1;
-                    d->fn = variant == 0 ? (KernelFn)ms_x2_kernel<32, 6, 2048, 384, 2, true> : (KernelFn)ms_x2_kernel<32, 6, 2048, 384, 2, false>;
+                    d->fn = variant == 0 ? (KernelFn)ms_x2_kernel<32, 6, 2048, 384, 2, true>
+                          : variant == 2 ? (KernelFn)ms_x2_kernel<32, 6, 2048, 384, 3, false> : (KernelFn)ms_x2_kernel<32, 6, 2048, 384, 2, false>;
                     smem = ms_x2_smem_bytes(v);
                 }
             }
@@ -534,6 +538,8 @@ static int pick_kernel(ldpc_gpu_decoder *d)
 geometry:
     if (smem > (size_t)max_optin)
         return set_err(LDPC_GPU_ERR_UNSUPPORTED, "shared-memory scratch (" + std::to_string(smem) + " B) exceeds one SM");
+    if ((d->cfg.flags & LDPC_GPU_F_CERT_STOP) && !d->x2)
+        return set_err(LDPC_GPU_ERR_UNSUPPORTED, "LDPC_GPU_F_CERT_STOP needs LDPC_GPU_PREC_F16X2 on an exact lattice (plain / offset min-sum, dyadic quantiser step, the 802.3an H)");
     CU_TRY(cudaFuncSetAttribute((const void *)d->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes fa;
     CU_TRY(cudaFuncGetAttributes(&fa, (const void *)d->fn));
@@ -597,6 +603,7 @@ extern "C" int ldpc_gpu_decoder_destroy(ldpc_gpu_decoder *d)
     if (d->d_redo_list) cudaFree(d->d_redo_list);
     if (d->d_redo_count) cudaFree(d->d_redo_count);
     if (d->d_redo_total) cudaFree(d->d_redo_total);
+    if (d->h_redo) cudaFreeHost(d->h_redo);
     if (d->d_counters) cudaFree(d->d_counters);
     if (d->d_ws) cudaFree(d->d_ws);
     if (d->d_cwtab) cudaFree(d->d_cwtab);
@@ -620,10 +627,11 @@ extern "C" int ldpc_gpu_decoder_create(const ldpc_gpu_code *code, const ldpc_gpu
          (rc = build_schedule(d, code, cfg->precision == LDPC_GPU_PREC_F64 ? 8 : 4))) ||
         (rc = pick_kernel(d))) { ldpc_gpu_decoder_destroy(d); return rc; }
     if (d->x2) {
-        ldpc_gpu_decoder_cfg c64 = *cfg; c64.precision = LDPC_GPU_PREC_F64;
+        ldpc_gpu_decoder_cfg c64 = *cfg; c64.precision = LDPC_GPU_PREC_F64; c64.flags &= ~(uint32_t)LDPC_GPU_F_CERT_STOP;
         if ((rc = ldpc_gpu_decoder_create(code, &c64, device, &d->redo))) { ldpc_gpu_decoder_destroy(d); return rc; }
         if (cudaMalloc(&d->d_redo_count, 2 * sizeof(unsigned int)) != cudaSuccess || cudaMalloc(&d->d_redo_total, sizeof(unsigned long long)) != cudaSuccess ||
-            cudaMemset(d->d_redo_total, 0, sizeof(unsigned long long)) != cudaSuccess) { ldpc_gpu_decoder_destroy(d); return set_err(LDPC_GPU_ERR_NOMEM, "redo-list allocation failed"); }
+            cudaMemset(d->d_redo_total, 0, sizeof(unsigned long long)) != cudaSuccess ||
+            cudaHostAlloc((void **)&d->h_redo, 2 * sizeof(unsigned int), cudaHostAllocDefault) != cudaSuccess) { ldpc_gpu_decoder_destroy(d); return set_err(LDPC_GPU_ERR_NOMEM, "redo-list allocation failed"); }
     }
     for (Slot &s : d->slot) {
         if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&s.k0) != cudaSuccess ||
@@ -771,13 +779,31 @@ static int launch(ldpc_gpu_decoder *d, const DecParams &p, const FrameIO &io, cu
     d->fn<<<(unsigned)want, d->block, d->smem, st>>>(d->dev, p, io2);
     CU_TRY(cudaGetLastError());
     d->last_launches++;
-    if (d->x2) {                                          // the frames the packed kernel could not certify, fp64, same stream, no host round trip
-        FrameIO io3 = io; io3.frame_list = io2.redo_list; io3.n_frames_dev = io2.redo_count;
-        ldpc_gpu_decoder *r = d->redo;
-        r->fn<<<(unsigned)std::min<long long>(io.n_frames, r->grid_full), r->block, r->smem, st>>>(r->dev, p, io3);
-        CU_TRY(cudaGetLastError());
-        d->last_launches++;
+    if (d->x2) {                                          // how many frames the packed kernel could not certify: read by redo_after_sync
+        const int half = (st == d->slot[1].st) ? 1 : 0;
+        CU_TRY(cudaMemcpyAsync(&d->h_redo[half], d->d_redo_count + half, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     }
+    return LDPC_GPU_OK;
+}
+
+// Exact-lattice kernel: after the stream of a launch has been synchronised, decode the frames it could not certify (about 5 in
+// 10^6 at the operating point) with the fp64 parity instantiation, same FrameIO, same stream.  *ran tells the caller whether
+// outputs changed.  Nothing is launched in the common case.
+static int redo_after_sync(ldpc_gpu_decoder *d, const DecParams &p, const FrameIO &io, cudaStream_t st, bool *ran)
+{
+    if (ran) *ran = false;
+    if (!d->x2) return LDPC_GPU_OK;
+    const int half = (st == d->slot[1].st) ? 1 : 0;
+    const unsigned int n = d->h_redo[half];
+    if (n == 0) return LDPC_GPU_OK;
+    FrameIO io3 = io; io3.workspace = nullptr; io3.ws_stride = 0;
+    io3.frame_list = d->d_redo_list + (size_t)half * d->redo_cap; io3.n_frames_dev = d->d_redo_count + half;
+    ldpc_gpu_decoder *r = d->redo;
+    r->fn<<<(unsigned)std::min<long long>((long long)n, r->grid_full), r->block, r->smem, st>>>(r->dev, p, io3);
+    CU_TRY(cudaGetLastError());
+    d->last_launches++;
+    CU_TRY(cudaStreamSynchronize(st));
+    if (ran) *ran = true;
     return LDPC_GPU_OK;
 }
 
@@ -792,6 +818,8 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
     if (b->y_dtype != LDPC_GPU_DT_F64 && b->y_dtype != LDPC_GPU_DT_F32 && b->y_dtype != LDPC_GPU_DT_F16 && b->y_dtype != LDPC_GPU_DT_Q8)
         return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown y_dtype");
     const int N = d->N, kind = d->cfg.kind;
+    if ((d->cfg.flags & LDPC_GPU_F_CERT_STOP) && b->out_soft)
+        return set_err(LDPC_GPU_ERR_INVALID_ARG, "LDPC_GPU_F_CERT_STOP reports decisions, not the a-posteriori sums of iteration T: out_soft must be NULL");
     if (b->y_dtype == LDPC_GPU_DT_Q8 && !(kind == LDPC_GPU_KIND_MINSUM && (d->cfg.flags & LDPC_GPU_F_QUANTIZE_SAMPLES) && d->cfg.Q >= 2 && d->cfg.Q <= 6))
         return set_err(LDPC_GPU_ERR_INVALID_ARG, "LDPC_GPU_DT_Q8 carries quantiser levels: it needs a min-sum decoder with LDPC_GPU_F_QUANTIZE_SAMPLES and 2 <= Q <= 6");
     const int rps = rows_per_step(d->cfg.flags);
@@ -827,6 +855,7 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
         CU_TRY(cudaEventRecord(d->slot[0].k1, st0));
         CU_TRY(cudaStreamSynchronize(st0));
         float ms = 0; cudaEventElapsedTime(&ms, d->slot[0].k0, d->slot[0].k1); d->last_kernel_ms = ms;
+        if ((rc = redo_after_sync(d, p, io, st0, nullptr))) return rc;
     } else if (b->mem == LDPC_GPU_MEM_HOST) {
         // two-slot pipeline: H2D / kernel / D2H of consecutive chunks overlap on two streams
         const size_t per_frame = esz * N + (b->out_soft ? ssz * N : 0) + 8 * noise_pf + (b->codeword ? N : 0) + bpf + 16;
@@ -838,17 +867,32 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
         chunk = std::max<long long>(chunk, 16ll * d->grid_full * d->frames_per_cta);
         chunk = std::min<long long>(chunk, std::max<long long>(1, (b->n_frames + 1) / 2));
         if (b->n_frames <= 2 * (long long)d->grid_full) chunk = std::max<long long>(1, b->n_frames);
+        auto copy_out = [&](Slot &s) -> int {             // results of the slot's chunk, device -> caller
+            const long long f0 = s.f0, nf = s.nf;
+            if (b->out_bits)   CU_TRY(cudaMemcpyAsync(b->out_bits + (size_t)f0 * bpf, s.bits.p, bpf * nf, cudaMemcpyDeviceToHost, s.st));
+            if (b->out_iters)  CU_TRY(cudaMemcpyAsync(b->out_iters + f0, s.iters.p, 4 * (size_t)nf, cudaMemcpyDeviceToHost, s.st));
+            if (b->out_soft)   CU_TRY(cudaMemcpyAsync((char *)b->out_soft + (size_t)f0 * N * ssz, s.soft.p, ssz * N * nf, cudaMemcpyDeviceToHost, s.st));
+            if (b->out_errors) CU_TRY(cudaMemcpyAsync(b->out_errors + f0, s.errs.p, 4 * (size_t)nf, cudaMemcpyDeviceToHost, s.st));
+            if (b->out_flags)  CU_TRY(cudaMemcpyAsync(b->out_flags + f0, s.flags.p, (size_t)nf, cudaMemcpyDeviceToHost, s.st));
+            return LDPC_GPU_OK;
+        };
+        auto drain = [&](Slot &s) -> int {                // wait for the slot's chunk; redo what the exact-lattice kernel left open
+            CU_TRY(cudaStreamSynchronize(s.st));
+            float ms = 0; cudaEventElapsedTime(&ms, s.k0, s.k1); d->last_kernel_ms += ms;
+            bool ran = false;
+            int r2 = redo_after_sync(d, p, s.io, s.st, &ran);
+            if (r2) return r2;
+            if (ran) { if ((r2 = copy_out(s))) return r2; CU_TRY(cudaStreamSynchronize(s.st)); }
+            return LDPC_GPU_OK;
+        };
         // any failure inside the loop must not leave async copies in flight on the caller's buffers
         auto run_chunks = [&]() -> int {
         int c = 0;
         for (long long f0 = 0; f0 < b->n_frames; f0 += chunk, c++) {
             const long long nf = std::min<long long>(chunk, b->n_frames - f0);
             Slot &s = d->slot[c & 1];
-            if (s.used) {                                 // drain this slot's previous chunk
-                CU_TRY(cudaStreamSynchronize(s.st));
-                float ms = 0; cudaEventElapsedTime(&ms, s.k0, s.k1); d->last_kernel_ms += ms;
-            }
-            s.used = true;
+            if (s.used && (rc = drain(s))) return rc;     // this slot's previous chunk
+            s.used = true; s.f0 = f0; s.nf = nf;
             if ((rc = s.y.reserve(esz * N * nf))) return rc;
             CU_TRY(cudaMemcpyAsync(s.y.p, (const char *)b->y + (size_t)f0 * N * esz, esz * N * nf, cudaMemcpyHostToDevice, s.st));
             io.y = s.y.p; io.n_frames = nf; io.frame_begin = f0;
@@ -875,13 +919,10 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
             if (b->out_errors) { if ((rc = s.errs.reserve(4 * (size_t)nf))) return rc; io.out_errors = (int *)s.errs.p; }
             if (b->out_flags)  { if ((rc = s.flags.reserve((size_t)nf))) return rc; io.out_flags = (uint8_t *)s.flags.p; }
             CU_TRY(cudaEventRecord(s.k0, s.st));
+            s.io = io;
             if ((rc = launch(d, p, io, s.st))) return rc;
             CU_TRY(cudaEventRecord(s.k1, s.st));
-            if (b->out_bits)   CU_TRY(cudaMemcpyAsync(b->out_bits + (size_t)f0 * bpf, s.bits.p, bpf * nf, cudaMemcpyDeviceToHost, s.st));
-            if (b->out_iters)  CU_TRY(cudaMemcpyAsync(b->out_iters + f0, s.iters.p, 4 * (size_t)nf, cudaMemcpyDeviceToHost, s.st));
-            if (b->out_soft)   CU_TRY(cudaMemcpyAsync((char *)b->out_soft + (size_t)f0 * N * ssz, s.soft.p, ssz * N * nf, cudaMemcpyDeviceToHost, s.st));
-            if (b->out_errors) CU_TRY(cudaMemcpyAsync(b->out_errors + f0, s.errs.p, 4 * (size_t)nf, cudaMemcpyDeviceToHost, s.st));
-            if (b->out_flags)  CU_TRY(cudaMemcpyAsync(b->out_flags + f0, s.flags.p, (size_t)nf, cudaMemcpyDeviceToHost, s.st));
+            if ((rc = copy_out(s))) return rc;
         }
         return LDPC_GPU_OK;
         };
@@ -894,8 +935,7 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
         }
         for (Slot &s : d->slot) if (s.used) {
             s.used = false;
-            CU_TRY(cudaStreamSynchronize(s.st));
-            float ms = 0; cudaEventElapsedTime(&ms, s.k0, s.k1); d->last_kernel_ms += ms;
+            if ((rc = drain(s))) { const std::string msg = g_err; for (Slot &t : d->slot) { cudaStreamSynchronize(t.st); t.used = false; } return set_err(rc, msg); }
         }
     } else return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown batch.mem");
     if (cnt) return fetch_counters(d, cnt, st0);
@@ -926,6 +966,7 @@ extern "C" int ldpc_gpu_simulate(ldpc_gpu_decoder *d, const ldpc_gpu_channel *ch
         const long long nf = std::min<long long>(per_launch, a->n_frames - done);
         io.n_frames = nf; io.frame_begin = a->frame_begin + done;
         if ((rc = launch(d, p, io, st))) return rc;
+        if (d->x2) { CU_TRY(cudaStreamSynchronize(st)); if ((rc = redo_after_sync(d, p, io, st, nullptr))) return rc; }
         done += nf;
         if (stop_rule && done < a->n_frames) {            // poll the reference's loop condition (decodeMinSum.cpp:189)
             unsigned long long h[CNT_N];

@@ -295,7 +295,12 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
         int sa = X2_EXACT, sb = X2_EXACT;
         uint32_t vn_ran = 0u;                                                     // bit h: the previous variable phase checked frame h
         unsigned int *fl = reinterpret_cast<unsigned int *>(&st[2]), *vb = reinterpret_cast<unsigned int *>(&st[4]);
+        const bool cert_stop = (p.flags & LDPC_GPU_F_CERT_STOP) != 0;
+        bool stopped = false;
         for (int it = 0; it < p.T; it++) {
+            // LDPC_GPU_F_CERT_STOP: once neither frame is EXACT any more, no later iteration can change what is reported (a CERTIFIED
+            // frame's decisions are fixed by the lemma, an UNCERTIFIED frame is redone anyway): leave the loop, decisions from S
+            if (cert_stop && it > 0 && sa != X2_EXACT && sb != X2_EXACT) { stopped = true; break; }
             const bool last = (it == p.T - 1);
             if (last) for (int w = tid; w < 2 * nwords; w += nt) dbits[w] = 0u;
             // ---- check-node phase: one row per thread, both frames -----------------------------------
@@ -375,8 +380,17 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
             __syncthreads();
             if (tid == 0 && open_cert) { fl[it & 1] = 0u; vb[(it + 1) & 1] = 0u; }   // both were read by everybody before this barrier
         }
-        if (tid == 0) { st[0] = sa; st[1] = sb; }
-        __syncthreads();
+        if (stopped) {                                                            // decisions of the skipped iterations = sign(S) now
+            for (int w = tid; w < 2 * nwords; w += nt) dbits[w] = 0u;
+            __syncthreads();
+            for (int col = tid; col < N; col += nt) {
+                const int i = (int)__ldg(&c.var_of_col[col]);
+                const __half2 sum = h2_from(S[col]);
+                if (!(__low2float(sum) > 0.0f)) atomicOr(&dbits[i >> 5], 1u << (i & 31));
+                if (!(__high2float(sum) > 0.0f)) atomicOr(&dbits[nwords + (i >> 5)], 1u << (i & 31));
+            }
+            __syncthreads();
+        }
         // frames whose decisions are not certified go to the redo list instead of being reported
         const int enda = sa, endb = sb;
         if (tid == 0) {

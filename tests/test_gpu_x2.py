@@ -105,6 +105,28 @@ def test_x2_simulate_counters_equal_fp64_instantiation(snr):
     assert d16.simulate(snr, R, 2026, 12345, 64).counters == o
 
 
+def test_x2_certified_stop_reports_the_same_results():
+    """LDPC_GPU_F_CERT_STOP: iterations after a frame's decisions are certified final are skipped; decisions, iteration counts
+    (T, as the reference accounts them) and counters are still those of T full iterations."""
+    orc = Oracle("802_3_H")
+    cfg64 = abi.default_cfg(abi.KIND_MINSUM, **OMS)
+    stop = dict(OMS, flags=OMS["flags"] + ["certStop"])
+    for snr in (3.7, 4.4):
+        y, _, _, _ = cases.make_inputs(orc.N, cfg64, snr, R, 777, 31)
+        a = orc.decode(cfg64, snr, R, y)
+        b = _dec(stop).decode(snr, R, y, want_soft=False)
+        assert np.array_equal(a.bits, b.bits) and np.array_equal(a.iters, b.iters) and np.array_equal(a.errors, b.errors)
+        assert a.counters == b.counters
+    d = _dec(stop)
+    s1 = d.simulate(4.0, R, 9, 0, 50000).counters
+    s2 = capi.Decoder(capi.Code(code_path("802_3_H")), abi.default_cfg(abi.KIND_MINSUM, **OMS)).simulate(4.0, R, 9, 0, 50000).counters
+    assert s1 == s2
+    with pytest.raises(capi.LdpcGpuError):                                   # sums of iteration T are not available
+        d.decode(4.0, R, np.ones((2, orc.N)))
+    with pytest.raises(capi.LdpcGpuError):                                   # and the flag exists for the exact-lattice kernel only
+        capi.Decoder(capi.Code(code_path("802_3_H")), abi.default_cfg(abi.KIND_MINSUM, precision=abi.PREC_F32, **stop))
+
+
 def test_non_lattice_configs_keep_the_labelled_kernel():
     d = _dec(dict(flags=["quantizeSamples", "normalizedMS"], num_iterations=10, Ymax=2.0, Q=6, alpha=1.25))
     assert not d.stats()[0]

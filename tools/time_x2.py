@@ -13,11 +13,11 @@ F = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 19
 code = capi.Code(os.path.join(ROOT, "codes", "802_3", "802_3_H.alist"))
 
 
-def run(label, prec, env, T, channel):
+def run(label, prec, env, T, channel, extra_flags=()):
     for k in ("LDPC_GPU_X2_VARIANT", "LDPC_GPU_NO_X2"):
         os.environ.pop(k, None)
     os.environ.update(env)
-    cfg = abi.default_cfg(abi.KIND_MINSUM, flags=["quantizeSamples", "offsetMS"], num_iterations=T, precision=prec,
+    cfg = abi.default_cfg(abi.KIND_MINSUM, flags=["quantizeSamples", "offsetMS"] + list(extra_flags), num_iterations=T, precision=prec,
                           Ymax=1.9375, Q=5, delta=0.125, channel_mode=channel)
     dec = capi.Decoder(code, cfg)
     dec.simulate(4.0, 0.8413, 1, 0, F)
@@ -33,7 +33,9 @@ def run(label, prec, env, T, channel):
 for T in (0, 10):
     for ch in (0, 1):
         run("x2 reload (variant 1)", abi.PREC_F16X2, {"LDPC_GPU_X2_VARIANT": "1"}, T, ch)
-        run("x2 keep (variant 0)", abi.PREC_F16X2, {"LDPC_GPU_X2_VARIANT": "0"}, T, ch)
+        run("x2 3 CTAs/SM (variant 2)", abi.PREC_F16X2, {"LDPC_GPU_X2_VARIANT": "2"}, T, ch)
+        if T:
+            run("x2 certified stop", abi.PREC_F16X2, {"LDPC_GPU_X2_VARIANT": "1"}, T, ch, ["certStop"])
         run("h2rc labelled", abi.PREC_F16X2, {"LDPC_GPU_NO_X2": "1"}, T, ch)
         run("fp32 ms_rc", abi.PREC_F32, {}, T, ch)
 run("fp64 ms_rc", abi.PREC_F64, {}, 10, 0)
