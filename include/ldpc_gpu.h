@@ -250,6 +250,16 @@ int  ldpc_gpu_simulate(ldpc_gpu_decoder *dec, const ldpc_gpu_channel *ch,
 int  ldpc_gpu_redecode_stats(ldpc_gpu_decoder *dec, const ldpc_gpu_channel *ch, const ldpc_gpu_sim_args *args,
                              int32_t n_redecodes, int32_t *outcomes, ldpc_gpu_counters *counters);
 
+/* Replay of ONE frame of the throughput entry, addressed by (seed, frame_id), with a per-iteration trace (SURVEY.md 8(f) N2;
+ * replaces the trace files of src/replayGDBF.cpp:312-314,368-373 and NGDBFhw's LOG_PROCESSING dump, src/NGDBFhw.cpp:304-335):
+ * row t (t = 0 .. *n_rows - 1) = the hard decisions after iteration t + 1 (trace_d, HOST [max_rows][ceil(N/8)], packed like
+ * out_bits) and the syndromes that iteration started from, i.e. of the decisions after iteration t, row 0: of the channel's
+ * hard decisions (trace_syn, optional HOST [max_rows][ceil(M/8)], bit 1 = check unsatisfied).  *n_rows = iterations executed
+ * (the bit-flipping decoders stop at the first all-satisfied syndrome; rows beyond max_rows are counted, not stored).
+ * Output smoothing and re-decoding phases are left out of the trace, as in the reference's trace files.  O(T) small launches. */
+int  ldpc_gpu_replay_frame(ldpc_gpu_decoder *dec, const ldpc_gpu_channel *ch, uint64_t seed, int64_t frame_id, int32_t max_rows,
+                           uint8_t *trace_d, uint8_t *trace_syn, int32_t *n_rows, int32_t *final_errors);
+
 /* The exact samples ldpc_gpu_simulate feeds its decoder for frames
  * [frame_begin, frame_begin+n_frames): y is HOST [F][N] doubles.  noise, if
  * non-NULL, receives the decoder-side raw RNG outputs in ldpc_gpu_batch layout

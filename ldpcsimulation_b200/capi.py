@@ -20,7 +20,7 @@ EXPORTS = [
     "ldpc_gpu_code_create", "ldpc_gpu_code_load_alist", "ldpc_gpu_code_dims", "ldpc_gpu_code_destroy",
     "ldpc_gpu_code_random_codewords",
     "ldpc_gpu_decoder_cfg_default", "ldpc_gpu_iter_hist_len", "ldpc_gpu_decoder_create", "ldpc_gpu_decoder_destroy",
-    "ldpc_gpu_decoder_set_codewords", "ldpc_gpu_decode_batch", "ldpc_gpu_simulate", "ldpc_gpu_redecode_stats", "ldpc_gpu_channel_dump",
+    "ldpc_gpu_decoder_set_codewords", "ldpc_gpu_decode_batch", "ldpc_gpu_simulate", "ldpc_gpu_redecode_stats", "ldpc_gpu_replay_frame", "ldpc_gpu_channel_dump",
     "ldpc_gpu_philox4x32", "ldpc_gpu_last_timing", "ldpc_gpu_decoder_stats", "ldpc_gpu_decoder_geometry",
     "ldpc_gpu_comm_unique_id", "ldpc_gpu_comm_init", "ldpc_gpu_comm_destroy", "ldpc_gpu_allreduce_counters",
 ]
@@ -56,6 +56,8 @@ def lib():
         L.ldpc_gpu_simulate.argtypes = [C.c_void_p, C.POINTER(abi.Channel), C.POINTER(abi.SimArgs), C.POINTER(abi.Counters)]
         L.ldpc_gpu_redecode_stats.argtypes = [C.c_void_p, C.POINTER(abi.Channel), C.POINTER(abi.SimArgs), C.c_int32, C.c_void_p,
                                               C.POINTER(abi.Counters)]
+        L.ldpc_gpu_replay_frame.argtypes = [C.c_void_p, C.POINTER(abi.Channel), C.c_uint64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.ldpc_gpu_channel_dump.argtypes = [C.c_void_p, C.POINTER(abi.Channel), C.c_uint64, C.c_int64, C.c_int64,
                                             C.c_void_p, C.c_void_p, C.c_int64]
         L.ldpc_gpu_philox4x32.argtypes = [C.c_void_p] * 3
@@ -221,6 +223,19 @@ class Decoder:
         out = np.zeros((n_frames, n_redecodes), np.int32)
         check(lib().ldpc_gpu_redecode_stats(self.h, C.byref(ch), C.byref(a), int(n_redecodes), _ptr(out), C.byref(cnt)))
         return out, cnt.as_dict()
+
+    def replay_frame(self, snr_db, R, seed, frame_id, max_rows=None):
+        """Per-iteration trace of one seed-addressed frame: (d [rows][N] 0/1, syn [rows][M] 0/1, rows executed, final error weight)."""
+        T = self.cfg.num_iterations
+        max_rows = T if max_rows is None else max_rows
+        M = self.code.M
+        td = np.zeros((max_rows, (self.N + 7) // 8), np.uint8)
+        ts = np.zeros((max_rows, (M + 7) // 8), np.uint8)
+        n, e = C.c_int32(), C.c_int32()
+        ch = abi.Channel(snr_db, R)
+        check(lib().ldpc_gpu_replay_frame(self.h, C.byref(ch), seed, frame_id, max_rows, _ptr(td), _ptr(ts), C.byref(n), C.byref(e)))
+        k = min(n.value, max_rows)
+        return (np.unpackbits(td[:k], axis=1, bitorder="little")[:, :self.N], np.unpackbits(ts[:k], axis=1, bitorder="little")[:, :M], n.value, e.value)
 
     def channel_dump(self, snr_db, R, seed, frame_begin, n_frames, noise_rows=None):
         ch = abi.Channel(snr_db, R)

@@ -293,6 +293,7 @@ struct ldpc_gpu_decoder {
     long long *d_redo_list = nullptr; size_t redo_cap = 0;
     unsigned int *d_redo_count = nullptr; unsigned long long *d_redo_total = nullptr;
     unsigned int *h_redo = nullptr;          // pinned [2]: the two slots' redo counts, copied back behind every launch
+    std::vector<int> h_mlist, h_rowdeg; int h_dcm = 0;   // host copy of the rows of H (syndromes of ldpc_gpu_replay_frame)
 };
 
 // Does the configuration put plain / offset min-sum on a lattice binary16 holds exactly (ldpc_ms_x2.cuh)?
@@ -621,6 +622,7 @@ extern "C" int ldpc_gpu_decoder_create(const ldpc_gpu_code *code, const ldpc_gpu
     CU_TRY(cudaSetDevice(device));
     ldpc_gpu_decoder *d = new ldpc_gpu_decoder;
     d->device = device; d->cfg = *cfg; d->N = code->N; d->M = code->M;
+    d->h_mlist = code->mlist; d->h_rowdeg = code->row_deg; d->h_dcm = code->dc_max;
     cudaDeviceGetAttribute(&d->n_sm, cudaDevAttrMultiProcessorCount, device);
     if ((rc = build_device_code(d, code)) ||
         ((cfg->kind == LDPC_GPU_KIND_MINSUM || (cfg->kind == LDPC_GPU_KIND_BP && cfg->precision != LDPC_GPU_PREC_F64)) &&
@@ -1033,6 +1035,73 @@ extern "C" int ldpc_gpu_redecode_stats(ldpc_gpu_decoder *d, const ldpc_gpu_chann
     if (cnt) rc = fetch_counters(d, cnt, st); else CU_TRY(cudaStreamSynchronize(st));
     float ms = 0; cudaEventElapsedTime(&ms, d->slot[0].k0, d->slot[0].k1); d->last_kernel_ms = ms;
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// replay of one seed-addressed frame with a per-iteration trace (second half; src/replayGDBF.cpp:306-373
+// writes, per executed flip step, the decisions after the step and the syndromes the step started from; NGDBFhw's
+// LOG_PROCESSING dump, src/NGDBFhw.cpp:304-335, carries the same two vectors).  The frame is a function of (seed, frame id), so
+// the trace is produced kernel-agnostically: the frame is decoded with T = 0, 1, 2, ... iterations (same channel samples, same
+// decoder-noise rows) and row t pairs the decisions after t + 1 iterations with the syndrome of the decisions after t.
+// A debugging tool: O(T) single-frame launches.
+// ------------------------------------------------------------------------------------------------
+extern "C" int ldpc_gpu_replay_frame(ldpc_gpu_decoder *d, const ldpc_gpu_channel *ch, uint64_t seed, int64_t frame_id, int32_t max_rows,
+                                     uint8_t *trace_d, uint8_t *trace_syn, int32_t *n_rows, int32_t *final_errors)
+{
+    if (!d || !trace_d || !n_rows || max_rows < 0) return set_err(LDPC_GPU_ERR_INVALID_ARG, "bad argument");
+    DecParams p; int rc = channel_params(d, ch, p); if (rc) return rc;
+    CU_TRY(cudaSetDevice(d->device));
+    const int N = d->N, M = d->M, T = d->cfg.num_iterations;
+    const size_t bpf = (size_t)(N + 7) / 8, spf = (size_t)(M + 7) / 8;
+    // the trace is the raw decision trajectory: output smoothing only post-processes it (decodeGDBF.cpp:358-367), re-decoding
+    // phases restart it (RNGDBF.cpp:280): phase 1 is traced
+    p.flags &= ~(uint32_t)LDPC_GPU_F_OUTPUTSMOOTHING;
+    if (p.maxphase > 1) p.maxphase = 1;
+    cudaStream_t st = d->slot[0].st;
+    DevBuf bits, iters, errs;
+    if ((rc = bits.reserve(bpf)) || (rc = iters.reserve(4)) || (rc = errs.reserve(4))) { bits.release(); iters.release(); errs.release(); return rc; }
+    std::vector<uint8_t> prev(bpf), cur(bpf);
+    FrameIO io; memset(&io, 0, sizeof io);
+    io.n_frames = 1; io.frame_begin = frame_id; io.seed = seed; io.cw_table = d->d_cwtab; io.n_cw = d->n_cw;
+    io.out_bits = (uint8_t *)bits.p; io.out_iters = (int *)iters.p; io.out_errors = (int *)errs.p;
+    auto run = [&](int t, std::vector<uint8_t> &out, int *it, int *err) -> int {
+        DecParams q = p; q.T = t;
+        int r = launch(d, q, io, st); if (r) return r;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return set_err(LDPC_GPU_ERR_CUDA, "replay: kernel failed");
+        if ((r = redo_after_sync(d, q, io, st, nullptr))) return r;
+        if (cudaMemcpy(out.data(), bits.p, bpf, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(it, iters.p, 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(err, errs.p, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return set_err(LDPC_GPU_ERR_CUDA, "replay: copy failed");
+        return LDPC_GPU_OK;
+    };
+    int it = 0, err = 0, rows = 0;
+    rc = run(0, prev, &it, &err);
+    for (int t = 1; t <= T && !rc; t++) {
+        rc = run(t, cur, &it, &err);
+        if (rc) break;
+        // bit-flipping decoders and DD-BMP stop early: a run that executed fewer than t steps adds no row
+        const bool early = (d->cfg.kind == LDPC_GPU_KIND_GDBF || d->cfg.kind == LDPC_GPU_KIND_NGDBF_HW) ? it < t
+                         : (d->cfg.kind == LDPC_GPU_KIND_DDBMP ? it < t - 1 : false);
+        if (early) break;
+        if (rows < max_rows) {
+            memcpy(trace_d + (size_t)rows * bpf, cur.data(), bpf);
+            if (trace_syn) {
+                uint8_t *sy = trace_syn + (size_t)rows * spf;
+                memset(sy, 0, spf);
+                for (int j = 0; j < M; j++) {
+                    int par = 0;
+                    for (int k = 0; k < d->h_rowdeg[j]; k++) { const int i = d->h_mlist[(size_t)j * d->h_dcm + k]; par ^= (prev[i >> 3] >> (i & 7)) & 1; }
+                    if (par) sy[j >> 3] |= (uint8_t)(1u << (j & 7));
+                }
+            }
+        }
+        rows++;
+        prev.swap(cur);
+    }
+    bits.release(); iters.release(); errs.release();
+    if (rc) return rc;
+    *n_rows = rows;
+    if (final_errors) *final_errors = err;
+    return LDPC_GPU_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
