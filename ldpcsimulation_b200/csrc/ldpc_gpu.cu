@@ -354,7 +354,7 @@ static int build_schedule(ldpc_gpu_decoder *d, const ldpc_gpu_code *c, size_t re
 {
     CodeDev &v = d->dev;
     v.sched = nullptr; v.col_of_var = nullptr; v.var_of_col = nullptr; v.row_slot = nullptr;
-    if (v.regular_dc <= 0 || v.regular_dv <= 0 || v.regular_dc % 4 || v.N > 65535 || getenv("LDPC_GPU_NO_SCHED")) return LDPC_GPU_OK;
+    if (v.regular_dc <= 0 || v.regular_dc % 4 || v.N > 65535 || getenv("LDPC_GPU_NO_SCHED")) return LDPC_GPU_OK;
     const int N = v.N, M = v.M, dc = v.regular_dc, dvm = c->dv_max, dcm = c->dc_max;
     std::vector<int> ml((size_t)M * dc);
     for (int j = 0; j < M; j++) for (int k = 0; k < dc; k++) ml[(size_t)j * dc + k] = c->mlist[(size_t)j * dcm + k];
@@ -498,6 +498,12 @@ static int pick_kernel(ldpc_gpu_decoder *d)
                     block = 384;
                 }
             }
+            else if (v.sched && v.regular_dc == 32 && v.dv_max == 6 && v.N == 2048 && v.M <= 384 && !getenv("LDPC_GPU_NO_RC")) {
+                // the full-rank 802.3an H (802_3.alist: M = 325, dv in {5, 6}): the same register-resident kernel, rows that mix slots
+                smem = f64 ? ms_rc_smem_bytes<double>(v) : ms_rc_smem_bytes<float>(v);
+                fast = f64 ? (KernelFn)ms_rc_kernel<double, 32, 6, 2048, 384, 1, false> : (KernelFn)ms_rc_kernel<float, 32, 6, 2048, 384, 2, false>;
+                block = 384;
+            }
             else if (v.regular_dc == 32 && v.regular_dv == 6) fast = MS_FAST(32, 6, true, true);
             else if (v.regular_dc == 32 && v.dv_max <= 6) fast = MS_FAST(32, 6, true, false);
             else if (v.dc_max <= 8 && v.regular_dv == 3 && v.M <= 512 && !f64 && !getenv("LDPC_GPU_NO_SMALL"))
@@ -547,7 +553,8 @@ geometry:
     const int by_regs = (65536 / std::max(1, fa.numRegs)) & ~31;      // one CTA must fit the register file
     const int block_wanted = block;
     block = std::max(32, std::min(block, std::min(by_regs, fa.maxThreadsPerBlock & ~31)));
-    if (block != block_wanted && (d->fn == (KernelFn)ms_rc_kernel<float, 32, 6, 2048, 384, 2> || d->fn == (KernelFn)ms_rc_kernel<double, 32, 6, 2048, 384, 1>))
+    if (block != block_wanted && (d->fn == (KernelFn)ms_rc_kernel<float, 32, 6, 2048, 384, 2> || d->fn == (KernelFn)ms_rc_kernel<double, 32, 6, 2048, 384, 1> ||
+                                  d->fn == (KernelFn)ms_rc_kernel<float, 32, 6, 2048, 384, 2, false> || d->fn == (KernelFn)ms_rc_kernel<double, 32, 6, 2048, 384, 1, false>))
         return set_err(LDPC_GPU_ERR_UNSUPPORTED, "ms_rc_kernel is written for blocks of exactly 384 threads");
     int nb = 0;
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)d->fn, block, smem));

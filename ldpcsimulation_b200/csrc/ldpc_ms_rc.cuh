@@ -35,7 +35,7 @@ template <> LDPC_DEVINL void fold2<double>(bool &a, double x, double y) { SignOp
 // this phase, the ALU pipe is the busy one; written as PTX mad so that it is neither hoisted into an
 // ALU-pipe IADD3 nor needs a replicated code path per slot, which thrashed the instruction cache:
 // measured 10 % slower than ms_sched_kernel), the constant part is an immediate of the LDS.
-template <typename Real, int DC, int DV, int NB>
+template <typename Real, int DC, int DV, int NB, bool USLOT>
 LDPC_DEVINL void rc_check_row(unsigned char *msgb, const int slot, const uint4 *__restrict__ sched, const int M, const int j, Real (&v)[DC],
                               const bool normalized, const bool offset, const Real alpha, const Real inv_alpha, const Real delta)
 {
@@ -50,7 +50,8 @@ LDPC_DEVINL void rc_check_row(unsigned char *msgb, const int slot, const uint4 *
         for (int q = 0; q < 4; q++) {
             const int k = g * 4 + q;
             uint32_t so;
-            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(so) : "r"((uint32_t)slot), "r"((uint32_t)-NB), "r"(off[q]));
+            if (USLOT) asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(so) : "r"((uint32_t)slot), "r"((uint32_t)-NB), "r"(off[q]));
+            else so = off[q] & (uint32_t)(NB - 1);                                         // rows that mix slots: NB is a power of two (checked by the host)
             v[k] = *reinterpret_cast<const Real *>(msgb + DV * NB + so) - v[k];            // v2c = sum - c2v
         }
         // two edges per update of (min1, min2): lo / hi of the pair, then three-input minima (FMNMX3 on
@@ -109,7 +110,7 @@ LDPC_DEVINL float min_xorsign_abs(float a, float b)
 //           +-1/alpha (the row's sign product) finishes the message: the same rounding of the same operands
 //           as scaling min1 / min2 once per row.  1 ALU-pipe + 2 FMA-pipe instructions per edge instead of
 //           FSETP + FSEL + LOP3 on the ALU pipe, which is the pipe that bounds this phase.
-template <int DC, int DV, int NB>
+template <int DC, int DV, int NB, bool USLOT>
 LDPC_DEVINL void rc_check_row_f32(unsigned char *msgb, const int slot, const uint4 (&sw)[RC_NPRE], const uint4 *__restrict__ sched, const int M, const int j, float (&v)[DC],
                                   const bool normalized, const bool offset, const float inv_alpha, const float delta, const float alpha_div)
 {
@@ -123,7 +124,8 @@ LDPC_DEVINL void rc_check_row_f32(unsigned char *msgb, const int slot, const uin
         for (int q = 0; q < 4; q++) {
             const int k = g * 4 + q;
             uint32_t so;
-            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(so) : "r"((uint32_t)slot), "r"((uint32_t)-NB), "r"(off[q]));
+            if (USLOT) asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(so) : "r"((uint32_t)slot), "r"((uint32_t)-NB), "r"(off[q]));
+            else so = off[q] & (uint32_t)(NB - 1);
             v[k] = *reinterpret_cast<const float *>(msgb + DV * NB + so) - v[k];          // v2c = sum - c2v
         }
 #pragma unroll
@@ -170,7 +172,10 @@ LDPC_DEVINL void rc_check_row_f32(unsigned char *msgb, const int slot, const uin
     else second_pass(std::false_type(), std::false_type());
 }
 
-template <typename Real, int DC, int DV, int NFIX, int NT_MAX, int MINB>
+// USLOT: every edge of a row sits in the same slot of its variables' lists (row_slot; the redundant-row 802.3an H).  Without it
+// (the full-rank 802_3.alist: dv in {5, 6}, rows mix slots) the sum's address is the message offset modulo the plane size, and
+// the planes of slots a variable does not have stay zero from the kernel's start.
+template <typename Real, int DC, int DV, int NFIX, int NT_MAX, int MINB, bool USLOT = true>
 __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, const DecParams p, const FrameIO io)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -193,7 +198,8 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
     const uint32_t qflags = p.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES);
     const bool fcond = !io.y || io.y_dtype != LDPC_GPU_DT_F64;
     const bool has_row = tid < M;
-    const int slot = has_row ? (int)__ldg(&c.row_slot[tid]) : -1;
+    const int slot = (USLOT && has_row) ? (int)__ldg(&c.row_slot[tid]) : -1;
+    if (!USLOT) { for (int q = tid; q < DV * N; q += nt) msg[q] = (Real)0; __syncthreads(); }
 
     CtaTotals tot; tot.clear();
     // channel front end, software-pipelined across frames exactly as in ms_sched_kernel
@@ -289,8 +295,8 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
             if (last) for (int w = tid; w < nwords; w += nt) dbits[w] = 0u;
             // ---- check-node phase: one row per thread ------------------------------------------------
             if (has_row) {
-                if constexpr (sizeof(Real) == 4) rc_check_row_f32<DC, DV, NB>(msgb, slot, sw, c.sched, M, tid, v, normalized, offset, inv_alpha, delta, p.alpha_div_f);
-                else rc_check_row<Real, DC, DV, NB>(msgb, slot, c.sched, M, tid, v, normalized, offset, alpha, inv_alpha, delta);
+                if constexpr (sizeof(Real) == 4) rc_check_row_f32<DC, DV, NB, USLOT>(msgb, slot, sw, c.sched, M, tid, v, normalized, offset, inv_alpha, delta, p.alpha_div_f);
+                else rc_check_row<Real, DC, DV, NB, USLOT>(msgb, slot, c.sched, M, tid, v, normalized, offset, alpha, inv_alpha, delta);
             }
             // next frame's channel samples, one block per thread, right after the thread's row: the generator is a long
             // dependent chain on the FMA pipe and the check phase is issue / ALU bound, so the warps still in their rows

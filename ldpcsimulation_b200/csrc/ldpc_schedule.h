@@ -35,8 +35,8 @@ inline RowSchedule build_row_schedule(int N, int M, int dc, const std::vector<in
 {
     RowSchedule rs;
     const int B = 32;
-    if (N % B || M % B || dc < 1) return rs;
-    const int W = M / B, per_bank = N / B;
+    if (N % B || dc < 1) return rs;
+    const int W = (M + B - 1) / B, per_bank = N / B;              // the last warp may own fewer than 32 rows
     // ---- 1. balanced bank assignment -----------------------------------------------------------
     // edges of variable i as a list of warps (with multiplicity)
     std::vector<std::vector<int>> warps_of(N);
@@ -45,7 +45,9 @@ inline RowSchedule build_row_schedule(int N, int M, int dc, const std::vector<in
     for (int i = 0; i < N; i++) bank[i] = i % B;
     std::vector<int> load((size_t)W * B, 0);
     for (int i = 0; i < N; i++) for (int w : warps_of[i]) load[(size_t)w * B + bank[i]]++;
-    auto sq = [&](int v) { const long long d = v - dc; return d * d; };
+    // a warp's lane x bank multigraph splits into dc conflict-free steps iff no bank receives more than dc of its edges
+    // (Koenig: colours = maximum degree); for a full warp (32 dc edges) that means exactly dc per bank
+    auto sq = [&](int v) { const long long d = v > dc ? v - dc : 0; return d * d; };
     long long cost = 0;
     for (int v : load) cost += sq(v);
     std::mt19937 rng(seed);
@@ -70,7 +72,7 @@ inline RowSchedule build_row_schedule(int N, int M, int dc, const std::vector<in
         for (int w : warps_of[b]) { load[(size_t)w * B + bb]--; load[(size_t)w * B + ba]++; }
         bank[a] = bb; bank[b] = ba;
     };
-    if ((size_t)warps_of[0].size() > 15) return rs;               // scratch map above holds 4*dv entries
+    for (int i = 0; i < N; i++) if (warps_of[i].size() > 15) return rs;   // scratch map above holds 4*dv entries
     const long long max_tries = 40LL * 1000 * 1000;
     for (long long it = 0; it < max_tries && cost > 0; it++) {
         const int a = (int)(rng() % N), b = (int)(rng() % N);
@@ -92,9 +94,9 @@ inline RowSchedule build_row_schedule(int N, int M, int dc, const std::vector<in
     rs.order.assign((size_t)M * dc, -1);
     std::vector<int> lane_col((size_t)B * dc), bank_col((size_t)B * dc);   // [node][colour] -> edge id or -1
     for (int w = 0; w < W; w++) {
-        const int nE = B * dc;
+        const int rows = std::min(B, M - w * B), nE = rows * dc;
         std::vector<int> eu(nE), ev(nE), ecol(nE, -1);                      // edge e = lane*dc + k
-        for (int l = 0; l < B; l++) for (int k = 0; k < dc; k++) { eu[l * dc + k] = l; ev[l * dc + k] = bank[mlist[(size_t)(w * B + l) * dc + k]]; }
+        for (int l = 0; l < rows; l++) for (int k = 0; k < dc; k++) { eu[l * dc + k] = l; ev[l * dc + k] = bank[mlist[(size_t)(w * B + l) * dc + k]]; }
         std::fill(lane_col.begin(), lane_col.end(), -1); std::fill(bank_col.begin(), bank_col.end(), -1);
         for (int e = 0; e < nE; e++) {
             const int u = eu[e], v = ev[e];
@@ -123,12 +125,14 @@ inline RowSchedule build_row_schedule(int N, int M, int dc, const std::vector<in
         // verify: every step is a permutation of banks
         for (int t = 0; t < dc; t++) {
             unsigned seen = 0;
-            for (int l = 0; l < B; l++) {
+            for (int l = 0; l < rows; l++) {
                 const int k = rs.order[(size_t)(w * B + l) * dc + t];
                 if (k < 0) return rs;
-                seen |= 1u << bank[mlist[(size_t)(w * B + l) * dc + k]];
+                const unsigned bit = 1u << bank[mlist[(size_t)(w * B + l) * dc + k]];
+                if (seen & bit) return rs;
+                seen |= bit;
             }
-            if (seen != 0xffffffffu) return rs;
+            if (rows == B && seen != 0xffffffffu) return rs;
         }
     }
     rs.ok = true;
