@@ -421,12 +421,20 @@ def main():
         hw_noise.copy_(torch.randn((Fe, abi.HW_QBUF), generator=gen, device="cuda", dtype=torch.float64))
 
     def run_e2e(decoder, torch_dtype, abi_dtype, steps=e2e_steps):
-        y_host = torch.empty((Fe, NB), dtype=torch_dtype, pin_memory=True)
-        if abi_dtype == abi.DT_Q8:                                # the samples as a Q-bit converter delivers them: signed quantiser levels
+        Qb = W["q8"][1] if W["q8"] else 8
+        y_host = torch.empty((Fe, NB * Qb // 8) if abi_dtype == abi.DT_QP else (Fe, NB), dtype=torch_dtype, pin_memory=True)
+        if abi_dtype in (abi.DT_Q8, abi.DT_QP):                   # the samples as a Q-bit converter delivers them: signed quantiser levels
             Ymax, Nq = float(W["q8"][0]), 2.0 ** W["q8"][1]
             a = y_dev.abs().double()
             k = torch.where(a > Ymax, torch.full_like(a, 32.0), torch.clamp(torch.floor(a * (Nq - 1.0) / (2.0 * Ymax)), min=1.0))
-            y_host.copy_(torch.where(y_dev >= 0, k, -k).to(torch.int8))
+            if abi_dtype == abi.DT_Q8:
+                y_host.copy_(torch.where(y_dev >= 0, k, -k).to(torch.int8))
+            else:                                                 # Q bits per sample: sign | (magnitude level - 1), saturation = all ones
+                code = ((torch.clamp(k, max=2.0 ** (Qb - 1)) - 1).to(torch.uint8) | ((y_dev < 0).to(torch.uint8) << (Qb - 1)))
+                sh, w8 = torch.arange(Qb, device=code.device, dtype=torch.uint8), (1 << torch.arange(8, device=code.device)).to(torch.int32)
+                for f0 in range(0, Fe, 4096):                     # (bounded scratch: the bit tensor is 8 x the code tensor)
+                    bits = ((code[f0:f0 + 4096].unsqueeze(-1) >> sh) & 1).reshape(-1, NB * Qb // 8, 8).to(torch.int32)
+                    y_host[f0:f0 + 4096].copy_((bits * w8).sum(-1).to(torch.uint8))
         else:
             y_host.copy_(y_dev.to(torch_dtype))
         torch.cuda.synchronize()
@@ -453,10 +461,12 @@ def main():
         if W["q8"]:
             # headline e2e: the decoder quantises its samples to Q bits, so the host hands over what a Q-bit converter delivers, one byte per
             # sample (LDPC_GPU_DT_Q8; bit-identical to raw double samples: tests/test_gpu_parity.py::test_quantiser_level_input_equals_raw_sample_input)
-            v8, e2e_launches, ber8 = run_e2e(dec, torch.int8, abi.DT_Q8)
-            e2e = {"value": v8, "unit": "Gbit/s", "h2d_bytes_per_step": Fe * NB * 1, "d2h_bytes_per_step": Fe * ((NB + 7) // 8 + 4), "steps": e2e_steps,
-                   "api": "ldpc_gpu_decode_batch(mem=HOST, y_dtype=Q8): pinned %d-bit quantiser levels (one byte per sample) in, packed decisions + iteration counts out" % W["q8"][1],
-                   "decoded_ber": ber8}
+            vp, e2e_launches, berp = run_e2e(dec, torch.uint8, abi.DT_QP)
+            v8, _, ber8 = run_e2e(dec, torch.int8, abi.DT_Q8, steps=3)
+            e2e = {"value": vp, "unit": "Gbit/s", "h2d_bytes_per_step": Fe * NB * W["q8"][1] // 8, "d2h_bytes_per_step": Fe * ((NB + 7) // 8 + 4), "steps": e2e_steps,
+                   "api": "ldpc_gpu_decode_batch(mem=HOST, y_dtype=QP): pinned %d-bit quantiser levels, bit-packed (%d bits per sample), in; packed decisions + iteration counts out" % (W["q8"][1], W["q8"][1]),
+                   "decoded_ber": berp,
+                   "byte_levels": {"value": v8, "h2d_bytes_per_step": Fe * NB, "decoded_ber": ber8}}
         v64, l64, ber64 = run_e2e(dec, torch.float64, abi.DT_F64, steps=3)
         v32, _, ber32 = run_e2e(dec, torch.float32, abi.DT_F32, steps=3)
         v16, _, ber16 = run_e2e(dec, torch.float16, abi.DT_F16, steps=3)
@@ -481,7 +491,7 @@ def main():
             if prec2 == precision:
                 continue
             out, d2 = short_value(wl, prec2, frames)
-            ve, _, _ = run_e2e(d2, torch.int8, abi.DT_Q8, steps=3)
+            ve, _, _ = run_e2e(d2, torch.uint8, abi.DT_QP, steps=3)
             out["e2e"] = ve
             if prec2 == "x2":
                 out["exact_lattice_kernel"], out["redo_frames"] = d2.stats()

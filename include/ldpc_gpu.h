@@ -85,6 +85,11 @@ extern "C" {
                                    binary16 pair, v2c clamped to +-512.  NOT the reference's arithmetic: decisions
                                    match on converging frames, BER/FER within confidence intervals */
 
+#define LDPC_GPU_DT_QP   4   /* the same quantiser levels, bit-packed: Q bits per sample (Q = cfg.Q, 2 <= Q <= 8), sample i of a frame in bits
+                              * [iQ, (i+1)Q) of the frame's N*Q/8 bytes (little-endian bit order; N*Q must be a multiple of 32).  Code =
+                              * (negative << (Q-1)) | (min(k, 2^(Q-1)) - 1) with k the Q8 level magnitude (saturation = all ones).  A host that
+                              * streams samples to several GPUs is bound by its own memory bandwidth: 5 bits instead of 8 per sample. */
+
 /* ---- on-device noise generator (Philox4x32-10 keyed by (seed, frame id) either way) ---- */
 #define LDPC_GPU_CHANNEL_EXACT 0   /* Box-Muller in explicitly rounded fp32 polynomials: reproducible bit for bit on a CPU (oracle/) */
 #define LDPC_GPU_CHANNEL_FAST  1   /* Box-Muller on the SFU approximations (lg2 / sqrt / sin / cos .approx) and y = x fma(sigma, n, 1) in

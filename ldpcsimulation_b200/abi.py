@@ -36,7 +36,7 @@ MACRO_FLAGS = {
 PREC_F64, PREC_F32, PREC_F16X2 = 0, 1, 2
 CHANNEL_EXACT, CHANNEL_FAST = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
-DT_F64, DT_F32, DT_F16, DT_Q8 = 0, 1, 2, 3
+DT_F64, DT_F32, DT_F16, DT_Q8, DT_QP = 0, 1, 2, 3, 4
 HW_QBUF = 2648
 
 
@@ -138,3 +138,15 @@ def quantizer_levels(y, Ymax, Q):
     L = np.floor(a * (Nq - 1.0) / (2.0 * Ymax))
     k = np.where(a > Ymax, 32.0, np.maximum(1.0, L))
     return np.where(y >= 0, k, -k).astype(np.int8)
+
+
+def quantizer_levels_packed(y, Ymax, Q):
+    """LDPC_GPU_DT_QP encoding: quantizer_levels() packed Q bits per sample, [F][N*Q/8] bytes."""
+    import numpy as np
+    k = quantizer_levels(y, Ymax, Q).astype(np.int32)
+    F, N = k.shape
+    assert (N * Q) % 32 == 0
+    mag = np.minimum(np.abs(k), 2 ** (Q - 1)) - 1
+    code = (mag | ((k < 0).astype(np.int32) << (Q - 1))).astype(np.uint8)
+    bits = ((code[:, :, None] >> np.arange(Q)) & 1).astype(np.uint8).reshape(F, N * Q)
+    return np.packbits(bits, axis=1, bitorder="little")

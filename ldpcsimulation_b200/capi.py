@@ -172,7 +172,7 @@ class Decoder:
                want_soft=True, y_dtype=abi.DT_F64, outputs=True):
         """Host-memory parity entry.  y: [F][N] raw channel samples."""
         N = self.N
-        y = np.ascontiguousarray(y, dtype={abi.DT_F64: np.float64, abi.DT_F32: np.float32, abi.DT_F16: np.float16, abi.DT_Q8: np.int8}[y_dtype])
+        y = np.ascontiguousarray(y, dtype={abi.DT_F64: np.float64, abi.DT_F32: np.float32, abi.DT_F16: np.float16, abi.DT_Q8: np.int8, abi.DT_QP: np.uint8}[y_dtype])
         F = y.shape[0]
         out = Result(bits=np.zeros((F, (N + 7) // 8), np.uint8) if outputs else None,
                      iters=np.zeros(F, np.int32) if outputs else None,

@@ -110,12 +110,32 @@ LDPC_DEVINL float fast_channel_sample(const DecParams &p, const uint8_t *cw, int
     return (cw && i < N && cw[i]) ? -y : y;
 }
 
+// LDPC_GPU_DT_QP: the four Q-bit level codes of block b of frame f -> conditioned values (what quantize() makes of the samples)
+LDPC_DEVINL void packed_levels4(const FrameIO &io, const DecParams &p, const int N, const long long f, const int b, double y[4])
+{
+    const int Q = p.Q;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(io.y) + (size_t)f * (((size_t)N * Q) >> 5);   // N*Q is a multiple of 32
+    const uint32_t bit = (uint32_t)(4 * b * Q), wi = bit >> 5, sh = bit & 31u;
+    const uint32_t lo = __ldg(w + wi), hi = (sh + 4 * Q > 32) ? __ldg(w + wi + 1) : 0u;
+    const uint32_t v = __funnelshift_r(lo, hi, sh);
+    const uint32_t mmask = (1u << (Q - 1)) - 1u;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t code = (v >> (q * Q)) & ((1u << Q) - 1u);
+        const uint32_t mag = code & mmask;
+        const double a = (mag == mmask) ? p.Ymax : __dmul_rn((double)(mag + 1u), p.ms_step);
+        y[q] = (code >> (Q - 1)) ? -a : a;
+    }
+}
+
 // a2: four raw channel samples y = x(1 + sigma n) of block b (src/decodeMinSum.cpp:216), from the
 // caller's array or from the Philox channel.
 LDPC_DEVINL void raw_samples4(const FrameIO &io, const DecParams &p, const CodeDev &c, long long f, const uint8_t *cw, int b, double y[4])
 {
     const int i0 = 4 * b;
-    if (io.y) {
+    if (io.y && io.y_dtype == LDPC_GPU_DT_QP) {
+        packed_levels4(io, p, c.N, f, b, y);
+    } else if (io.y) {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int i = i0 + q;

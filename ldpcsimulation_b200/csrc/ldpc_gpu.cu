@@ -824,13 +824,16 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
     if (!d || !b) return set_err(LDPC_GPU_ERR_INVALID_ARG, "decoder or batch is NULL");
     if (b->n_frames < 0) return set_err(LDPC_GPU_ERR_INVALID_ARG, "n_frames < 0");
     if (b->n_frames > 0 && !b->y) return set_err(LDPC_GPU_ERR_INVALID_ARG, "batch.y is NULL");
-    if (b->y_dtype != LDPC_GPU_DT_F64 && b->y_dtype != LDPC_GPU_DT_F32 && b->y_dtype != LDPC_GPU_DT_F16 && b->y_dtype != LDPC_GPU_DT_Q8)
+    if (b->y_dtype != LDPC_GPU_DT_F64 && b->y_dtype != LDPC_GPU_DT_F32 && b->y_dtype != LDPC_GPU_DT_F16 && b->y_dtype != LDPC_GPU_DT_Q8 && b->y_dtype != LDPC_GPU_DT_QP)
         return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown y_dtype");
     const int N = d->N, kind = d->cfg.kind;
     if ((d->cfg.flags & LDPC_GPU_F_CERT_STOP) && b->out_soft)
         return set_err(LDPC_GPU_ERR_INVALID_ARG, "LDPC_GPU_F_CERT_STOP reports decisions, not the a-posteriori sums of iteration T: out_soft must be NULL");
     if (b->y_dtype == LDPC_GPU_DT_Q8 && !(kind == LDPC_GPU_KIND_MINSUM && (d->cfg.flags & LDPC_GPU_F_QUANTIZE_SAMPLES) && d->cfg.Q >= 2 && d->cfg.Q <= 6))
         return set_err(LDPC_GPU_ERR_INVALID_ARG, "LDPC_GPU_DT_Q8 carries quantiser levels: it needs a min-sum decoder with LDPC_GPU_F_QUANTIZE_SAMPLES and 2 <= Q <= 6");
+    if (b->y_dtype == LDPC_GPU_DT_QP && !(kind == LDPC_GPU_KIND_MINSUM && (d->cfg.flags & LDPC_GPU_F_QUANTIZE_SAMPLES) && d->cfg.Q >= 2 && d->cfg.Q <= 8 &&
+                                          ((long long)N * d->cfg.Q) % 32 == 0 && ((size_t)b->y & 3) == 0))
+        return set_err(LDPC_GPU_ERR_INVALID_ARG, "LDPC_GPU_DT_QP carries bit-packed quantiser levels: it needs a min-sum decoder with LDPC_GPU_F_QUANTIZE_SAMPLES, 2 <= Q <= 8, N*Q a multiple of 32 and a 4-byte aligned buffer");
     const int rps = rows_per_step(d->cfg.flags);
     if (kind == LDPC_GPU_KIND_GDBF && rps > 0) {
         const int ph = (d->cfg.flags & LDPC_GPU_F_REDECODE) ? std::max(1, d->cfg.maxphase) : 1;
@@ -843,13 +846,14 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
             if (b->qpointer0[f] < 0 || b->qpointer0[f] >= LDPC_GPU_HW_QBUF - N)
                 return set_err(LDPC_GPU_ERR_INVALID_ARG, "batch.qpointer0 outside [0, LDPC_GPU_HW_QBUF - N): the noise window wraps there (src/NGDBFhw.cpp:356-358)");
     DecParams p; int rc = channel_params(d, ch, p); if (rc) return rc;
-    if (b->y_dtype == LDPC_GPU_DT_Q8) p.flags &= ~(uint32_t)(LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES);   // the levels ARE the quantiser's output
+    if (b->y_dtype == LDPC_GPU_DT_Q8 || b->y_dtype == LDPC_GPU_DT_QP) p.flags &= ~(uint32_t)(LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES);   // the levels ARE the quantiser's output
     CU_TRY(cudaSetDevice(d->device));
     d->last_kernel_ms = 0; d->last_launches = 0;
     cudaStream_t st0 = d->slot[0].st;
     if (cnt) { if ((rc = zero_counters(d, st0))) return rc; CU_TRY(cudaStreamSynchronize(st0)); }
 
     const size_t esz = b->y_dtype == LDPC_GPU_DT_F64 ? 8 : b->y_dtype == LDPC_GPU_DT_F32 ? 4 : b->y_dtype == LDPC_GPU_DT_F16 ? 2 : 1, bpf = (size_t)(N + 7) / 8;
+    const size_t ybytes = b->y_dtype == LDPC_GPU_DT_QP ? ((size_t)N * d->cfg.Q) / 8 : esz * N;   // sample bytes per frame
     const size_t ssz = b->y_dtype == LDPC_GPU_DT_F64 ? 8 : 4;     // out_soft element size
     const size_t noise_pf = kind == LDPC_GPU_KIND_NGDBF_HW ? (size_t)LDPC_GPU_HW_QBUF : (kind == LDPC_GPU_KIND_GDBF && b->noise ? (size_t)b->noise_rows * N : 0);
     FrameIO io; memset(&io, 0, sizeof io);
@@ -867,7 +871,7 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
         if ((rc = redo_after_sync(d, p, io, st0, nullptr))) return rc;
     } else if (b->mem == LDPC_GPU_MEM_HOST) {
         // two-slot pipeline: H2D / kernel / D2H of consecutive chunks overlap on two streams
-        const size_t per_frame = esz * N + (b->out_soft ? ssz * N : 0) + 8 * noise_pf + (b->codeword ? N : 0) + bpf + 16;
+        const size_t per_frame = ybytes + (b->out_soft ? ssz * N : 0) + 8 * noise_pf + (b->codeword ? N : 0) + bpf + 16;
         // chunks small enough that the first H2D and the last D2H (the parts no kernel hides) are a few percent
         // of the batch, large enough to give every CTA tens of frames
         const char *cb = getenv("LDPC_GPU_CHUNK_MB");
@@ -902,8 +906,8 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
             Slot &s = d->slot[c & 1];
             if (s.used && (rc = drain(s))) return rc;     // this slot's previous chunk
             s.used = true; s.f0 = f0; s.nf = nf;
-            if ((rc = s.y.reserve(esz * N * nf))) return rc;
-            CU_TRY(cudaMemcpyAsync(s.y.p, (const char *)b->y + (size_t)f0 * N * esz, esz * N * nf, cudaMemcpyHostToDevice, s.st));
+            if ((rc = s.y.reserve(ybytes * nf))) return rc;
+            CU_TRY(cudaMemcpyAsync(s.y.p, (const char *)b->y + (size_t)f0 * ybytes, ybytes * nf, cudaMemcpyHostToDevice, s.st));
             io.y = s.y.p; io.n_frames = nf; io.frame_begin = f0;
             io.noise = nullptr; io.codeword = nullptr; io.qpointer0 = nullptr;
             if (b->noise && noise_pf) {

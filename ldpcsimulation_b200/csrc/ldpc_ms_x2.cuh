@@ -146,7 +146,7 @@ LDPC_DEVINL uint32_t x2_check_row(unsigned char *msgb, const int slot, const uin
 
 // Lean channel front ends of the min-sum family (fp32 conditioning): the sample source is a launch constant,
 // so each source gets its own straight-line code instead of raw_samples4's per-sample dispatch through doubles.
-enum { SRC_PHILOX = 0, SRC_PHILOX_FAST = 1, SRC_Q8 = 2, SRC_OTHER = 3 };
+enum { SRC_PHILOX = 0, SRC_PHILOX_FAST = 1, SRC_Q8 = 2, SRC_OTHER = 3, SRC_QP = 4 };
 
 template <int SRC, bool HASCW>
 LDPC_DEVINL void ms_cond4_f32(const FrameIO &io, const DecParams &p, const CodeDev &c, const long long f, const uint8_t *cw, const int b,
@@ -174,6 +174,11 @@ LDPC_DEVINL void ms_cond4_f32(const FrameIO &io, const DecParams &p, const CodeD
             const int k = (int)(signed char)((w >> (8 * q)) & 0xffu);
             vf[q] = (k >= 32) ? p.Ymax_f : (k <= -32) ? -p.Ymax_f : (float)__dmul_rn((double)k, p.ms_step);
         }
+    } else if (SRC == SRC_QP) {                                // bit-packed quantiser levels
+        double y4[4];
+        packed_levels4(io, p, c.N, f, b, y4);
+#pragma unroll
+        for (int q = 0; q < 4; q++) vf[q] = (float)y4[q];
     } else {
         double y4[4];
         raw_samples4(io, p, c, f, cw, b, y4);
@@ -194,6 +199,7 @@ LDPC_DEVINL int ms_sample_source(const FrameIO &io, const DecParams &p, const in
 {
     if (!io.y) return p.channel_mode == LDPC_GPU_CHANNEL_FAST ? SRC_PHILOX_FAST : SRC_PHILOX;
     if (io.y_dtype == LDPC_GPU_DT_Q8 && (N & 3) == 0 && ((size_t)io.y & 3) == 0) return SRC_Q8;
+    if (io.y_dtype == LDPC_GPU_DT_QP) return SRC_QP;
     return SRC_OTHER;
 }
 
@@ -275,6 +281,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
             case SRC_PHILOX:      gen_pair(std::integral_constant<int, SRC_PHILOX>(), std::true_type(), fa, fb, cwa, cwb); break;
             case SRC_PHILOX_FAST: gen_pair(std::integral_constant<int, SRC_PHILOX_FAST>(), std::true_type(), fa, fb, cwa, cwb); break;
             case SRC_Q8:          gen_pair(std::integral_constant<int, SRC_Q8>(), std::true_type(), fa, fb, cwa, cwb); break;
+            case SRC_QP:          gen_pair(std::integral_constant<int, SRC_QP>(), std::true_type(), fa, fb, cwa, cwb); break;
             default:              gen_pair(std::integral_constant<int, SRC_OTHER>(), std::true_type(), fa, fb, cwa, cwb); break;
             }
         } else {
@@ -282,6 +289,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
             case SRC_PHILOX:      gen_pair(std::integral_constant<int, SRC_PHILOX>(), std::false_type(), fa, fb, cwa, cwb); break;
             case SRC_PHILOX_FAST: gen_pair(std::integral_constant<int, SRC_PHILOX_FAST>(), std::false_type(), fa, fb, cwa, cwb); break;
             case SRC_Q8:          gen_pair(std::integral_constant<int, SRC_Q8>(), std::false_type(), fa, fb, cwa, cwb); break;
+            case SRC_QP:          gen_pair(std::integral_constant<int, SRC_QP>(), std::false_type(), fa, fb, cwa, cwb); break;
             default:              gen_pair(std::integral_constant<int, SRC_OTHER>(), std::false_type(), fa, fb, cwa, cwb); break;
             }
         }

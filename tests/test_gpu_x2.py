@@ -127,6 +127,25 @@ def test_x2_certified_stop_reports_the_same_results():
         capi.Decoder(capi.Code(code_path("802_3_H")), abi.default_cfg(abi.KIND_MINSUM, precision=abi.PREC_F32, **stop))
 
 
+@pytest.mark.parametrize("prec", [abi.PREC_F16X2, abi.PREC_F32, abi.PREC_F64])
+def test_bit_packed_levels_equal_byte_levels(prec):
+    """LDPC_GPU_DT_QP: the quantiser levels packed Q bits per sample decode exactly like the one-byte levels and the raw samples."""
+    orc = Oracle("802_3_H")
+    code = capi.Code(code_path("802_3_H"))
+    for kw, Ymax, Q in ((OMS, 1.9375, 5), (dict(flags=["quantizeSamples", "normalizedMS"], num_iterations=7, Ymax=2.0, Q=6, alpha=1.25), 2.0, 6)):
+        if prec == abi.PREC_F16X2 and Q == 6:
+            continue
+        cfg = abi.default_cfg(abi.KIND_MINSUM, precision=prec, **kw)
+        y, _, _, _ = cases.make_inputs(orc.N, cfg, 3.9, R, 333, 8)
+        y[0, :6] = [0.0, -0.0, 1e-9, Ymax, -Ymax * (1 + 1e-12), 5.0]
+        dec = capi.Decoder(code, cfg)
+        a = dec.decode(3.9, R, abi.quantizer_levels(y, Ymax, Q), y_dtype=abi.DT_Q8)
+        b = dec.decode(3.9, R, abi.quantizer_levels_packed(y, Ymax, Q), y_dtype=abi.DT_QP)
+        c = dec.decode(3.9, R, y)
+        assert np.array_equal(a.bits, b.bits) and np.array_equal(a.soft, b.soft) and a.counters == b.counters
+        assert np.array_equal(a.bits, c.bits) and a.counters == c.counters
+
+
 def test_non_lattice_configs_keep_the_labelled_kernel():
     d = _dec(dict(flags=["quantizeSamples", "normalizedMS"], num_iterations=10, Ymax=2.0, Q=6, alpha=1.25))
     assert not d.stats()[0]
