@@ -56,6 +56,14 @@ extern "C" {
 #define LDPC_GPU_KIND_GDBF      2   /* src/decodeGDBF.cpp, src/RNGDBF.cpp (LDPC_GPU_F_REDECODE) */
 #define LDPC_GPU_KIND_NGDBF_HW  3   /* src/NGDBFhw.cpp */
 #define LDPC_GPU_KIND_DDBMP     4   /* src/decodeDDBMP.cpp */
+#define LDPC_GPU_KIND_NGDBF_SC 5 /* NGDBF as the reference's SystemC model runs it (SystemC/NGDBF/inc/nodes.h:76-138,
+                                   inc/decoder.h:183-254): Nq = 2^Q level quantiser with end points, local
+                                   threshold adapted both ways (theta /= lambda on a flip, *= lambda otherwise), w = alpha*Ymax/dv,
+                                   one quantised Gaussian per clock shifted node to node, smoothing over the last `windowsize`
+                                   (32 in the model) iterations, one clock of pipeline delay.  Parameters: num_iterations, theta,
+                                   lambda, Ymax, Q (the model's `precision`), alpha, windowsize, noiseScale (1 in the model).
+                                   batch.noise: [F][noise_rows] raw N(0,1) values, noise_rows >= N + T + 1.  No runnable reference
+                                   (SystemC absent): parity unpinned, checked against the C restatement in oracle/. */
 
 /* ---- flag bits: one per reference -D macro (Makefile:24-71) ------------ */
 #define LDPC_GPU_F_QUANTIZE_SAMPLES       (1u << 0)   /* -D quantizeSamples  */
@@ -214,6 +222,9 @@ int  ldpc_gpu_code_create(int N, int M, int biggest_num_n, int biggest_num_m,
                           ldpc_gpu_code **out);
 /* Host alist parser (padded or unpadded rows, src/alist.cpp:22-95 semantics). */
 int  ldpc_gpu_code_load_alist(const char *path, ldpc_gpu_code **out);
+/* The SystemC trees store H transposed (first header number = checks; SystemC/NGDBF/src/ldpcsim.cpp:107-110 reads
+ * p.N = alist.M, p.M = alist.N and walks `mlist` per symbol): same parser, roles of the two lists swapped. */
+int  ldpc_gpu_code_load_alist_transposed(const char *path, ldpc_gpu_code **out);
 int  ldpc_gpu_code_dims(const ldpc_gpu_code *code, int *N, int *M, int *E, int *dv_max, int *dc_max);
 int  ldpc_gpu_code_destroy(ldpc_gpu_code *code);
 /* SURVEY.md 8(f) N1 -- codewords for codes that ship without a data.enc (the reference lists

@@ -4,7 +4,7 @@ import ctypes as C
 OK = 0
 ERR_INVALID_ARG, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_COMM, ERR_IO, ERR_BAD_CODE = -1, -2, -3, -4, -5, -6, -7
 
-KIND_MINSUM, KIND_BP, KIND_GDBF, KIND_NGDBF_HW, KIND_DDBMP = 0, 1, 2, 3, 4
+KIND_MINSUM, KIND_BP, KIND_GDBF, KIND_NGDBF_HW, KIND_DDBMP, KIND_NGDBF_SC = 0, 1, 2, 3, 4, 5
 
 F_QUANTIZE_SAMPLES = 1 << 0
 F_SATURATE_SAMPLES = 1 << 1
@@ -102,6 +102,8 @@ def default_cfg(kind, **kw):
         c.num_iterations, c.Ymax, c.noiseScale, c.maxphase, c.NQ = 600, 1.625, 0.95, 1, 5
     if kind == KIND_MINSUM:
         c.alpha = 1.25
+    if kind == KIND_NGDBF_SC:                    # SystemC/NGDBF/example.sh
+        c.num_iterations, c.theta, c.lambda_, c.Q, c.Ymax, c.alpha, c.windowsize, c.noiseScale = 100, -0.5, 0.975, 4, 3.0, 0.95, 32, 1.0
     for k, v in kw.items():
         if k == "lambda":
             k = "lambda_"
@@ -115,6 +117,11 @@ def default_cfg(kind, **kw):
 
 def gdbf_rows_per_step(flags):
     return (1 if flags & F_ADDNOISE else 0) + (1 if flags & F_QUANTIZEPROBABILITIES else 0)
+
+
+def sc_noise_len(cfg, N):
+    """Entries per frame of batch.noise for KIND_NGDBF_SC: the per-frame window of the node-to-node noise chain."""
+    return N + cfg.num_iterations + 1
 
 
 def noise_rows_needed(cfg):

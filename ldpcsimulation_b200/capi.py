@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("LDPC_GPU_LIB", os.path.join(HERE, "_build", "libldpc_
 # every symbol include/ldpc_gpu.h declares
 EXPORTS = [
     "ldpc_gpu_version", "ldpc_gpu_last_error", "ldpc_gpu_init", "ldpc_gpu_shutdown", "ldpc_gpu_device_count",
-    "ldpc_gpu_code_create", "ldpc_gpu_code_load_alist", "ldpc_gpu_code_dims", "ldpc_gpu_code_destroy",
+    "ldpc_gpu_code_create", "ldpc_gpu_code_load_alist", "ldpc_gpu_code_load_alist_transposed", "ldpc_gpu_code_dims", "ldpc_gpu_code_destroy",
     "ldpc_gpu_code_random_codewords",
     "ldpc_gpu_decoder_cfg_default", "ldpc_gpu_iter_hist_len", "ldpc_gpu_decoder_create", "ldpc_gpu_decoder_destroy",
     "ldpc_gpu_decoder_set_codewords", "ldpc_gpu_decode_batch", "ldpc_gpu_simulate", "ldpc_gpu_redecode_stats", "ldpc_gpu_replay_frame", "ldpc_gpu_channel_dump",
@@ -45,6 +45,7 @@ def lib():
         L.ldpc_gpu_last_error.restype = C.c_char_p
         L.ldpc_gpu_code_create.argtypes = [C.c_int] * 4 + [C.c_void_p] * 4 + [C.POINTER(C.c_void_p)]
         L.ldpc_gpu_code_load_alist.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.ldpc_gpu_code_load_alist_transposed.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.ldpc_gpu_code_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5
         L.ldpc_gpu_code_destroy.argtypes = [C.c_void_p]
         L.ldpc_gpu_code_random_codewords.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.POINTER(C.c_int)]
@@ -89,9 +90,11 @@ class Result(dict):
 class Code:
     """Parity-check matrix handle (reference: alist_struct, inc/alist.h:21-36)."""
 
-    def __init__(self, alist_path=None, arrays=None):
+    def __init__(self, alist_path=None, arrays=None, transposed=False):
         self.h = C.c_void_p()
-        if alist_path is not None:
+        if alist_path is not None and transposed:
+            check(lib().ldpc_gpu_code_load_alist_transposed(os.fsencode(alist_path), C.byref(self.h)))
+        elif alist_path is not None:
             check(lib().ldpc_gpu_code_load_alist(os.fsencode(alist_path), C.byref(self.h)))
         else:
             N, M, dv, dc, num_n, num_m, nl, ml = arrays
@@ -245,6 +248,9 @@ class Decoder:
         noise = None
         if self.cfg.kind == abi.KIND_NGDBF_HW:
             noise = np.zeros((n_frames, abi.HW_QBUF), np.float64)
+        elif self.cfg.kind == abi.KIND_NGDBF_SC:
+            noise_rows = abi.sc_noise_len(self.cfg, self.N)
+            noise = np.zeros((n_frames, noise_rows), np.float64)
         elif noise_rows:
             noise = np.zeros((n_frames, noise_rows, self.N), np.float64)
         check(lib().ldpc_gpu_channel_dump(self.h, C.byref(ch), seed, frame_begin, n_frames, _ptr(y), _ptr(noise), noise_rows))

@@ -28,6 +28,7 @@
 #include "ldpc_ms_h2rc.cuh"
 #include "ldpc_ms_x2.cuh"
 #include "ldpc_bf_kernels.cuh"
+#include "ldpc_sc_kernel.cuh"
 
 using namespace ldpc;
 
@@ -145,7 +146,7 @@ extern "C" int ldpc_gpu_code_create(int N, int M, int dvm, int dcm, const int *n
 // alist text: header, weights, N column rows, M row rows (src/alist.cpp:71-91).  Rows are read line
 // by line, so both the zero-padded layout the reference's default loader needs and the unpadded
 // layout of its -DCPPSTYLE branch (src/alist.cpp:26-62) are accepted.
-extern "C" int ldpc_gpu_code_load_alist(const char *path, ldpc_gpu_code **out)
+static int load_alist(const char *path, bool transposed, ldpc_gpu_code **out)
 {
     if (!out) return set_err(LDPC_GPU_ERR_INVALID_ARG, "out is NULL");
     *out = nullptr;
@@ -183,8 +184,12 @@ extern "C" int ldpc_gpu_code_load_alist(const char *path, ldpc_gpu_code **out)
         for (long v : rows[4 + N + j]) { if (v == 0) continue; if (cnt >= dcm) return set_err(LDPC_GPU_ERR_BAD_CODE, "row longer than biggest_num_m"); ml[(size_t)j * dcm + cnt++] = (int)v; }
         if (cnt != num_m[j]) return set_err(LDPC_GPU_ERR_BAD_CODE, "row weight does not match its entries");
     }
+    if (transposed)      // the file describes H^T: its "columns" are the checks (SystemC/NGDBF/src/ldpcsim.cpp:107-110)
+        return ldpc_gpu_code_create((int)M, (int)N, (int)dcm, (int)dvm, num_m.data(), num_n.data(), ml.data(), nl.data(), out);
     return ldpc_gpu_code_create((int)N, (int)M, (int)dvm, (int)dcm, num_n.data(), num_m.data(), nl.data(), ml.data(), out);
 }
+extern "C" int ldpc_gpu_code_load_alist(const char *path, ldpc_gpu_code **out) { return load_alist(path, false, out); }
+extern "C" int ldpc_gpu_code_load_alist_transposed(const char *path, ldpc_gpu_code **out) { return load_alist(path, true, out); }
 
 // GF(2) reduced row-echelon form of H, dense bit rows.
 static int build_encoder(ldpc_gpu_code *c)
@@ -336,6 +341,9 @@ extern "C" int ldpc_gpu_decoder_cfg_default(int kind, ldpc_gpu_decoder_cfg *c)
     c->w = 0.185; c->theta0 = -0.525; c->MAXLLR = 20;             // NGDBFhw.cpp:48-57, decodeBP.cpp:58
     if (kind == LDPC_GPU_KIND_NGDBF_HW) { c->num_iterations = 600; c->Ymax = 1.625; c->noiseScale = 0.95; c->maxphase = 1; c->NQ = 5; }
     if (kind == LDPC_GPU_KIND_MINSUM) c->alpha = 1.25;
+    if (kind == LDPC_GPU_KIND_NGDBF_SC) {                         // SystemC/NGDBF/example.sh
+        c->num_iterations = 100; c->theta = -0.5; c->lambda = 0.975; c->Q = 4; c->Ymax = 3.0; c->alpha = 0.95; c->windowsize = 32; c->noiseScale = 1.0;
+    }
     return LDPC_GPU_OK;
 }
 
@@ -541,6 +549,10 @@ static int pick_kernel(ldpc_gpu_decoder *d)
         smem = hw_smem_bytes(v);
         block = std::min(1024, std::max(128, round32(v.M)));                // measured: one check per thread, 3 CTAs/SM
         if (const char *hb = getenv("LDPC_GPU_HW_BLOCK")) block = std::max(64, atoi(hb) & ~31);
+    } else if (kind == LDPC_GPU_KIND_NGDBF_SC) {
+        d->fn = (KernelFn)sc_kernel;
+        smem = sc_smem_bytes(v, d->cfg.num_iterations, d->cfg.Q);
+        block = std::min(1024, std::max(128, round32(std::max(v.M, (v.N + 1) / 2))));
     } else return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown decoder kind");
 geometry:
     if (smem > (size_t)max_optin)
@@ -587,6 +599,11 @@ static int validate_cfg(const ldpc_gpu_decoder_cfg &c)
     if (c.kind == LDPC_GPU_KIND_NGDBF_HW) {
         if (c.num_iterations < 1 || c.w <= 0 || c.Ymax <= 0) return set_err(LDPC_GPU_ERR_INVALID_ARG, "NGDBFhw needs T >= 1, w > 0, Ymax > 0");
         if (c.maxphase > 15) return set_err(LDPC_GPU_ERR_INVALID_ARG, "maxphase must be <= 15");
+    }
+    if (c.kind == LDPC_GPU_KIND_NGDBF_SC) {
+        if (c.num_iterations < 1 || c.Q < 1 || c.Q > 8 || !(c.Ymax > 0) || !(c.lambda > 0) || c.windowsize < 0)
+            return set_err(LDPC_GPU_ERR_INVALID_ARG, "NGDBF_SC needs T >= 1, 1 <= Q <= 8, Ymax > 0, lambda > 0, windowsize >= 0");
+        if (c.precision != LDPC_GPU_PREC_F64) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "NGDBF_SC exists in the double arithmetic of the SystemC model only (LDPC_GPU_PREC_F64)");
     }
     if ((c.kind == LDPC_GPU_KIND_MINSUM && (c.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES))) || c.kind == LDPC_GPU_KIND_DDBMP)
         if (!(c.Ymax > 0) || (((c.flags & LDPC_GPU_F_QUANTIZE_SAMPLES) || c.kind == LDPC_GPU_KIND_DDBMP) && (c.Q < 1 || c.Q > 30)))
@@ -841,6 +858,8 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
         if (b->noise_rows < (int64_t)d->cfg.num_iterations * ph * rps) return set_err(LDPC_GPU_ERR_INVALID_ARG, "batch.noise_rows is smaller than T * phases * rows-per-step");
     }
     if (kind == LDPC_GPU_KIND_NGDBF_HW && !b->noise) return set_err(LDPC_GPU_ERR_INVALID_ARG, "NGDBFhw needs its per-frame noise buffer in batch.noise");
+    if (kind == LDPC_GPU_KIND_NGDBF_SC && (!b->noise || b->noise_rows < (int64_t)N + d->cfg.num_iterations + 1))
+        return set_err(LDPC_GPU_ERR_INVALID_ARG, "NGDBF_SC needs batch.noise = [F][noise_rows] normals with noise_rows >= N + T + 1 (the node-to-node noise chain)");
     if (kind == LDPC_GPU_KIND_NGDBF_HW && b->qpointer0 && b->mem == LDPC_GPU_MEM_HOST)
         for (int64_t f = 0; f < b->n_frames; f++)
             if (b->qpointer0[f] < 0 || b->qpointer0[f] >= LDPC_GPU_HW_QBUF - N)
@@ -855,7 +874,8 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
     const size_t esz = b->y_dtype == LDPC_GPU_DT_F64 ? 8 : b->y_dtype == LDPC_GPU_DT_F32 ? 4 : b->y_dtype == LDPC_GPU_DT_F16 ? 2 : 1, bpf = (size_t)(N + 7) / 8;
     const size_t ybytes = b->y_dtype == LDPC_GPU_DT_QP ? ((size_t)N * d->cfg.Q) / 8 : esz * N;   // sample bytes per frame
     const size_t ssz = b->y_dtype == LDPC_GPU_DT_F64 ? 8 : 4;     // out_soft element size
-    const size_t noise_pf = kind == LDPC_GPU_KIND_NGDBF_HW ? (size_t)LDPC_GPU_HW_QBUF : (kind == LDPC_GPU_KIND_GDBF && b->noise ? (size_t)b->noise_rows * N : 0);
+    const size_t noise_pf = kind == LDPC_GPU_KIND_NGDBF_HW ? (size_t)LDPC_GPU_HW_QBUF : kind == LDPC_GPU_KIND_NGDBF_SC ? (size_t)b->noise_rows
+                          : (kind == LDPC_GPU_KIND_GDBF && b->noise ? (size_t)b->noise_rows * N : 0);
     FrameIO io; memset(&io, 0, sizeof io);
     io.y_dtype = b->y_dtype; io.noise_rows = b->noise_rows;
     if (cnt) { io.counters = d->d_counters; io.ew_hist = d->d_ew; io.it_hist = d->d_it; io.ph_hist = d->d_ph; }
@@ -1006,8 +1026,8 @@ extern "C" int ldpc_gpu_redecode_stats(ldpc_gpu_decoder *d, const ldpc_gpu_chann
 {
     if (!d || !a || !outcomes) return set_err(LDPC_GPU_ERR_INVALID_ARG, "NULL argument");
     if (a->n_frames < 0 || n_redecodes < 1) return set_err(LDPC_GPU_ERR_INVALID_ARG, "n_frames < 0 or n_redecodes < 1");
-    if (d->cfg.kind != LDPC_GPU_KIND_GDBF && d->cfg.kind != LDPC_GPU_KIND_NGDBF_HW)
-        return set_err(LDPC_GPU_ERR_UNSUPPORTED, "re-decode statistics need a decoder with its own noise (GDBF family, NGDBFhw)");
+    if (d->cfg.kind != LDPC_GPU_KIND_GDBF && d->cfg.kind != LDPC_GPU_KIND_NGDBF_HW && d->cfg.kind != LDPC_GPU_KIND_NGDBF_SC)
+        return set_err(LDPC_GPU_ERR_UNSUPPORTED, "re-decode statistics need a decoder with its own noise (GDBF family, NGDBFhw, NGDBF_SC)");
     DecParams p; int rc = channel_params(d, ch, p); if (rc) return rc;
     CU_TRY(cudaSetDevice(d->device));
     cudaStream_t st = d->slot[0].st;
@@ -1060,6 +1080,8 @@ extern "C" int ldpc_gpu_replay_frame(ldpc_gpu_decoder *d, const ldpc_gpu_channel
                                      uint8_t *trace_d, uint8_t *trace_syn, int32_t *n_rows, int32_t *final_errors)
 {
     if (!d || !trace_d || !n_rows || max_rows < 0) return set_err(LDPC_GPU_ERR_INVALID_ARG, "bad argument");
+    if (d->cfg.kind == LDPC_GPU_KIND_NGDBF_SC)
+        return set_err(LDPC_GPU_ERR_UNSUPPORTED, "replay: the SystemC-model decoder's smoothing window is tied to T, a run with fewer iterations is not a prefix of the full run");
     DecParams p; int rc = channel_params(d, ch, p); if (rc) return rc;
     CU_TRY(cudaSetDevice(d->device));
     const int N = d->N, M = d->M, T = d->cfg.num_iterations;
@@ -1090,7 +1112,7 @@ extern "C" int ldpc_gpu_replay_frame(ldpc_gpu_decoder *d, const ldpc_gpu_channel
         rc = run(t, cur, &it, &err);
         if (rc) break;
         // bit-flipping decoders and DD-BMP stop early: a run that executed fewer than t steps adds no row
-        const bool early = (d->cfg.kind == LDPC_GPU_KIND_GDBF || d->cfg.kind == LDPC_GPU_KIND_NGDBF_HW) ? it < t
+        const bool early = (d->cfg.kind == LDPC_GPU_KIND_GDBF || d->cfg.kind == LDPC_GPU_KIND_NGDBF_HW || d->cfg.kind == LDPC_GPU_KIND_NGDBF_SC) ? it < t
                          : (d->cfg.kind == LDPC_GPU_KIND_DDBMP ? it < t - 1 : false);
         if (early) break;
         if (rows < max_rows) {
@@ -1135,6 +1157,11 @@ __global__ void dump_kernel(const CodeDev c, const DecParams p, const FrameIO io
                 float n4[4]; normal4(io.seed, fid, (uint32_t)b, (uint32_t)io.noise_row_base, STREAM_DECODER, n4);
                 for (int q = 0; q < 4; q++) if (4 * b + q < LDPC_GPU_HW_QBUF) io.dump_noise[(size_t)f * LDPC_GPU_HW_QBUF + 4 * b + q] = (double)n4[q];
             }
+        } else if (p.kind == LDPC_GPU_KIND_NGDBF_SC) {
+            for (int b = threadIdx.x; b < (int)((io.noise_rows + 3) / 4); b += blockDim.x) {
+                float n4[4]; normal4(io.seed, fid, (uint32_t)b, (uint32_t)io.noise_row_base, STREAM_DECODER, n4);
+                for (int q = 0; q < 4; q++) if (4 * b + q < io.noise_rows) io.dump_noise[(size_t)f * io.noise_rows + 4 * b + q] = (double)n4[q];
+            }
         } else if (p.kind == LDPC_GPU_KIND_GDBF && p.rows_per_step > 0) {
             for (long long row = 0; row < io.noise_rows; row++) {
                 const int which = (int)(row % p.rows_per_step);
@@ -1157,7 +1184,7 @@ extern "C" int ldpc_gpu_channel_dump(ldpc_gpu_decoder *d, const ldpc_gpu_channel
     DecParams p; int rc = channel_params(d, ch, p); if (rc) return rc;
     CU_TRY(cudaSetDevice(d->device));
     const int N = d->N;
-    const size_t npf = d->cfg.kind == LDPC_GPU_KIND_NGDBF_HW ? (size_t)LDPC_GPU_HW_QBUF : (size_t)noise_rows * N;
+    const size_t npf = d->cfg.kind == LDPC_GPU_KIND_NGDBF_HW ? (size_t)LDPC_GPU_HW_QBUF : d->cfg.kind == LDPC_GPU_KIND_NGDBF_SC ? (size_t)noise_rows : (size_t)noise_rows * N;
     DevBuf by, bn;
     if ((rc = by.reserve(8 * (size_t)N * n_frames))) return rc;
     if (noise && npf) if ((rc = bn.reserve(8 * npf * n_frames))) { by.release(); return rc; }

@@ -595,6 +595,70 @@ static int hw_frame(const oracle_code *H, const ldpc_gpu_decoder_cfg *cfg, doubl
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* LDPC_GPU_KIND_NGDBF_SC: restatement of the reference's SystemC NGDBF model              */
+/* (/root/reference/SystemC/NGDBF/inc/nodes.h:76-138,167-201; inc/decoder.h:183-254;       */
+/* inc/ldpcsim.h:85-119).  PARITY UNPINNED: SystemC is absent, the model cannot be run    */
+/* here; this restatement is the only checker of the GPU kernel.         */
+/* ------------------------------------------------------------------------------------ */
+static double sc_quantize(const double *thr, const double *val, int Nq, double Y)
+{   /* inc/ldpcsim.h:98-119 */
+    int k = 0;
+    for (int i = 0; i < Nq - 1; i++) if (Y > thr[i]) k = i + 1;
+    return val[k];
+}
+
+static int sc_frame(const oracle_code *H, const ldpc_gpu_decoder_cfg *cfg, double sigma, const double *y,
+                    const double *noise, int64_t nlen, workspace *w, frame_result *res)
+{
+    const int N = H->N, M = H->M, dvm = H->dv_max, dcm = H->dc_max, T = cfg->num_iterations, W = cfg->windowsize;
+    if (cfg->Q < 1 || cfg->Q > 8) return fail("NGDBF_SC: 1 <= Q <= 8");
+    if (!noise || nlen < (int64_t)N + T + 1) return fail("NGDBF_SC needs N + T + 1 noise values per frame");
+    const int Nq = 1 << cfg->Q;                                           /* src/ldpcsim.cpp:114 */
+    double thr[256], val[256];
+    for (int i = 0; i < Nq - 1; i++) {                                    /* inc/ldpcsim.h:85-96 */
+        thr[i] = -cfg->Ymax * (Nq - 2.0) / (Nq - 1.0) + i * (2.0 * cfg->Ymax / (Nq - 1.0));
+        val[i] = -cfg->Ymax + i * (2.0 * cfg->Ymax / (Nq - 1.0));
+    }
+    val[Nq - 1] = cfg->Ymax;
+    double *r = w->yq, *thl = w->theta;
+    double *q = (double *)malloc(sizeof(double) * (size_t)(N + T + 1));
+    int *updown = w->dsum, *x = w->d;
+    const double noiseSigma = sigma * cfg->noiseScale;
+    res->uncoded = 0;
+    for (int i = 0; i < N; i++) {                                         /* decoder.h:212, nodes.h:80-97 */
+        r[i] = sc_quantize(thr, val, Nq, y[i]);
+        x[i] = (r[i] > 0) ? 1 : -1;
+        thl[i] = cfg->theta; updown[i] = 0;
+        if (x[i] * w->c[i] < 0) res->uncoded++;
+    }
+    for (int k = 0; k < N + T + 1; k++) q[k] = sc_quantize(thr, val, Nq, noiseSigma * noise[k]);   /* decoder.h:187 */
+    int t, all_stop = 0;
+    for (t = 1; ; t++) {
+        all_stop = 1;                                                     /* nodes.h:167-201: products of the previous clock's messages */
+        for (int j = 0; j < M; j++) {
+            int prod = 1;
+            for (int k = 0; k < H->row_deg[j]; k++) prod *= x[H->mlist[(size_t)j * dcm + k]];
+            w->c2s[j] = prod;
+            if (prod != 1) all_stop = 0;
+        }
+        if (t > T - W) for (int i = 0; i < N; i++) updown[i] += x[i];    /* decoder.h:221-227 (1 - 2 Sd = x) */
+        if (all_stop || t > T) break;                                     /* :248-249 */
+        for (int i = 0; i < N; i++) {                                     /* nodes.h:104-137 */
+            const double wgt = cfg->alpha * cfg->Ymax / H->col_deg[i];    /* :59 */
+            double E = x[i] * r[i] + q[(N - 1 - i) + (t - 1)];            /* :107; the chain: node i reads what node i-1 read a clock earlier */
+            for (int s2 = 0; s2 < H->col_deg[i]; s2++) E += wgt * w->c2s[H->nlist[(size_t)i * dvm + s2]];   /* :113-114 */
+            if (E < sc_quantize(thr, val, Nq, thl[i])) { thl[i] = thl[i] / cfg->lambda; x[i] = -x[i]; }      /* :117-121 */
+            else thl[i] = thl[i] * cfg->lambda;                           /* :123-126 */
+        }
+    }
+    res->smoothed = (t >= T);                                             /* decoder.h:236-246 */
+    if (res->smoothed) for (int i = 0; i < N; i++) x[i] = (updown[i] > 0) ? 1 : -1;
+    res->it = t - 1; res->satisfied = all_stop; res->smoothing_used = res->smoothed; res->phases = 1;
+    free(q);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* Batch driver + a19 accounting (src/decodeMinSum.cpp:270-288 and siblings)             */
 /* ------------------------------------------------------------------------------------ */
 static int iter_hist_len(const ldpc_gpu_decoder_cfg *cfg)
@@ -634,6 +698,9 @@ int oracle_decode_batch(const oracle_code *H, const ldpc_gpu_decoder_cfg *cfg, c
         case LDPC_GPU_KIND_NGDBF_HW:
             rc = hw_frame(H, cfg, sigma, y, b->noise ? b->noise + (size_t)f * LDPC_GPU_HW_QBUF : NULL,
                           b->qpointer0 ? b->qpointer0[f] : 0, &w, &res, d01, c01);
+            break;
+        case LDPC_GPU_KIND_NGDBF_SC:
+            rc = sc_frame(H, cfg, sigma, y, b->noise ? b->noise + (size_t)f * b->noise_rows : NULL, b->noise_rows, &w, &res);
             break;
         default: rc = fail("unknown decoder kind");
         }
@@ -780,6 +847,12 @@ int oracle_channel_dump(const oracle_code *H, const ldpc_gpu_decoder_cfg *cfg, c
                 float n4[4]; oracle_normal4(seed, fid, (uint32_t)blk, 0, 1, n4);
                 for (int q = 0; q < 4 && blk * 4 + q < LDPC_GPU_HW_QBUF; q++) nf[blk * 4 + q] = (double)n4[q];
             }
+        } else if (cfg->kind == LDPC_GPU_KIND_NGDBF_SC) {
+            double *nf = noise + (size_t)f * noise_rows;
+            for (int blk = 0; blk * 4 < noise_rows; blk++) {
+                float n4[4]; oracle_normal4(seed, fid, (uint32_t)blk, 0, 1, n4);
+                for (int q = 0; q < 4 && blk * 4 + q < noise_rows; q++) nf[blk * 4 + q] = (double)n4[q];
+            }
         } else if (cfg->kind == LDPC_GPU_KIND_GDBF) {
             const int rps = gdbf_rows_per_step(cfg->flags);
             for (int64_t row = 0; row < noise_rows; row++) {
@@ -804,9 +877,9 @@ int oracle_simulate(const oracle_code *H, const ldpc_gpu_decoder_cfg *cfg, const
                     ldpc_gpu_counters *cnt)
 {
     const int N = H->N;
-    const int64_t rows = noise_rows_needed(cfg);
+    const int64_t rows = cfg->kind == LDPC_GPU_KIND_NGDBF_SC ? (int64_t)N + cfg->num_iterations + 1 : noise_rows_needed(cfg);
     double *y = (double *)malloc(sizeof(double) * N);
-    size_t nsz = cfg->kind == LDPC_GPU_KIND_NGDBF_HW ? LDPC_GPU_HW_QBUF : (size_t)rows * N;
+    size_t nsz = cfg->kind == LDPC_GPU_KIND_NGDBF_HW ? LDPC_GPU_HW_QBUF : cfg->kind == LDPC_GPU_KIND_NGDBF_SC ? (size_t)rows : (size_t)rows * N;
     double *noise = nsz ? (double *)malloc(sizeof(double) * nsz) : NULL;
     uint8_t *cw = (uint8_t *)calloc((size_t)N, 1);
     int rc = 0;

@@ -174,6 +174,9 @@ class Oracle:
         noise = None
         if cfg.kind == abi.KIND_NGDBF_HW:
             noise = np.zeros((n_frames, abi.HW_QBUF), np.float64)
+        elif cfg.kind == abi.KIND_NGDBF_SC:
+            noise_rows = abi.sc_noise_len(cfg, self.N)
+            noise = np.zeros((n_frames, noise_rows), np.float64)
         elif noise_rows:
             noise = np.zeros((n_frames, noise_rows, self.N), np.float64)
         ncw = 0 if codewords is None else len(codewords)
