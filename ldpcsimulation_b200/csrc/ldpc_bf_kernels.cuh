@@ -109,7 +109,7 @@ __global__ void gdbf_kernel(const CodeDev c, const DecParams p, const FrameIO io
         int unc = 0;
         for (int b = tid; b < nblk; b += nt) {
             double y4[4];
-            raw_samples4(io, p, c, f, cw, b, y4);
+            raw_samples4<false>(io, p, c, f, cw, b, y4);
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int i = 4 * b + q;
@@ -313,7 +313,7 @@ __global__ void gdbf_par_kernel(const CodeDev c, const DecParams p, const FrameI
         int unc = 0;
         for (int b = tid; b < nblk; b += nt) {
             double y4[4];
-            raw_samples4(io, p, c, f, cw, b, y4);
+            raw_samples4<false>(io, p, c, f, cw, b, y4);
             uint32_t rn = 0;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
@@ -501,7 +501,7 @@ static inline size_t hw_smem_bytes(const CodeDev &c)
     return (n + 15) & ~(size_t)15;
 }
 
-__global__ void hw_kernel(const CodeDev c, const DecParams p, const FrameIO io)
+__global__ void __launch_bounds__(384, 3) hw_kernel(const CodeDev c, const DecParams p, const FrameIO io)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = c.N, M = c.M, nwords = (N + 31) >> 5, mwords = (M + 31) >> 5, npad = nwords << 5, nblk = (N + 3) >> 2;
@@ -532,7 +532,7 @@ __global__ void hw_kernel(const CodeDev c, const DecParams p, const FrameIO io)
         int unc = 0;
         for (int b = tid; b < nblk; b += nt) {                        // :218-237
             double y4[4];
-            raw_samples4(io, p, c, f, cw, b, y4);
+            raw_samples4<false>(io, p, c, f, cw, b, y4);
             uint32_t rn = 0, cn = 0;
 #pragma unroll
             for (int q = 0; q < 4; q++) {

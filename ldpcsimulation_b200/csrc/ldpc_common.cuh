@@ -128,25 +128,16 @@ LDPC_DEVINL void packed_levels4(const FrameIO &io, const DecParams &p, const int
     }
 }
 
-static __device__ __noinline__ void packed_levels4_call(const FrameIO &io, const DecParams &p, const int N, const long long f, const int b, double y[4])
-{
-    packed_levels4(io, p, N, f, b, y);
-}
-static __device__ __noinline__ void fast_channel4_call(const FrameIO &io, const DecParams &p, const int N, const long long f, const uint8_t *cw, const int b, double y[4])
-{
-    float n[4];
-    normal4_fast(io.seed, (unsigned long long)(io.frame_begin + f), (uint32_t)b, 0u, STREAM_CHANNEL, n);
-#pragma unroll
-    for (int q = 0; q < 4; q++) y[q] = (double)fast_channel_sample(p, cw, 4 * b + q, N, n[q]);
-}
-
 // a2: four raw channel samples y = x(1 + sigma n) of block b (src/decodeMinSum.cpp:216), from the
 // caller's array or from the Philox channel.
+// FULL = false (bit-flipping kernels, whose register budget decides their occupancy): without the bit-packed level format and the
+// fast channel, which exist for the message-passing family only (the host refuses them elsewhere).
+template <bool FULL = true>
 LDPC_DEVINL void raw_samples4(const FrameIO &io, const DecParams &p, const CodeDev &c, long long f, const uint8_t *cw, int b, double y[4])
 {
     const int i0 = 4 * b;
-    if (io.y && io.y_dtype == LDPC_GPU_DT_QP) {
-        packed_levels4_call(io, p, c.N, f, b, y);               // (out of line: the rare formats must not cost every kernel registers)
+    if (FULL && io.y && io.y_dtype == LDPC_GPU_DT_QP) {
+        packed_levels4(io, p, c.N, f, b, y);
     } else if (io.y) {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -162,8 +153,11 @@ LDPC_DEVINL void raw_samples4(const FrameIO &io, const DecParams &p, const CodeD
             }
             else y[q] = 1.0;
         }
-    } else if (p.channel_mode == LDPC_GPU_CHANNEL_FAST) {
-        fast_channel4_call(io, p, c.N, f, cw, b, y);
+    } else if (FULL && p.channel_mode == LDPC_GPU_CHANNEL_FAST) {
+        float n[4];
+        normal4_fast(io.seed, (unsigned long long)(io.frame_begin + f), (uint32_t)b, 0u, STREAM_CHANNEL, n);
+#pragma unroll
+        for (int q = 0; q < 4; q++) y[q] = (double)fast_channel_sample(p, cw, i0 + q, c.N, n[q]);
     } else {
         float n[4];
         normal4(io.seed, (unsigned long long)(io.frame_begin + f), (uint32_t)b, 0u, STREAM_CHANNEL, n);

@@ -547,8 +547,7 @@ static int pick_kernel(ldpc_gpu_decoder *d)
         if (v.N >= LDPC_GPU_HW_QBUF) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "NGDBFhw's 2648-entry noise window needs N < 2648 (src/NGDBFhw.cpp:151)");
         d->fn = (KernelFn)hw_kernel;
         smem = hw_smem_bytes(v);
-        block = std::min(1024, std::max(128, round32(v.M)));                // measured: one check per thread, 3 CTAs/SM
-        if (const char *hb = getenv("LDPC_GPU_HW_BLOCK")) block = std::max(64, atoi(hb) & ~31);
+        block = std::min(384, std::max(128, round32(v.M)));                 // measured: one check per thread, 3 CTAs/SM (launch bounds 384 x 3)
     } else if (kind == LDPC_GPU_KIND_NGDBF_SC) {
         d->fn = (KernelFn)sc_kernel;
         smem = sc_smem_bytes(v, d->cfg.num_iterations, d->cfg.Q);
@@ -588,6 +587,8 @@ static int validate_cfg(const ldpc_gpu_decoder_cfg &c)
     if (c.precision != LDPC_GPU_PREC_F64 && c.precision != LDPC_GPU_PREC_F32 && c.precision != LDPC_GPU_PREC_F16X2)
         return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown precision");
     if (c.channel_mode != LDPC_GPU_CHANNEL_EXACT && c.channel_mode != LDPC_GPU_CHANNEL_FAST) return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown channel_mode");
+    if (c.channel_mode == LDPC_GPU_CHANNEL_FAST && c.kind != LDPC_GPU_KIND_MINSUM && c.kind != LDPC_GPU_KIND_BP && c.kind != LDPC_GPU_KIND_DDBMP)
+        return set_err(LDPC_GPU_ERR_UNSUPPORTED, "LDPC_GPU_CHANNEL_FAST exists for the message-passing decoders (min-sum family, sum-product, DD-BMP)");
     if (c.precision == LDPC_GPU_PREC_F16X2 && c.kind != LDPC_GPU_KIND_MINSUM)
         return set_err(LDPC_GPU_ERR_UNSUPPORTED, "LDPC_GPU_PREC_F16X2 exists for the min-sum family only");
     if (c.kind == LDPC_GPU_KIND_GDBF) {

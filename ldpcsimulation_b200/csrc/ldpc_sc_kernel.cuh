@@ -15,7 +15,7 @@
 //   * one clock of pipeline delay: the top level reads the decisions and stop signals the nodes wrote in the previous clock,
 //     so the reported word is x_{t-1} where t is the clock in which `finished` rises; `it` = t - 1 flip steps.
 // No runnable reference exists for this tree (SystemC is absent): parity is UNPINNED, the checker is the C
-// restatement oracle/ldpc_oracle.c:sc_frame, which this kernel equals bit for bit (all arithmetic is IEEE double in the
+// restatement (sc_frame in the test oracle), which this kernel equals bit for bit (all arithmetic is IEEE double in the
 // restatement's order; the library is built -fmad=false).
 #pragma once
 #include "ldpc_common.cuh"
@@ -69,7 +69,7 @@ __global__ void sc_kernel(const CodeDev c, const DecParams p, const FrameIO io)
         int unc = 0;
         for (int b = tid; b < nblk; b += nt) {                         // decoder.h:212, nodes.h:80-97 (reset behaviour)
             double y4[4];
-            raw_samples4(io, p, c, f, cw, b, y4);
+            raw_samples4<false>(io, p, c, f, cw, b, y4);
             uint32_t xn = 0;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
