@@ -509,6 +509,24 @@ def main():
             out, _ = short_value(name, WORKLOADS[name]["precision"], frames)
             out["workload"] = WORKLOADS[name]["text"]
             others[name] = out
+    if not args.no_extras:                                   # BASELINE configs[4]: non-binary GF(16) min-max, frames sharded like everything else
+        nbc = capi.NbCode(os.path.join(ROOT, "codes", "NB", "gf16.reg.1536.768.alist"))
+        nbd = capi.NbDecoder(nbc, 15, device=local)
+        Fn = 2960
+        nbd.simulate(3.5, 0.5, 1234, 0, 296)
+        barrier()
+        t3 = time.perf_counter()
+        begin, n = shard.step_range(0, rank, world, Fn)
+        rnb = nbd.simulate(3.5, 0.5, 1234, 10 ** 6 + begin, n)
+        barrier()
+        w3 = max_over_ranks(time.perf_counter() - t3)
+        others["nb_gf16_minmax"] = {"value": Fn * world * nbc.N * nbc.m / w3 / 1e9, "unit": "Gbit/s", "dtype": "f64", "frames_per_step_per_gpu": Fn, "steps": 1,
+                                    "kernel_ms_per_step": rnb.kernel_ms, "fer_this_rank": rnb.counters["wordErrors"] / max(1, rnb.counters["totalWords"]),
+                                    "ber_this_rank": rnb.counters["errors"] / max(1, rnb.counters["totalBits"]),
+                                    "avg_iterations": rnb.counters["totalIterations"] / max(1, rnb.counters["totalWords"]),
+                                    "workload": "BASELINE configs[4]: GF(16) regular (2,4) code of 1536 symbols (codes/NB/gf16.reg.1536.768.alist, generated: the reference ships "
+                                                "no GF(16) code), min-max decoding T<=15 with syndrome stop, Eb/N0=3.5 dB; parity unpinned (no runnable reference), "
+                                                "checked bit for bit against the C restatement of the published algorithm"}
     if world > 1:
         capi.lib().ldpc_gpu_comm_destroy()
         dist.destroy_process_group()

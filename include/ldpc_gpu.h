@@ -309,6 +309,29 @@ int  ldpc_gpu_comm_destroy(void);
  * error_weight_hist [N], iter_hist [ldpc_gpu_iter_hist_len(cfg)], phase_hist [max(1, cfg->maxphase)]. */
 int  ldpc_gpu_allreduce_counters(ldpc_gpu_counters *counters, int N, const ldpc_gpu_decoder_cfg *cfg);
 
+/* ---- non-binary GF(q) codes (BASELINE.json configs[4]) --------------------
+ * The reference's SystemC/NB-LDPC tree does not compile and decodes nothing (SURVEY.md "Read this first" 6): PARITY UNPINNED.
+ * Kept from it: the code format (SystemC/NB-LDPC/src/alist.cpp:23-56,97-124: header `N M q`, then the binary alist layout with
+ * every index followed by its GF value, `0 0` padding) and the symbol <-> bit mapping (bit b of the integer value, least
+ * significant first, inc/nodes.h:104-108).  The decoder is textbook min-max (csrc/ldpc_nb_kernel.cuh), q in {2, 4, 8, 16},
+ * GF(2^m) in the polynomial basis modulo x^2+x+1, x^3+x+1, x^4+x+1; stop at the first all-zero syndrome or after T iterations.
+ * Samples: y [F][N*m] doubles, bit b of symbol i at [i*m + b], BPSK bit 0 -> +1.  All-zero codeword in ldpc_gpu_nb_simulate
+ * (Philox channel keyed by (seed, frame id) as everywhere else).  Counters: errors = bit errors, smoothingUsed = symbol errors. */
+typedef struct ldpc_gpu_nb_code ldpc_gpu_nb_code;
+typedef struct ldpc_gpu_nb_decoder ldpc_gpu_nb_decoder;
+int  ldpc_gpu_nb_code_create(int N, int M, int q, int biggest_num_n, int biggest_num_m, const int *num_nlist, const int *num_mlist,
+                             const int *nlist_flat, const int *nvals_flat, const int *mlist_flat, const int *mvals_flat,
+                             ldpc_gpu_nb_code **out);
+int  ldpc_gpu_nb_code_load_alist(const char *path, ldpc_gpu_nb_code **out);
+int  ldpc_gpu_nb_code_dims(const ldpc_gpu_nb_code *code, int *N, int *M, int *q, int *E);
+int  ldpc_gpu_nb_code_destroy(ldpc_gpu_nb_code *code);
+int  ldpc_gpu_nb_decoder_create(const ldpc_gpu_nb_code *code, int num_iterations, int device, ldpc_gpu_nb_decoder **out);
+int  ldpc_gpu_nb_decoder_destroy(ldpc_gpu_nb_decoder *dec);
+int  ldpc_gpu_nb_decode_batch(ldpc_gpu_nb_decoder *dec, const ldpc_gpu_channel *ch, int64_t n_frames, const double *y,
+                              uint8_t *out_symbols, int32_t *out_iters, ldpc_gpu_counters *counters);
+int  ldpc_gpu_nb_simulate(ldpc_gpu_nb_decoder *dec, const ldpc_gpu_channel *ch, uint64_t seed, int64_t frame_begin, int64_t n_frames,
+                          ldpc_gpu_counters *counters, double *kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

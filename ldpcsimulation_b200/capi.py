@@ -23,6 +23,8 @@ EXPORTS = [
     "ldpc_gpu_decoder_set_codewords", "ldpc_gpu_decode_batch", "ldpc_gpu_simulate", "ldpc_gpu_redecode_stats", "ldpc_gpu_replay_frame", "ldpc_gpu_channel_dump",
     "ldpc_gpu_philox4x32", "ldpc_gpu_last_timing", "ldpc_gpu_decoder_stats", "ldpc_gpu_decoder_geometry",
     "ldpc_gpu_comm_unique_id", "ldpc_gpu_comm_init", "ldpc_gpu_comm_destroy", "ldpc_gpu_allreduce_counters",
+    "ldpc_gpu_nb_code_create", "ldpc_gpu_nb_code_load_alist", "ldpc_gpu_nb_code_dims", "ldpc_gpu_nb_code_destroy",
+    "ldpc_gpu_nb_decoder_create", "ldpc_gpu_nb_decoder_destroy", "ldpc_gpu_nb_decode_batch", "ldpc_gpu_nb_simulate",
 ]
 
 
@@ -70,6 +72,13 @@ def lib():
         L.ldpc_gpu_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.ldpc_gpu_allreduce_counters.argtypes = [C.POINTER(abi.Counters), C.c_int, C.POINTER(abi.DecoderCfg)]
         L.ldpc_gpu_iter_hist_len.argtypes = [C.POINTER(abi.DecoderCfg)]
+        L.ldpc_gpu_nb_code_load_alist.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.ldpc_gpu_nb_code_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+        L.ldpc_gpu_nb_code_destroy.argtypes = [C.c_void_p]
+        L.ldpc_gpu_nb_decoder_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.ldpc_gpu_nb_decoder_destroy.argtypes = [C.c_void_p]
+        L.ldpc_gpu_nb_decode_batch.argtypes = [C.c_void_p, C.POINTER(abi.Channel), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(abi.Counters)]
+        L.ldpc_gpu_nb_simulate.argtypes = [C.c_void_p, C.POINTER(abi.Channel), C.c_uint64, C.c_int64, C.c_int64, C.POINTER(abi.Counters), C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -255,6 +264,57 @@ class Decoder:
             noise = np.zeros((n_frames, noise_rows, self.N), np.float64)
         check(lib().ldpc_gpu_channel_dump(self.h, C.byref(ch), seed, frame_begin, n_frames, _ptr(y), _ptr(noise), noise_rows))
         return y, noise
+
+
+class NbCode:
+    """Non-binary GF(q) parity-check matrix (format of SystemC/NB-LDPC/src/alist.cpp:23-56)."""
+
+    def __init__(self, alist_path):
+        self.h = C.c_void_p()
+        check(lib().ldpc_gpu_nb_code_load_alist(os.fsencode(alist_path), C.byref(self.h)))
+        v = [C.c_int() for _ in range(4)]
+        check(lib().ldpc_gpu_nb_code_dims(self.h, *[C.byref(x) for x in v]))
+        self.N, self.M, self.q, self.E = [x.value for x in v]
+        self.m = self.q.bit_length() - 1
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().ldpc_gpu_nb_code_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class NbDecoder:
+    """Min-max decoder of a non-binary code on one GPU (csrc/ldpc_nb_kernel.cuh)."""
+
+    def __init__(self, code, num_iterations, device=0):
+        self.code, self.T = code, num_iterations
+        self.h = C.c_void_p()
+        check(lib().ldpc_gpu_nb_decoder_create(code.h, num_iterations, device, C.byref(self.h)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().ldpc_gpu_nb_decoder_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def decode(self, snr_db, R, y):
+        """y: [F][N*m] bit samples.  Returns symbols [F][N], iterations [F], counters."""
+        y = np.ascontiguousarray(y, np.float64)
+        F = y.shape[0]
+        sym, it = np.zeros((F, self.code.N), np.uint8), np.zeros(F, np.int32)
+        cnt, ch = abi.Counters(), abi.Channel(snr_db, R)
+        check(lib().ldpc_gpu_nb_decode_batch(self.h, C.byref(ch), F, _ptr(y), _ptr(sym), _ptr(it), C.byref(cnt)))
+        return Result(symbols=sym, iters=it, counters=cnt.as_dict())
+
+    def simulate(self, snr_db, R, seed, frame_begin, n_frames):
+        cnt, ch, ms = abi.Counters(), abi.Channel(snr_db, R), C.c_double()
+        check(lib().ldpc_gpu_nb_simulate(self.h, C.byref(ch), seed, frame_begin, n_frames, C.byref(cnt), C.byref(ms)))
+        return Result(counters=cnt.as_dict(), kernel_ms=ms.value)
 
 
 def philox4x32(ctr, key):

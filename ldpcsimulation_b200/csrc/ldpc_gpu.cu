@@ -29,6 +29,7 @@
 #include "ldpc_ms_x2.cuh"
 #include "ldpc_bf_kernels.cuh"
 #include "ldpc_sc_kernel.cuh"
+#include "ldpc_nb_kernel.cuh"
 
 using namespace ldpc;
 
@@ -1312,4 +1313,230 @@ extern "C" int ldpc_gpu_allreduce_counters(ldpc_gpu_counters *c, int N, const ld
     if (n_it) { memcpy(c->iter_hist, q, 8 * n_it); q += n_it; }
     if (n_ph) { memcpy(c->phase_hist, q, 8 * n_ph); q += n_ph; }
     return LDPC_GPU_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// non-binary GF(q) codes, min-max decoding (csrc/ldpc_nb_kernel.cuh).  Parity unpinned.
+// ------------------------------------------------------------------------------------------------
+struct ldpc_gpu_nb_code {
+    int N = 0, M = 0, q = 0, m = 0, E = 0, dv_max = 0, dc_max = 0;
+    std::vector<int> col_deg, row_deg, nlist, mlist;      // 0-based, -1 padded
+    std::vector<uint8_t> mvals;                           // [M*dc_max] h_jk
+    std::vector<uint8_t> mul, inv;
+};
+
+static int gf_tables(int q, std::vector<uint8_t> &mul, std::vector<uint8_t> &inv)
+{
+    int m = 0; while ((1 << m) < q) m++;
+    if ((1 << m) != q || m < 1 || m > 6) return -1;
+    static const int prim[7] = { 0, 0x3, 0x7, 0xB, 0x13, 0x25, 0x43 };        // x+1, x^2+x+1, x^3+x+1, x^4+x+1, x^5+x^2+1, x^6+x+1
+    mul.assign((size_t)q * q, 0); inv.assign(q, 0);
+    for (int a = 0; a < q; a++) for (int b = 0; b < q; b++) {
+        int r = 0, aa = a;
+        for (int k = 0; k < m; k++) { if ((b >> k) & 1) r ^= aa; aa <<= 1; if (aa & q) aa ^= prim[m]; }
+        mul[(size_t)a * q + b] = (uint8_t)r;
+    }
+    for (int a = 1; a < q; a++) for (int b = 1; b < q; b++) if (mul[(size_t)a * q + b] == 1) inv[a] = (uint8_t)b;
+    return m;
+}
+
+extern "C" int ldpc_gpu_nb_code_create(int N, int M, int q, int dvm, int dcm, const int *num_nlist, const int *num_mlist,
+                                       const int *nlist_flat, const int *nvals_flat, const int *mlist_flat, const int *mvals_flat,
+                                       ldpc_gpu_nb_code **out)
+{
+    if (!out) return set_err(LDPC_GPU_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (N <= 0 || M <= 0 || dvm <= 0 || dcm <= 0 || !num_nlist || !num_mlist || !nlist_flat || !mlist_flat || !mvals_flat)
+        return set_err(LDPC_GPU_ERR_INVALID_ARG, "bad dimensions or NULL array");
+    if (dcm > 8 || dvm > 16) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "non-binary decoder: dc_max <= 8, dv_max <= 16");
+    std::unique_ptr<ldpc_gpu_nb_code> c(new ldpc_gpu_nb_code);
+    c->m = gf_tables(q, c->mul, c->inv);
+    if (c->m < 0) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "non-binary decoder: q must be 2, 4, 8, 16, 32 or 64");
+    c->N = N; c->M = M; c->q = q; c->dv_max = dvm; c->dc_max = dcm;
+    c->col_deg.assign(num_nlist, num_nlist + N); c->row_deg.assign(num_mlist, num_mlist + M);
+    c->nlist.assign((size_t)N * dvm, -1); c->mlist.assign((size_t)M * dcm, -1); c->mvals.assign((size_t)M * dcm, 0);
+    long long En = 0, Em = 0;
+    for (int j = 0; j < M; j++) {
+        if (num_mlist[j] < 2 || num_mlist[j] > dcm) return set_err(LDPC_GPU_ERR_BAD_CODE, "row weight outside [2, biggest_num_m]");
+        Em += num_mlist[j];
+        for (int k = 0; k < num_mlist[j]; k++) {
+            const int v = mlist_flat[(size_t)j * dcm + k] - 1, h = mvals_flat[(size_t)j * dcm + k];
+            if (v < 0 || v >= N || h <= 0 || h >= q) return set_err(LDPC_GPU_ERR_BAD_CODE, "mlist entry or GF value out of range");
+            c->mlist[(size_t)j * dcm + k] = v; c->mvals[(size_t)j * dcm + k] = (uint8_t)h;
+        }
+    }
+    for (int i = 0; i < N; i++) {
+        if (num_nlist[i] < 0 || num_nlist[i] > dvm) return set_err(LDPC_GPU_ERR_BAD_CODE, "column weight exceeds biggest_num_n");
+        En += num_nlist[i];
+        for (int s2 = 0; s2 < num_nlist[i]; s2++) {
+            const int j = nlist_flat[(size_t)i * dvm + s2] - 1;
+            if (j < 0 || j >= M) return set_err(LDPC_GPU_ERR_BAD_CODE, "nlist entry out of range");
+            c->nlist[(size_t)i * dvm + s2] = j;
+            int found = -1;                                   // the two lists must describe the same matrix, values included
+            for (int k = 0; k < c->row_deg[j]; k++) if (c->mlist[(size_t)j * dcm + k] == i) found = k;
+            if (found < 0) return set_err(LDPC_GPU_ERR_BAD_CODE, "nlist is not the transpose of mlist");
+            if (nvals_flat && nvals_flat[(size_t)i * dvm + s2] != c->mvals[(size_t)j * dcm + found]) return set_err(LDPC_GPU_ERR_BAD_CODE, "nlist and mlist disagree on a GF value");
+        }
+    }
+    if (En != Em) return set_err(LDPC_GPU_ERR_BAD_CODE, "nlist and mlist hold different numbers of edges");
+    c->E = (int)Em;
+    *out = c.release();
+    return LDPC_GPU_OK;
+}
+
+// header `N M q`, then the binary layout with every index followed by its GF value, `0 0` padding
+// (/root/reference/SystemC/NB-LDPC/src/alist.cpp:23-56,97-124)
+extern "C" int ldpc_gpu_nb_code_load_alist(const char *path, ldpc_gpu_nb_code **out)
+{
+    if (!out || !path) return set_err(LDPC_GPU_ERR_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    std::ifstream f(path);
+    if (!f) return set_err(LDPC_GPU_ERR_IO, std::string("cannot open ") + path);
+    std::vector<long> t; long x;
+    while (f >> x) t.push_back(x);
+    if (t.size() < 5) return set_err(LDPC_GPU_ERR_BAD_CODE, "bad non-binary alist header");
+    const long N = t[0], M = t[1], q = t[2], dvm = t[3], dcm = t[4];
+    if (N <= 0 || M <= 0 || dvm <= 0 || dcm <= 0 || N > (1 << 24) || M > (1 << 24)) return set_err(LDPC_GPU_ERR_BAD_CODE, "bad non-binary alist dimensions");
+    const size_t need = 5 + (size_t)N + M + 2 * ((size_t)N * dvm + (size_t)M * dcm);
+    if (t.size() != need) return set_err(LDPC_GPU_ERR_BAD_CODE, "non-binary alist: token count does not match its header (rows must be padded with `0 0`)");
+    std::vector<int> nn(N), nm(M), nl((size_t)N * dvm), nv((size_t)N * dvm), ml((size_t)M * dcm), mv((size_t)M * dcm);
+    size_t p = 5;
+    for (long i = 0; i < N; i++) nn[i] = (int)t[p++];
+    for (long j = 0; j < M; j++) nm[j] = (int)t[p++];
+    for (size_t e = 0; e < (size_t)N * dvm; e++) { nl[e] = (int)t[p++]; nv[e] = (int)t[p++]; }
+    for (size_t e = 0; e < (size_t)M * dcm; e++) { ml[e] = (int)t[p++]; mv[e] = (int)t[p++]; }
+    return ldpc_gpu_nb_code_create((int)N, (int)M, (int)q, (int)dvm, (int)dcm, nn.data(), nm.data(), nl.data(), nv.data(), ml.data(), mv.data(), out);
+}
+extern "C" int ldpc_gpu_nb_code_dims(const ldpc_gpu_nb_code *c, int *N, int *M, int *q, int *E)
+{
+    if (!c) return set_err(LDPC_GPU_ERR_INVALID_ARG, "code is NULL");
+    if (N) *N = c->N; if (M) *M = c->M; if (q) *q = c->q; if (E) *E = c->E;
+    return LDPC_GPU_OK;
+}
+extern "C" int ldpc_gpu_nb_code_destroy(ldpc_gpu_nb_code *c) { delete c; return LDPC_GPU_OK; }
+
+struct ldpc_gpu_nb_decoder {
+    int device = 0, T = 0, grid = 0, block = 256;
+    NbCodeDev dev; std::vector<void *> owned;
+    double *d_ws = nullptr; size_t ws_stride = 0;
+    unsigned long long *d_counters = nullptr;
+    cudaStream_t st = nullptr; cudaEvent_t k0 = nullptr, k1 = nullptr;
+    double last_ms = 0;
+};
+typedef void (*NbKernelFn)(const NbCodeDev, const NbIO);
+
+extern "C" int ldpc_gpu_nb_decoder_destroy(ldpc_gpu_nb_decoder *d)
+{
+    if (!d) return LDPC_GPU_OK;
+    cudaSetDevice(d->device);
+    for (void *p : d->owned) cudaFree(p);
+    if (d->d_ws) cudaFree(d->d_ws);
+    if (d->d_counters) cudaFree(d->d_counters);
+    if (d->k0) cudaEventDestroy(d->k0); if (d->k1) cudaEventDestroy(d->k1);
+    if (d->st) cudaStreamDestroy(d->st);
+    delete d;
+    return LDPC_GPU_OK;
+}
+
+extern "C" int ldpc_gpu_nb_decoder_create(const ldpc_gpu_nb_code *c, int num_iterations, int device, ldpc_gpu_nb_decoder **out)
+{
+    if (!out) return set_err(LDPC_GPU_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (!c || num_iterations < 0) return set_err(LDPC_GPU_ERR_INVALID_ARG, "code is NULL or num_iterations < 0");
+    if (c->q > 16) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "non-binary kernel instantiations: q = 2, 4, 8, 16");
+    if (ldpc_gpu_device_count() <= 0) return set_err(LDPC_GPU_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    CU_TRY(cudaSetDevice(device));
+    ldpc_gpu_nb_decoder *d = new ldpc_gpu_nb_decoder;
+    d->device = device; d->T = num_iterations;
+    auto up = [&](const void *h, size_t n, const void **p) -> int {
+        void *q2 = nullptr;
+        if (cudaMalloc(&q2, std::max<size_t>(16, n)) != cudaSuccess) return set_err(LDPC_GPU_ERR_NOMEM, "cudaMalloc failed");
+        d->owned.push_back(q2);
+        if (cudaMemcpy(q2, h, n, cudaMemcpyHostToDevice) != cudaSuccess) return set_err(LDPC_GPU_ERR_CUDA, "cudaMemcpy failed");
+        *p = q2; return LDPC_GPU_OK;
+    };
+    const int N = c->N, M = c->M, dvm = c->dv_max, dcm = c->dc_max;
+    std::vector<int32_t> vn_edge((size_t)N * dvm, -1);
+    std::vector<uint8_t> cdeg(M), vdeg(N);
+    for (int j = 0; j < M; j++) cdeg[j] = (uint8_t)c->row_deg[j];
+    for (int i = 0; i < N; i++) {
+        vdeg[i] = (uint8_t)c->col_deg[i];
+        for (int s2 = 0; s2 < c->col_deg[i]; s2++) {
+            const int j = c->nlist[(size_t)i * dvm + s2];
+            for (int k = 0; k < c->row_deg[j]; k++) if (c->mlist[(size_t)j * dcm + k] == i) vn_edge[(size_t)i * dvm + s2] = j * dcm + k;
+        }
+    }
+    NbCodeDev &v = d->dev;
+    v.N = N; v.M = M; v.q = c->q; v.m = c->m; v.E = c->E; v.dv_max = dvm; v.dc_max = dcm;
+    int rc;
+    if ((rc = up(c->mlist.data(), c->mlist.size() * 4, (const void **)&v.cn_var)) || (rc = up(c->mvals.data(), c->mvals.size(), (const void **)&v.cn_val)) ||
+        (rc = up(cdeg.data(), cdeg.size(), (const void **)&v.cn_deg)) || (rc = up(vn_edge.data(), vn_edge.size() * 4, (const void **)&v.vn_edge)) ||
+        (rc = up(vdeg.data(), vdeg.size(), (const void **)&v.vn_deg)) || (rc = up(c->mul.data(), c->mul.size(), (const void **)&v.mul)) ||
+        (rc = up(c->inv.data(), c->inv.size(), (const void **)&v.inv))) { ldpc_gpu_nb_decoder_destroy(d); return rc; }
+    int n_sm = 0; cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    d->grid = 2 * n_sm;
+    d->ws_stride = ((2 * (size_t)M * dcm + (size_t)N) * c->q + ((size_t)N + 7) / 8 + 31) & ~(size_t)31;        // doubles
+    if (cudaMalloc(&d->d_ws, d->ws_stride * sizeof(double) * d->grid) != cudaSuccess || cudaMalloc(&d->d_counters, sizeof(unsigned long long) * CNT_N) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&d->st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&d->k0) != cudaSuccess || cudaEventCreate(&d->k1) != cudaSuccess) {
+        ldpc_gpu_nb_decoder_destroy(d); return set_err(LDPC_GPU_ERR_NOMEM, "non-binary decoder: allocation failed");
+    }
+    *out = d;
+    return LDPC_GPU_OK;
+}
+
+static int nb_run(ldpc_gpu_nb_decoder *d, const ldpc_gpu_channel *ch, NbIO io, ldpc_gpu_counters *cnt)
+{
+    if (!ch || !(ch->R > 0)) return set_err(LDPC_GPU_ERR_INVALID_ARG, "channel needs R > 0");
+    io.sigma = sqrt(pow(10.0, -ch->snr_db / 10.0) / ch->R / 2.0);
+    io.T = d->T; io.workspace = d->d_ws; io.ws_stride = d->ws_stride; io.counters = cnt ? d->d_counters : nullptr;
+    if (cnt) CU_TRY(cudaMemsetAsync(d->d_counters, 0, sizeof(unsigned long long) * CNT_N, d->st));
+    const NbKernelFn fn = d->dev.q == 2 ? (NbKernelFn)nb_minmax_kernel<2> : d->dev.q == 4 ? (NbKernelFn)nb_minmax_kernel<4>
+                        : d->dev.q == 8 ? (NbKernelFn)nb_minmax_kernel<8> : (NbKernelFn)nb_minmax_kernel<16>;
+    const long long want = std::min<long long>(io.n_frames, d->grid);
+    CU_TRY(cudaEventRecord(d->k0, d->st));
+    if (want > 0) { fn<<<(unsigned)want, d->block, 0, d->st>>>(d->dev, io); CU_TRY(cudaGetLastError()); }
+    CU_TRY(cudaEventRecord(d->k1, d->st));
+    if (cnt) {
+        unsigned long long h[CNT_N];
+        CU_TRY(cudaMemcpyAsync(h, d->d_counters, sizeof h, cudaMemcpyDeviceToHost, d->st));
+        CU_TRY(cudaStreamSynchronize(d->st));
+        cnt->errors += (int64_t)h[CNT_ERRORS]; cnt->totalBits += (int64_t)h[CNT_BITS]; cnt->totalWords += (int64_t)h[CNT_WORDS];
+        cnt->wordErrors += (int64_t)h[CNT_WORDERRS]; cnt->totalIterations += (int64_t)h[CNT_ITERS]; cnt->undetectedWords += (int64_t)h[CNT_UNDETECTED];
+        cnt->smoothingUsed += (int64_t)h[CNT_SMOOTH];
+    } else CU_TRY(cudaStreamSynchronize(d->st));
+    float ms = 0; cudaEventElapsedTime(&ms, d->k0, d->k1); d->last_ms = ms;
+    return LDPC_GPU_OK;
+}
+
+extern "C" int ldpc_gpu_nb_decode_batch(ldpc_gpu_nb_decoder *d, const ldpc_gpu_channel *ch, int64_t n_frames, const double *y,
+                                        uint8_t *out_symbols, int32_t *out_iters, ldpc_gpu_counters *cnt)
+{
+    if (!d || n_frames < 0 || (n_frames > 0 && !y)) return set_err(LDPC_GPU_ERR_INVALID_ARG, "bad argument");
+    CU_TRY(cudaSetDevice(d->device));
+    const size_t ny = (size_t)n_frames * d->dev.N * d->dev.m;
+    DevBuf by, bs, bi;
+    int rc;
+    if ((rc = by.reserve(8 * ny)) || (out_symbols && (rc = bs.reserve((size_t)n_frames * d->dev.N))) || (out_iters && (rc = bi.reserve(4 * (size_t)n_frames)))) { by.release(); bs.release(); bi.release(); return rc; }
+    NbIO io; memset(&io, 0, sizeof io);
+    io.n_frames = n_frames; io.y = (const double *)by.p; io.out_symbols = out_symbols ? (uint8_t *)bs.p : nullptr; io.out_iters = out_iters ? (int *)bi.p : nullptr;
+    cudaError_t e = ny ? cudaMemcpy(by.p, y, 8 * ny, cudaMemcpyHostToDevice) : cudaSuccess;
+    rc = e == cudaSuccess ? nb_run(d, ch, io, cnt) : set_err(LDPC_GPU_ERR_CUDA, "copy failed");
+    if (!rc && out_symbols && n_frames) e = cudaMemcpy(out_symbols, bs.p, (size_t)n_frames * d->dev.N, cudaMemcpyDeviceToHost);
+    if (!rc && e == cudaSuccess && out_iters && n_frames) e = cudaMemcpy(out_iters, bi.p, 4 * (size_t)n_frames, cudaMemcpyDeviceToHost);
+    by.release(); bs.release(); bi.release();
+    if (!rc && e != cudaSuccess) return set_err(LDPC_GPU_ERR_CUDA, "copy failed");
+    return rc;
+}
+
+extern "C" int ldpc_gpu_nb_simulate(ldpc_gpu_nb_decoder *d, const ldpc_gpu_channel *ch, uint64_t seed, int64_t frame_begin, int64_t n_frames,
+                                    ldpc_gpu_counters *cnt, double *kernel_ms)
+{
+    if (!d || !cnt || n_frames < 0) return set_err(LDPC_GPU_ERR_INVALID_ARG, "bad argument");
+    CU_TRY(cudaSetDevice(d->device));
+    NbIO io; memset(&io, 0, sizeof io);
+    io.n_frames = n_frames; io.frame_begin = frame_begin; io.seed = seed;
+    int rc = nb_run(d, ch, io, cnt);
+    if (kernel_ms) *kernel_ms = d->last_ms;
+    return rc;
 }

@@ -63,11 +63,11 @@ def newer(target, sources):
 def build_restatement(force=False):
     os.makedirs(BUILD, exist_ok=True)
     out = os.path.join(BUILD, "libldpc_oracle.so")
-    srcs = [os.path.join(HERE, "ldpc_oracle.c"), os.path.join(HERE, "ldpc_oracle.h"),
+    srcs = [os.path.join(HERE, "ldpc_oracle.c"), os.path.join(HERE, "ldpc_nb_oracle.c"), os.path.join(HERE, "ldpc_oracle.h"),
             os.path.join(HERE, "..", "include", "ldpc_gpu.h")]
     if force or not newer(out, srcs):
         run(["gcc", "-O2", "-g", "-std=c11", "-D_GNU_SOURCE", "-ffp-contract=off", "-fPIC", "-shared", "-Wall",
-             srcs[0], "-lm", "-o", out])
+             srcs[0], srcs[1], "-lm", "-o", out])
     return out
 
 

@@ -210,6 +210,52 @@ class Oracle:
 
 
 # ------------------------------------------------------------------------------------------------
+class NbOracle:
+    """Min-max decoding of non-binary codes, C restatement (oracle/ldpc_nb_oracle.c).  Parity unpinned."""
+
+    def __init__(self, alist_path):
+        L = Oracle.lib()
+        L.oracle_nb_code_load_alist.restype = C.c_void_p
+        L.oracle_nb_code_load_alist.argtypes = [C.c_char_p]
+        L.oracle_nb_code_free.argtypes = [C.c_void_p]
+        L.oracle_nb_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+        L.oracle_nb_decode.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_nb_simulate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p]
+        self.L = L
+        self.h = L.oracle_nb_code_load_alist(os.fsencode(alist_path))
+        if not self.h:
+            raise ValueError("oracle: cannot load " + alist_path)
+        v = [C.c_int() for _ in range(4)]
+        L.oracle_nb_dims(self.h, *[C.byref(x) for x in v])
+        self.N, self.M, self.q, self.m = [x.value for x in v]
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.oracle_nb_code_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def _counters(c):
+        return {"errors": int(c[0]), "uncodedErrors": 0, "totalBits": int(c[1]), "totalWords": int(c[2]), "wordErrors": int(c[3]),
+                "totalIterations": int(c[4]), "smoothingUsed": int(c[6]), "undetectedWords": int(c[5])}
+
+    def decode(self, T, y):
+        y = np.ascontiguousarray(y, np.float64)
+        F = y.shape[0]
+        sym, it, cnt = np.zeros((F, self.N), np.uint8), np.zeros(F, np.int32), np.zeros(8, np.int64)
+        self.L.oracle_nb_decode(self.h, T, F, _ptr(y), _ptr(sym), _ptr(it), _ptr(cnt))
+        return Result(symbols=sym, iters=it, counters=self._counters(cnt))
+
+    def simulate(self, T, snr_db, R, seed, frame_begin, n_frames):
+        cnt = np.zeros(8, np.int64)
+        self.L.oracle_nb_simulate(self.h, T, snr_db, R, seed, frame_begin, n_frames, _ptr(cnt))
+        return Result(counters=self._counters(cnt))
+
+
+# ------------------------------------------------------------------------------------------------
 class Reference:
     """One variant of the reference's own object code (oracle/_ref/libref_<variant>.so)."""
 
