@@ -123,8 +123,11 @@ LDPC_DEVINL uint32_t x2_check_row(unsigned char *msgb, const int slot, const uin
     const uint32_t eng = __hgt2_mask(t2, h2_from(k.x2_cap2));                         // t2 >= t1
     const uint32_t bad = ~__hge2_mask(h2_from(m1a), h2_from(k.x2_m02)) | sg;             // bit 15 / 31 of each half
     const uint32_t flags = ((eng & 0x00010001u) << 1) | ((bad >> 15) & 0x00010001u);
-    uint32_t s1 = h2_bits(o1) ^ sg, d12 = h2_bits(o1) ^ h2_bits(o2);
-    asm("" : "+r"(s1), "+r"(d12));                                              // keep the two row constants as they are: two LOP3 per edge below
+    // second pass, per edge:  c2v = sign(v) * (row sign) * (|v| == min1 ? o2 : o1)  as  HSET2.BF (1.0 where the edge attains the row
+    // minimum) -> HFMA2 eq * (s2 - s1) + s1 (exact on the lattice; the FMA pipe is the idle one in this phase, the ALU pipe --
+    // HMNMX2 / LOP3 / HSET2 -- the busy one: r2e capture) -> one LOP3 for sign(v)
+    const uint32_t s1 = h2_bits(o1) ^ sg, s2 = h2_bits(o2) ^ sg;
+    const __half2 ds = __hsub2(h2_from(s2), h2_from(s1));
     const uint4 *sched2 = sched + k.zero;                                        // == sched, but ptxas cannot merge the second pass's loads with the first's
     if (!KEEP) wn = x2_sched_again(&sched2[j]);
 #pragma unroll
@@ -135,8 +138,8 @@ LDPC_DEVINL uint32_t x2_check_row(unsigned char *msgb, const int slot, const uin
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int e = g * 4 + q;
-            const uint32_t eq = __heq2_mask(__habs2(h2_from(v[e])), h2_from(m1a));  // 0xffff where this edge attains the row minimum
-            const uint32_t o = x2_and_xor(eq, d12, x2_and_xor(v[e], 0x80008000u, s1));   // sign(v) s1, or sign(v) s2 on the argmin edge
+            const __half2 eq = __heq2(__habs2(h2_from(v[e])), h2_from(m1a));       // 1.0 where this edge attains the row minimum
+            const uint32_t o = x2_and_xor(v[e], 0x80008000u, h2_bits(__hfma2(eq, ds, h2_from(s1))));   // sign(v) s1, or sign(v) s2 on the argmin edge
             v[e] = o;                                                              // c2v, kept for the next iteration
             *reinterpret_cast<uint32_t *>(msgb + off[q]) = o;
         }
