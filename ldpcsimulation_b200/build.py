@@ -15,7 +15,7 @@ LIB = os.path.join(OUT, "libldpc_gpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
-              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-Wno-deprecated-gpu-targets"]
+              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-Wno-deprecated-gpu-targets", "-split-compile", "0"]
 
 
 def _newer(target, sources):

@@ -24,6 +24,7 @@
 #include "ldpc_ms_rc.cuh"
 #include "ldpc_schedule.h"
 #include "ldpc_ms_tile.cuh"
+#include "ldpc_ms_quad.cuh"
 #include "ldpc_ms_h2.cuh"
 #include "ldpc_ms_h2rc.cuh"
 #include "ldpc_ms_x2.cuh"
@@ -515,6 +516,17 @@ static int pick_kernel(ldpc_gpu_decoder *d)
             }
             else if (v.regular_dc == 32 && v.regular_dv == 6) fast = MS_FAST(32, 6, true, true);
             else if (v.regular_dc == 32 && v.dv_max <= 6) fast = MS_FAST(32, 6, true, false);
+            else if (!f64 && v.M <= 512 && v.dc_max <= 8 && v.dv_max <= 4 && !getenv("LDPC_GPU_NO_QUAD") &&
+                     ms_quad_smem_bytes<1>(v) * 2 <= (size_t)max_optin) {
+                // small codes (BASELINE configs[0], the (3,6) PEG code): four frames per thread, c2v resident in registers (ldpc_ms_quad.cuh)
+                const char *qv = getenv("LDPC_GPU_QUAD_VARIANT");                        // A/B switch: 0 = 4 frames x 2 CTAs/SM, 1 = 8 frames x 1 CTA/SM
+                const bool wide = qv && atoi(qv) == 1 && ms_quad_smem_bytes<2>(v) <= (size_t)max_optin;
+                if (v.regular_dc == 6 && v.dv_max <= 3) fast = wide ? (KernelFn)ms_quad_kernel<6, 3, true, 2, 512, 1> : (KernelFn)ms_quad_kernel<6, 3, true, 1, 512, 2>;
+                else fast = wide ? (KernelFn)ms_quad_kernel<8, 4, false, 2, 512, 1> : (KernelFn)ms_quad_kernel<8, 4, false, 1, 512, 2>;
+                d->frames_per_cta = wide ? 8 : 4;
+                smem = wide ? ms_quad_smem_bytes<2>(v) : ms_quad_smem_bytes<1>(v);
+                block = std::max(128, round32(v.M));
+            }
             else if (v.dc_max <= 8 && v.regular_dv == 3 && v.M <= 512 && !f64 && !getenv("LDPC_GPU_NO_SMALL"))
                 fast = (KernelFn)ms_fast_kernel<float, 8, 3, false, true, 512, 4>;     // small (3,6)-class codes: 4 frames per SM at 32 registers (3.17 -> 3.46 Gbit/s on PEG, T = 50; 3 frames at 40 registers: 3.39)
             else if (v.dc_max <= 8 && v.regular_dv == 3) fast = MS_FAST(8, 3, false, true);
