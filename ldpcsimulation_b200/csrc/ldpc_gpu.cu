@@ -393,6 +393,46 @@ static int build_schedule(ldpc_gpu_decoder *d, const ldpc_gpu_code *c, size_t re
     return LDPC_GPU_OK;
 }
 
+// Small codes (ldpc_ms_quad.cuh): rows sorted by weight, one per thread; per-thread edge words in an order in which the eight lanes of
+// a 16-byte access phase fall into distinct 16-byte bank groups (ldpc_schedule.h, build_group_schedule), natural order otherwise.
+static int build_quad_tables(ldpc_gpu_decoder *d, const ldpc_gpu_code *c)
+{
+    CodeDev &v = d->dev;
+    v.quad_edge = nullptr; v.quad_steps = nullptr; v.quad_col_of_var = nullptr; v.quad_var_of_col = nullptr;
+    const int N = v.N, M = v.M, dvm = c->dv_max, dcm = c->dc_max;
+    if (M > 512 || dcm > 8 || dvm > 4 || v.dvN > 65535 || N > 65534) return LDPC_GPU_OK;
+    for (int j = 0; j < M; j++) if (c->row_deg[j] < 2) return LDPC_GPU_OK;            // the padded row update needs two finite minima
+    std::vector<int> rdeg(M), ml((size_t)M * dcm, 0);
+    for (int j = 0; j < M; j++) { rdeg[j] = c->row_deg[j]; for (int k = 0; k < rdeg[j]; k++) ml[(size_t)j * dcm + k] = c->mlist[(size_t)j * dcm + k]; }
+    GroupSchedule gs;
+    if (!getenv("LDPC_GPU_NO_SCHED")) gs = build_group_schedule(N, M, dcm, rdeg, ml, 8);
+    if (!gs.ok) {                                                                      // natural order, rows still sorted by weight
+        gs.col.resize(N); gs.var_of_col.resize(N); gs.row_of_thread.resize(M); gs.step.assign((size_t)M * dcm, -1);
+        std::iota(gs.col.begin(), gs.col.end(), 0); std::iota(gs.var_of_col.begin(), gs.var_of_col.end(), 0);
+        std::iota(gs.row_of_thread.begin(), gs.row_of_thread.end(), 0);
+        std::stable_sort(gs.row_of_thread.begin(), gs.row_of_thread.end(), [&](int a, int b) { return rdeg[a] > rdeg[b]; });
+        for (int t = 0; t < M; t++) for (int k = 0; k < rdeg[gs.row_of_thread[t]]; k++) gs.step[(size_t)t * dcm + k] = k;
+    }
+    std::vector<uint32_t> tab((size_t)8 * M, ((uint32_t)N << 16) | (uint32_t)v.dvN);
+    std::vector<uint8_t> steps(M, 0);
+    for (int t = 0; t < M; t++) {
+        const int j = gs.row_of_thread[t];
+        for (int s = 0; s < dcm; s++) {
+            const int k = gs.step[(size_t)t * dcm + s];
+            if (k < 0) continue;
+            const int i = c->mlist[(size_t)j * dcm + k], sl = c->vn_slot[(size_t)j * dcm + k];
+            tab[(size_t)s * M + t] = ((uint32_t)gs.col[i] << 16) | (uint32_t)(sl * N + gs.col[i]);
+            steps[t] = (uint8_t)(s + 1);
+        }
+    }
+    std::vector<uint16_t> cov(N), voc(N);
+    for (int i = 0; i < N; i++) { cov[i] = (uint16_t)gs.col[i]; voc[i] = (uint16_t)gs.var_of_col[i]; }
+    int rc;
+    if ((rc = upload(d, tab, &v.quad_edge)) || (rc = upload(d, steps, &v.quad_steps)) || (rc = upload(d, cov, &v.quad_col_of_var)) ||
+        (rc = upload(d, voc, &v.quad_var_of_col))) return rc;
+    return LDPC_GPU_OK;
+}
+
 static int build_device_code(ldpc_gpu_decoder *d, const ldpc_gpu_code *c)
 {
     CodeDev &v = d->dev;
@@ -516,15 +556,11 @@ static int pick_kernel(ldpc_gpu_decoder *d)
             }
             else if (v.regular_dc == 32 && v.regular_dv == 6) fast = MS_FAST(32, 6, true, true);
             else if (v.regular_dc == 32 && v.dv_max <= 6) fast = MS_FAST(32, 6, true, false);
-            else if (!f64 && v.M <= 512 && v.dc_max <= 8 && v.dv_max <= 4 && !getenv("LDPC_GPU_NO_QUAD") &&
-                     ms_quad_smem_bytes<1>(v) * 2 <= (size_t)max_optin) {
+            else if (!f64 && v.quad_edge && !getenv("LDPC_GPU_NO_QUAD") && ms_quad_smem_bytes(v) * 2 <= (size_t)max_optin) {
                 // small codes (BASELINE configs[0], the (3,6) PEG code): four frames per thread, c2v resident in registers (ldpc_ms_quad.cuh)
-                const char *qv = getenv("LDPC_GPU_QUAD_VARIANT");                        // A/B switch: 0 = 4 frames x 2 CTAs/SM, 1 = 8 frames x 1 CTA/SM
-                const bool wide = qv && atoi(qv) == 1 && ms_quad_smem_bytes<2>(v) <= (size_t)max_optin;
-                if (v.regular_dc == 6 && v.dv_max <= 3) fast = wide ? (KernelFn)ms_quad_kernel<6, 3, true, 2, 512, 1> : (KernelFn)ms_quad_kernel<6, 3, true, 1, 512, 2>;
-                else fast = wide ? (KernelFn)ms_quad_kernel<8, 4, false, 2, 512, 1> : (KernelFn)ms_quad_kernel<8, 4, false, 1, 512, 2>;
-                d->frames_per_cta = wide ? 8 : 4;
-                smem = wide ? ms_quad_smem_bytes<2>(v) : ms_quad_smem_bytes<1>(v);
+                fast = (v.regular_dv == 3) ? (KernelFn)ms_quad_kernel<8, 3, true, 512, 2> : (KernelFn)ms_quad_kernel<8, 4, false, 512, 2>;
+                d->frames_per_cta = 4;
+                smem = ms_quad_smem_bytes(v);
                 block = std::max(128, round32(v.M));
             }
             else if (v.dc_max <= 8 && v.regular_dv == 3 && v.M <= 512 && !f64 && !getenv("LDPC_GPU_NO_SMALL"))
@@ -665,6 +701,7 @@ extern "C" int ldpc_gpu_decoder_create(const ldpc_gpu_code *code, const ldpc_gpu
     if ((rc = build_device_code(d, code)) ||
         ((cfg->kind == LDPC_GPU_KIND_MINSUM || (cfg->kind == LDPC_GPU_KIND_BP && cfg->precision != LDPC_GPU_PREC_F64)) &&
          (rc = build_schedule(d, code, cfg->precision == LDPC_GPU_PREC_F64 ? 8 : 4))) ||
+        (cfg->kind == LDPC_GPU_KIND_MINSUM && cfg->precision == LDPC_GPU_PREC_F32 && (rc = build_quad_tables(d, code))) ||
         (rc = pick_kernel(d))) { ldpc_gpu_decoder_destroy(d); return rc; }
     if (d->x2) {
         ldpc_gpu_decoder_cfg c64 = *cfg; c64.precision = LDPC_GPU_PREC_F64; c64.flags &= ~(uint32_t)LDPC_GPU_F_CERT_STOP;

@@ -32,6 +32,11 @@ struct CodeDev {
     const uint16_t*col_of_var; // [N] storage column of variable i
     const uint16_t*var_of_col; // [N] inverse
     const uint8_t *row_slot; // [M] slot shared by every edge of row j (ldpc_ms_rc.cuh), or NULL when rows mix slots
+    // small codes, four frames per 16-byte word (ldpc_ms_quad.cuh; ldpc_schedule.h: build_group_schedule), or NULL
+    const uint32_t*quad_edge;  // [s*M + t]  step s of thread t: (storage column << 16) | (slot*N + storage column); idle steps: (N << 16) | dvN
+    const uint8_t *quad_steps; // [M] steps thread t needs (its last busy step + 1)
+    const uint16_t*quad_col_of_var; // [N] storage column of variable i
+    const uint16_t*quad_var_of_col; // [N] inverse
 };
 
 // Decoder configuration + per-call channel constants, all derived on the host in double with the

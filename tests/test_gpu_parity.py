@@ -284,17 +284,15 @@ def test_f16x2_refuses_other_codes_and_decoders():
     assert e.value.code == abi.ERR_UNSUPPORTED
 
 
-@pytest.mark.parametrize("qvariant", ["0", "1"])
 @pytest.mark.parametrize("variant", ["decodeMinSum", "decodeNormalizedMinSum", "decodeOffsetMinSum", "decodeSaturatedMinSum"])
-def test_small_code_multi_frame_kernel_equals_single_frame_kernel(variant, qvariant, monkeypatch):
-    """ms_quad_kernel (small codes: four / eight frames per thread in float4 words, c2v in the row thread's registers, sums
+def test_small_code_multi_frame_kernel_equals_single_frame_kernel(variant, monkeypatch):
+    """ms_quad_kernel (small codes: four frames per thread in float4 words, c2v in the row thread's registers, sums
     published by the variable phase) performs the fp32 operations of ms_fast_kernel<float> in the same order: decisions,
     iteration counts, flags, counters and a-posteriori sums bit-identical on every frame -- ragged tiles (F not a multiple
     of the tile), codewords and T = 0 included."""
     R, snr = 0.5, 2.2
     code = capi.Code(code_path("PEG"))
     cws = code.random_codewords(11, 3)
-    monkeypatch.setenv("LDPC_GPU_QUAD_VARIANT", qvariant)
     for T, F in ((0, 5), (1, 9), (7, 8), (50, 43)):
         cfg = cases.cfg_for(variant, code="PEG", num_iterations=T, precision=abi.PREC_F32)
         y, noise, rows, cw = cases.make_inputs(code.N, cfg, snr, R, F, 4400 + T, cws if T != 1 else None)
