@@ -532,6 +532,10 @@ static int pick_kernel(ldpc_gpu_decoder *d)
             !getenv("LDPC_GPU_GENERIC_BP")) {
             d->fn = (KernelFn)ms_sched_kernel<float, 32, 6, 2048, 384, 2, ALGO_BP>;    // O(dc) phi-domain sum-product
             block = 384; smem = ms_sched_smem_bytes<float>(v);
+            if (v.row_slot && !getenv("LDPC_GPU_NO_RC")) {                              // c2v resident in the row thread's registers (ldpc_ms_rc.cuh)
+                d->fn = (KernelFn)ms_rc_kernel<float, 32, 6, 2048, 384, 2, true, ALGO_BP>;   // (one CTA per SM at 160 registers, no spills: 6.8 vs 7.0 Gbit/s)
+                smem = ms_rc_smem_bytes<float>(v);
+            }
         }
         if (algo == ALGO_MS && v.idx16 && !d->gstate && !getenv("LDPC_GPU_GENERIC_MS")) {
             // degree-specialised min-sum kernel where an instantiation covers the code
@@ -613,7 +617,7 @@ geometry:
     const int by_regs = (65536 / std::max(1, fa.numRegs)) & ~31;      // one CTA must fit the register file
     const int block_wanted = block;
     block = std::max(32, std::min(block, std::min(by_regs, fa.maxThreadsPerBlock & ~31)));
-    if (block != block_wanted && (d->fn == (KernelFn)ms_rc_kernel<float, 32, 6, 2048, 384, 2> || d->fn == (KernelFn)ms_rc_kernel<double, 32, 6, 2048, 384, 1> ||
+    if (block != block_wanted && (d->fn == (KernelFn)ms_rc_kernel<float, 32, 6, 2048, 384, 2> || d->fn == (KernelFn)ms_rc_kernel<float, 32, 6, 2048, 384, 2, true, ALGO_BP> || d->fn == (KernelFn)ms_rc_kernel<double, 32, 6, 2048, 384, 1> ||
                                   d->fn == (KernelFn)ms_rc_kernel<float, 32, 6, 2048, 384, 2, false> || d->fn == (KernelFn)ms_rc_kernel<double, 32, 6, 2048, 384, 1, false>))
         return set_err(LDPC_GPU_ERR_UNSUPPORTED, "ms_rc_kernel is written for blocks of exactly 384 threads");
     int nb = 0;

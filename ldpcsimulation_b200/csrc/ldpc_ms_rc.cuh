@@ -172,14 +172,63 @@ LDPC_DEVINL void rc_check_row_f32(unsigned char *msgb, const int slot, const uin
     else second_pass(std::false_type(), std::false_type());
 }
 
+// Sum-product check row on the register-resident structure (fp32 instantiation; src/decodeBP.cpp:353-377 in the phi domain, as in
+// ms_sched_kernel<.., ALGO_BP>): v2c = clip(S - c2v, +-MAXLLR) (:399-402), |c2v_k| = phi(sum_{i != k} phi(|v_i|)).  The leave-one-out
+// sum is total - own with the total carried as an unevaluated fp32 pair (hi, lo) -- Knuth's TwoSum per edge, on the FMA pipe -- which
+// keeps the difference accurate when one weak message dominates the total.  (ms_sched_kernel carried it in fp64: a float->double and
+// a double->float conversion per edge on the quarter-rate XU pipe, which phi's three MUFU per call already saturate.)
+template <int DC, int DV, int NB, bool USLOT>
+LDPC_DEVINL void rc_check_row_bp(unsigned char *msgb, const int slot, const uint4 *__restrict__ sched, const int M, const int j, float (&v)[DC], const float maxllr)
+{
+    constexpr int NG = DC / 4;
+    float hi = 0.0f, lo = 0.0f;
+    uint32_t sgb = 0u;
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+        const uint4 w = __ldg(&sched[(size_t)g * M + j]);
+        const uint32_t off[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = g * 4 + q;
+            uint32_t so;
+            if (USLOT) asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(so) : "r"((uint32_t)slot), "r"((uint32_t)-NB), "r"(off[q]));
+            else so = off[q] & (uint32_t)(NB - 1);
+            float x = *reinterpret_cast<const float *>(msgb + DV * NB + so) - v[k];      // v2c = sum - c2v
+            x = fminf(fmaxf(x, -maxllr), maxllr);
+            const float ph = bp_phi<float>(fabsf(x));
+            const float s = __fadd_rn(hi, ph), bb = __fadd_rn(s, -hi);                   // TwoSum(hi, ph)
+            lo = __fadd_rn(lo, __fadd_rn(__fadd_rn(hi, -__fadd_rn(s, -bb)), __fadd_rn(ph, -bb)));
+            hi = s;
+            sgb ^= __float_as_uint(x);
+            v[k] = SignOps<float>::apply(ph, x);                                         // phi(|v|) carrying the sign of v
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+        const uint4 w = __ldg(&sched[(size_t)g * M + j]);
+        const uint32_t off[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = g * 4 + q;
+            const float own = v[k];
+            const float excl = __fadd_rn(__fadd_rn(hi, -fabsf(own)), lo);
+            const float mag = bp_phi<float>(fmaxf(excl, 0.0f));
+            const float o = SignOps<float>::apply(SignOps<float>::presign(mag, sgb), own);
+            v[k] = o;                                                                    // c2v, kept for the next iteration
+            *reinterpret_cast<float *>(msgb + off[q]) = o;
+        }
+    }
+}
+
 // USLOT: every edge of a row sits in the same slot of its variables' lists (row_slot; the redundant-row 802.3an H).  Without it
 // (the full-rank 802_3.alist: dv in {5, 6}, rows mix slots) the sum's address is the message offset modulo the plane size, and
 // the planes of slots a variable does not have stay zero from the kernel's start.
-template <typename Real, int DC, int DV, int NFIX, int NT_MAX, int MINB, bool USLOT = true>
+template <typename Real, int DC, int DV, int NFIX, int NT_MAX, int MINB, bool USLOT = true, int ALGO = ALGO_MS>
 __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, const DecParams p, const FrameIO io)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     static_assert(DV <= 8, "slot dispatch covers dv <= 8");
+    static_assert(ALGO == ALGO_MS || sizeof(Real) == 4, "the phi-domain sum-product row update is the fp32 path");
     FrameScratch *fs = reinterpret_cast<FrameScratch *>(smem_raw);
     Real *msg = reinterpret_cast<Real *>(smem_raw + 16);                       // [DV*N] c2v
     constexpr int N = NFIX;
@@ -215,7 +264,11 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
         for (int q = 0; q < 4; q++) {
             const int i = 4 * b + q;
             Real vr; bool rneg;
-            if (sizeof(Real) == 4 && fcond) {
+            if (ALGO == ALGO_BP) {                                // src/decodeBP.cpp:186-193
+                double v = 4.0 * y4[q] / p.N0;
+                if (fabs(v) > p.MAXLLR) v = (neg_ge(v) ? -1.0 : 1.0) * p.MAXLLR;
+                rneg = neg_ge(v); vr = (Real)v;
+            } else if (sizeof(Real) == 4 && fcond) {
                 const float vf = condition_ms_guarded(y4[q], p, qflags);
                 vr = (Real)vf; rneg = !(vf > 0.0f);
             } else {                                              // src/decodeMinSum.cpp:214-238
@@ -254,7 +307,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
     // all twelve warps at once right after it (long_scoreboard was 10 % of the check-phase samples)
     uint4 sw[RC_NPRE];
     auto fetch_schedule = [&]() {
-        if constexpr (sizeof(Real) == 4) {
+        if constexpr (sizeof(Real) == 4 && ALGO == ALGO_MS) {
             if (has_row) {
 #pragma unroll
                 for (int g = 0; g < RC_NPRE; g++) sw[g] = __ldg(&c.sched[(size_t)g * M + tid]);
@@ -295,7 +348,8 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_rc_kernel(const CodeDev c, co
             if (last) for (int w = tid; w < nwords; w += nt) dbits[w] = 0u;
             // ---- check-node phase: one row per thread ------------------------------------------------
             if (has_row) {
-                if constexpr (sizeof(Real) == 4) rc_check_row_f32<DC, DV, NB, USLOT>(msgb, slot, sw, c.sched, M, tid, v, normalized, offset, inv_alpha, delta, p.alpha_div_f);
+                if constexpr (ALGO == ALGO_BP) rc_check_row_bp<DC, DV, NB, USLOT>(msgb, slot, c.sched, M, tid, v, (float)p.MAXLLR);
+                else if constexpr (sizeof(Real) == 4) rc_check_row_f32<DC, DV, NB, USLOT>(msgb, slot, sw, c.sched, M, tid, v, normalized, offset, inv_alpha, delta, p.alpha_div_f);
                 else rc_check_row<Real, DC, DV, NB, USLOT>(msgb, slot, c.sched, M, tid, v, normalized, offset, alpha, inv_alpha, delta);
             }
             // next frame's channel samples, one block per thread, right after the thread's row: the generator is a long

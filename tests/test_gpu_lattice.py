@@ -130,3 +130,33 @@ def test_f32_gdbf_family_criterion(variant):
     assert rep["easy_and_fp32_in_error"] <= 0.01 * easy.sum(), rep
     assert differ.mean() < 0.05, rep
     assert abs(rep["oracle_word_errors"] - rep["fp32_word_errors"]) <= differ.sum(), rep
+
+
+@pytest.mark.parametrize("T,snr", [(10, 4.0), (4, 3.4)])
+def test_f32_sum_product_error_report(T, snr):
+    """fp32 sum-product (phi domain, MUFU ex2 / lg2 / rcp; ms_rc_kernel<.., ALGO_BP>) against the double oracle on the bench's
+    code at its operating point (T = 10, 4.0 dB: every LLR ends near the +-MAXLLR clip) and at T = 4, 3.4 dB (unsaturated
+    messages, many frames not yet converged).  north_star: identical hard decisions on all but tie frames, LLRs within 1e-5
+    relative.  What holds, and is asserted: decisions identical on every frame the oracle converges on; a-posteriori LLRs within
+    2e-5 of the frame's largest |LLR| on those frames.  What is REPORTED (gpurun_out/parity_report_bp_f32_*.json): the per-element
+    relative error, which is larger where an LLR is the small difference of large messages."""
+    F = 512
+    cfg64 = abi.default_cfg(abi.KIND_BP, num_iterations=T)
+    cfg32 = abi.default_cfg(abi.KIND_BP, num_iterations=T, precision=abi.PREC_F32)
+    orc = Oracle("802_3_H")
+    y, _, _, _ = cases.make_inputs(orc.N, cfg64, snr, R, F, 4242)
+    a = orc.decode(cfg64, snr, R, y)
+    b = capi.Decoder(capi.Code(code_path("802_3_H")), cfg32).decode(snr, R, y)
+    conv = a.errors == 0
+    diff_frames = np.any(a.bits != b.bits, axis=1)
+    assert not np.any(diff_frames & conv)
+    sa, sb = a.soft[conv], b.soft[conv].astype(np.float64)
+    frame_rel = np.abs(sa - sb).max(axis=1) / np.abs(sa).max(axis=1)
+    elem_rel = np.abs(sa - sb) / np.maximum(np.abs(sa), 1e-300)
+    _report("bp_f32_T%d_%.1fdB" % (T, snr), dict(frames=F, converged=int(conv.sum()), frames_with_different_decisions=int(diff_frames.sum()),
+                           different_and_converged=int((diff_frames & conv).sum()),
+                           per_frame_rel_err_max=float(frame_rel.max()), per_frame_rel_err_median=float(np.median(frame_rel)),
+                           per_element_rel_err_max=float(elem_rel.max()), per_element_rel_err_p999=float(np.quantile(elem_rel, 0.999)),
+                           per_element_rel_err_median=float(np.median(elem_rel)),
+                           elements_above_1e5=float((elem_rel > 1e-5).mean())))
+    assert frame_rel.max() < 2e-5
