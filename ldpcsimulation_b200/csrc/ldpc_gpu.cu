@@ -595,7 +595,6 @@ static int pick_kernel(ldpc_gpu_decoder *d)
         }
         block = std::min(1024, std::max(128, round32(std::max(v.M, (v.N + 3) / 4))));
         if (v.M <= 512 && v.N <= 4096) block = 256;                           // measured on the 802.3an H: 256 > 384 > 512
-        if (const char *gb = getenv("LDPC_GPU_GDBF_BLOCK")) block = std::max(64, atoi(gb) & ~31);
     } else if (kind == LDPC_GPU_KIND_NGDBF_HW) {
         if (v.N >= LDPC_GPU_HW_QBUF) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "NGDBFhw's 2648-entry noise window needs N < 2648 (src/NGDBFhw.cpp:151)");
         d->fn = (KernelFn)hw_kernel;
