@@ -262,7 +262,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="oms_8023", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="frames per step per GPU (value); 0 = per-workload default")
-    ap.add_argument("--e2e-frames", type=int, default=1 << 17, help="frames per step per GPU (e2e, host buffers)")
+    ap.add_argument("--e2e-frames", type=int, default=1 << 19, help="frames per step per GPU (e2e, host buffers; the side formats use at most 2^17)")
     ap.add_argument("--precision", default=None, choices=["x2", "f32", "f64"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip parity_f64 / fp32 / other_workloads")
@@ -409,9 +409,11 @@ def main():
 
     # ---- e2e: reference-facing call with host buffers -------------------------------------------
     Fe = args.e2e_frames if W["code"] != "dvbs2" else 1 << 11
+    if not W["q8"]:
+        Fe = min(Fe, 1 << 17)                            # no packed-level headline format: everything runs at the side formats' batch
     sigma = float(np.sqrt(10 ** (-snr / 10) / R / 2))
     gen = torch.Generator(device="cuda").manual_seed(7 + rank)
-    y_dev = 1.0 + sigma * torch.randn((Fe, NB), generator=gen, device="cuda", dtype=torch.float32)
+    y_dev_all = 1.0 + sigma * torch.randn((Fe, NB), generator=gen, device="cuda", dtype=torch.float32)
     bits_host = torch.empty((Fe, (NB + 7) // 8), dtype=torch.uint8, pin_memory=True)
     iters_host = torch.empty((Fe,), dtype=torch.int32, pin_memory=True)
     e2e_steps = max(3, min(args.steps, 10))
@@ -420,7 +422,11 @@ def main():
         hw_noise = torch.empty((Fe, abi.HW_QBUF), dtype=torch.float64, pin_memory=True)
         hw_noise.copy_(torch.randn((Fe, abi.HW_QBUF), generator=gen, device="cuda", dtype=torch.float64))
 
-    def run_e2e(decoder, torch_dtype, abi_dtype, steps=e2e_steps):
+    Fs = min(Fe, 1 << 17)                                # batch of the side formats (fp64 samples of 2^19 frames would pin 8.6 GB per rank)
+
+    def run_e2e(decoder, torch_dtype, abi_dtype, steps=e2e_steps, frames=None):
+        Fe = frames or Fs                                 # (shadows the headline batch size: everything below is per call)
+        y_dev = y_dev_all[:Fe]
         Qb = W["q8"][1] if W["q8"] else 8
         y_host = torch.empty((Fe, NB * Qb // 8) if abi_dtype == abi.DT_QP else (Fe, NB), dtype=torch_dtype, pin_memory=True)
         if abi_dtype in (abi.DT_Q8, abi.DT_QP):                   # the samples as a Q-bit converter delivers them: signed quantiser levels
@@ -453,7 +459,7 @@ def main():
             nl += decoder.last_timing()[1]
         barrier()
         w = max_over_ranks(time.perf_counter() - t1)
-        return Fe * steps * world * NB / w / 1e9, nl, float(np.unpackbits(bits_host.numpy()).mean())
+        return Fe * steps * world * NB / w / 1e9, nl, float(np.unpackbits(bits_host.numpy()[:Fe]).mean())
 
     noisy_gdbf = cfg.kind == abi.KIND_GDBF and abi.noise_rows_needed(cfg) > 0
     e2e = None
@@ -461,24 +467,25 @@ def main():
         if W["q8"]:
             # headline e2e: the decoder quantises its samples to Q bits, so the host hands over what a Q-bit converter delivers, one byte per
             # sample (LDPC_GPU_DT_Q8; bit-identical to raw double samples: tests/test_gpu_parity.py::test_quantiser_level_input_equals_raw_sample_input)
-            vp, e2e_launches, berp = run_e2e(dec, torch.uint8, abi.DT_QP)
+            vp, e2e_launches, berp = run_e2e(dec, torch.uint8, abi.DT_QP, frames=Fe)
             v8, _, ber8 = run_e2e(dec, torch.int8, abi.DT_Q8, steps=3)
             e2e = {"value": vp, "unit": "Gbit/s", "h2d_bytes_per_step": Fe * NB * W["q8"][1] // 8, "d2h_bytes_per_step": Fe * ((NB + 7) // 8 + 4), "steps": e2e_steps,
                    "api": "ldpc_gpu_decode_batch(mem=HOST, y_dtype=QP): pinned %d-bit quantiser levels, bit-packed (%d bits per sample), in; packed decisions + iteration counts out" % (W["q8"][1], W["q8"][1]),
                    "decoded_ber": berp,
-                   "byte_levels": {"value": v8, "h2d_bytes_per_step": Fe * NB, "decoded_ber": ber8}}
+                   "frames_per_step_per_gpu": Fe,
+                   "byte_levels": {"value": v8, "h2d_bytes_per_step": Fs * NB, "frames_per_step_per_gpu": Fs, "decoded_ber": ber8}}
         v64, l64, ber64 = run_e2e(dec, torch.float64, abi.DT_F64, steps=3)
         v32, _, ber32 = run_e2e(dec, torch.float32, abi.DT_F32, steps=3)
         v16, _, ber16 = run_e2e(dec, torch.float16, abi.DT_F16, steps=3)
         if e2e is None:
-            e2e = {"value": v64, "unit": "Gbit/s", "h2d_bytes_per_step": Fe * NB * 8 + (Fe * abi.HW_QBUF * 8 if hw_noise is not None else 0),
-                   "d2h_bytes_per_step": Fe * ((NB + 7) // 8 + 4), "steps": 3,
+            e2e = {"value": v64, "unit": "Gbit/s", "h2d_bytes_per_step": Fs * NB * 8 + (Fs * abi.HW_QBUF * 8 if hw_noise is not None else 0),
+                   "d2h_bytes_per_step": Fs * ((NB + 7) // 8 + 4), "steps": 3, "frames_per_step_per_gpu": Fs,
                    "api": "ldpc_gpu_decode_batch(mem=HOST, y_dtype=F64): pinned double samples (the reference's own sample type) in, packed decisions + iteration counts out",
                    "decoded_ber": ber64}
             e2e_launches = l64
-        e2e["fp64_samples"] = {"value": v64, "h2d_bytes_per_step": Fe * NB * 8, "decoded_ber": ber64}
-        e2e["fp32_samples"] = {"value": v32, "h2d_bytes_per_step": Fe * NB * 4, "decoded_ber": ber32}
-        e2e["fp16_samples"] = {"value": v16, "h2d_bytes_per_step": Fe * NB * 2, "decoded_ber": ber16}
+        e2e["fp64_samples"] = {"value": v64, "h2d_bytes_per_step": Fs * NB * 8, "frames_per_step_per_gpu": Fs, "decoded_ber": ber64}
+        e2e["fp32_samples"] = {"value": v32, "h2d_bytes_per_step": Fs * NB * 4, "frames_per_step_per_gpu": Fs, "decoded_ber": ber32}
+        e2e["fp16_samples"] = {"value": v16, "h2d_bytes_per_step": Fs * NB * 2, "frames_per_step_per_gpu": Fs, "decoded_ber": ber16}
     else:
         e2e = {"value": None, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "api": "not measured for this workload: the parity entry of a noisy bit-flipping decoder takes T x N doubles of decoder noise per frame"}
