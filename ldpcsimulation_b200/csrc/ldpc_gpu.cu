@@ -963,13 +963,58 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
             if (b->out_flags)  CU_TRY(cudaMemcpyAsync(b->out_flags + f0, s.flags.p, (size_t)nf, cudaMemcpyDeviceToHost, s.st));
             return LDPC_GPU_OK;
         };
-        auto drain = [&](Slot &s) -> int {                // wait for the slot's chunk; redo what the exact-lattice kernel left open
+        // Frames the exact-lattice kernel could not certify (about 5 in 10^6) are collected and decoded by the fp64 instantiation
+        // AFTER the last chunk: a redo launch in the middle of the pipeline needs a whole SM's shared memory, so it waits for the
+        // other slot's kernel to drain while the host, blocked on it, cannot queue the next chunk (3.5 % of the batch time, measured).
+        std::vector<long long> pending;
+        auto drain = [&](Slot &s) -> int {                // wait for the slot's chunk; note what the exact-lattice kernel left open
             CU_TRY(cudaStreamSynchronize(s.st));
             float ms = 0; cudaEventElapsedTime(&ms, s.k0, s.k1); d->last_kernel_ms += ms;
-            bool ran = false;
-            int r2 = redo_after_sync(d, p, s.io, s.st, &ran);
-            if (r2) return r2;
-            if (ran) { if ((r2 = copy_out(s))) return r2; CU_TRY(cudaStreamSynchronize(s.st)); }
+            if (d->x2) {
+                const int half = (s.st == d->slot[1].st) ? 1 : 0;
+                const unsigned int n = d->h_redo[half];
+                if (n) {
+                    std::vector<long long> ids(n);
+                    CU_TRY(cudaMemcpy(ids.data(), d->d_redo_list + (size_t)half * d->redo_cap, n * sizeof(long long), cudaMemcpyDeviceToHost));
+                    for (long long q : ids) pending.push_back(s.f0 + q);
+                }
+            }
+            return LDPC_GPU_OK;
+        };
+        auto redo_pending = [&]() -> int {                // the collected frames, compacted, through the fp64 decoder; results scattered back
+            if (pending.empty()) return LDPC_GPU_OK;
+            Slot &s = d->slot[0];
+            const size_t n = pending.size();
+            int r2;
+            if ((r2 = s.y.reserve(ybytes * n))) return r2;
+            if (b->codeword && (r2 = s.cw.reserve((size_t)N * n))) return r2;
+            for (size_t k = 0; k < n; k++) {
+                CU_TRY(cudaMemcpyAsync((char *)s.y.p + k * ybytes, (const char *)b->y + (size_t)pending[k] * ybytes, ybytes, cudaMemcpyHostToDevice, s.st));
+                if (b->codeword) CU_TRY(cudaMemcpyAsync((char *)s.cw.p + k * N, b->codeword + (size_t)pending[k] * N, (size_t)N, cudaMemcpyHostToDevice, s.st));
+            }
+            FrameIO ior = io;
+            ior.y = s.y.p; ior.n_frames = (long long)n; ior.frame_begin = 0; ior.codeword = b->codeword ? (const uint8_t *)s.cw.p : nullptr;
+            ior.noise = nullptr; ior.qpointer0 = nullptr; ior.workspace = nullptr; ior.ws_stride = 0;
+            ior.frame_list = nullptr; ior.n_frames_dev = nullptr; ior.redo_list = nullptr; ior.redo_count = nullptr; ior.redo_total = nullptr;
+            ior.out_bits = nullptr; ior.out_iters = nullptr; ior.out_soft = nullptr; ior.out_errors = nullptr; ior.out_flags = nullptr;
+            if (b->out_bits)   { if ((r2 = s.bits.reserve(bpf * n))) return r2;  ior.out_bits = (uint8_t *)s.bits.p; }
+            if (b->out_iters)  { if ((r2 = s.iters.reserve(4 * n))) return r2; ior.out_iters = (int *)s.iters.p; }
+            if (b->out_soft)   { if ((r2 = s.soft.reserve(ssz * N * n))) return r2; ior.out_soft = s.soft.p; }
+            if (b->out_errors) { if ((r2 = s.errs.reserve(4 * n))) return r2; ior.out_errors = (int *)s.errs.p; }
+            if (b->out_flags)  { if ((r2 = s.flags.reserve(n))) return r2; ior.out_flags = (uint8_t *)s.flags.p; }
+            ldpc_gpu_decoder *r = d->redo;
+            r->fn<<<(unsigned)std::min<long long>((long long)n, r->grid_full), r->block, r->smem, s.st>>>(r->dev, p, ior);
+            CU_TRY(cudaGetLastError());
+            d->last_launches++;
+            for (size_t k = 0; k < n; k++) {
+                const size_t f = (size_t)pending[k];
+                if (b->out_bits)   CU_TRY(cudaMemcpyAsync(b->out_bits + f * bpf, (char *)s.bits.p + k * bpf, bpf, cudaMemcpyDeviceToHost, s.st));
+                if (b->out_iters)  CU_TRY(cudaMemcpyAsync(b->out_iters + f, (int *)s.iters.p + k, 4, cudaMemcpyDeviceToHost, s.st));
+                if (b->out_soft)   CU_TRY(cudaMemcpyAsync((char *)b->out_soft + f * N * ssz, (char *)s.soft.p + k * N * ssz, ssz * N, cudaMemcpyDeviceToHost, s.st));
+                if (b->out_errors) CU_TRY(cudaMemcpyAsync(b->out_errors + f, (int *)s.errs.p + k, 4, cudaMemcpyDeviceToHost, s.st));
+                if (b->out_flags)  CU_TRY(cudaMemcpyAsync(b->out_flags + f, (uint8_t *)s.flags.p + k, 1, cudaMemcpyDeviceToHost, s.st));
+            }
+            CU_TRY(cudaStreamSynchronize(s.st));
             return LDPC_GPU_OK;
         };
         // any failure inside the loop must not leave async copies in flight on the caller's buffers
@@ -1024,6 +1069,7 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
             s.used = false;
             if ((rc = drain(s))) { const std::string msg = g_err; for (Slot &t : d->slot) { cudaStreamSynchronize(t.st); t.used = false; } return set_err(rc, msg); }
         }
+        if ((rc = redo_pending())) { const std::string msg = g_err; for (Slot &t : d->slot) cudaStreamSynchronize(t.st); cudaGetLastError(); return set_err(rc, msg); }
     } else return set_err(LDPC_GPU_ERR_INVALID_ARG, "unknown batch.mem");
     if (cnt) return fetch_counters(d, cnt, st0);
     return LDPC_GPU_OK;

@@ -82,6 +82,13 @@ def test_x2_redo_path_is_exact(monkeypatch):
     redo = dec.stats()[1]
     assert redo > 20, redo
     assert np.array_equal(a.bits, b.bits) and np.array_equal(a.errors, b.errors) and a.counters == b.counters
+    assert np.array_equal(a.iters, b.iters) and np.array_equal(a.flags, b.flags)
+    # with codewords (the host pipeline collects the uncertified frames of all chunks and re-decodes them, compacted, at the end)
+    cws = capi.Code(code_path("802_3_H")).random_codewords(3, 8)
+    yc, _, _, cw = cases.make_inputs(orc.N, cfg64, 3.8, R, 1201, 100, cws)
+    ac, bc = orc.decode(cfg64, 3.8, R, yc, codeword=cw), dec.decode(3.8, R, yc, codeword=cw)
+    assert dec.stats()[1] > redo
+    assert np.array_equal(ac.bits, bc.bits) and np.array_equal(ac.errors, bc.errors) and np.array_equal(ac.iters, bc.iters) and ac.counters == bc.counters
     # the throughput entry goes through the same redo launch
     s16 = dec.simulate(3.8, R, 77, 1000, 6000).counters
     monkeypatch.delenv("LDPC_GPU_X2_CAP_UNITS")
