@@ -110,13 +110,14 @@ LDPC_DEVINL float fast_channel_sample(const DecParams &p, const uint8_t *cw, int
     return (cw && i < N && cw[i]) ? -y : y;
 }
 
-// LDPC_GPU_DT_QP: the four Q-bit level codes of block b of frame f -> conditioned values (what quantize() makes of the samples)
-LDPC_DEVINL void packed_levels4(const FrameIO &io, const DecParams &p, const int N, const long long f, const int b, double y[4])
+// LDPC_GPU_DT_QP: the four Q-bit level codes of block b of a frame whose packed words start at w -> conditioned values (what
+// quantize() makes of the samples).  STAGED: w points into shared memory (the frame was staged by a bulk copy), else global.
+template <bool STAGED>
+LDPC_DEVINL void packed_levels4_at(const uint32_t *w, const DecParams &p, const int b, double y[4])
 {
     const int Q = p.Q;
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(io.y) + (size_t)f * (((size_t)N * Q) >> 5);   // N*Q is a multiple of 32
     const uint32_t bit = (uint32_t)(4 * b * Q), wi = bit >> 5, sh = bit & 31u;
-    const uint32_t lo = __ldg(w + wi), hi = (sh + 4 * Q > 32) ? __ldg(w + wi + 1) : 0u;
+    const uint32_t lo = STAGED ? w[wi] : __ldg(w + wi), hi = (sh + 4 * Q > 32) ? (STAGED ? w[wi + 1] : __ldg(w + wi + 1)) : 0u;
     const uint32_t v = __funnelshift_r(lo, hi, sh);
     const uint32_t mmask = (1u << (Q - 1)) - 1u;
 #pragma unroll
@@ -126,6 +127,34 @@ LDPC_DEVINL void packed_levels4(const FrameIO &io, const DecParams &p, const int
         const double a = (mag == mmask) ? p.Ymax : __dmul_rn((double)(mag + 1u), p.ms_step);
         y[q] = (code >> (Q - 1)) ? -a : a;
     }
+}
+LDPC_DEVINL void packed_levels4(const FrameIO &io, const DecParams &p, const int N, const long long f, const int b, double y[4])
+{
+    packed_levels4_at<false>(reinterpret_cast<const uint32_t *>(io.y) + (size_t)f * (((size_t)N * p.Q) >> 5), p, b, y);   // N*Q is a multiple of 32
+}
+
+// ---- 1-D bulk copies global -> shared through the TMA unit (cp.async.bulk, completion on an mbarrier) ---------------------
+// Used to stage the NEXT frames' packed samples while the current ones iterate (ldpc_ms_x2.cuh): the copy costs one thread two
+// instructions and no registers, and its DRAM latency disappears behind the iterations.  Addresses and sizes: multiples of 16 B.
+LDPC_DEVINL uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+LDPC_DEVINL void mbar_init(uint64_t *bar, const int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+LDPC_DEVINL void mbar_expect_tx(uint64_t *bar, const uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+LDPC_DEVINL void tma_load_1d(void *dst, const void *src, const uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+LDPC_DEVINL void mbar_wait(uint64_t *bar, const uint32_t parity)
+{
+    asm volatile("{\n .reg .pred P1;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n @P1 bra DONE;\n bra LAB_WAIT;\n DONE:\n }"
+                 :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 // a2: four raw channel samples y = x(1 + sigma n) of block b (src/decodeMinSum.cpp:216), from the

@@ -50,8 +50,8 @@ enum { X2_EXACT = 0, X2_CERT = 2, X2_UNCERT = 3 };
 
 static inline size_t ms_x2_smem_bytes(const CodeDev &c)
 {
-    return ((size_t)64 + 4 * ((size_t)c.dvN + 2 * (size_t)c.N) + 8 * (size_t)((c.N + 31) / 32) + 15) & ~(size_t)15;
-}
+    return (((size_t)64 + 4 * ((size_t)c.dvN + 2 * (size_t)c.N) + 8 * (size_t)((c.N + 31) / 32) + 15) & ~(size_t)15) + 2 * (size_t)c.N + 16;
+}                                                                                 // ... + staging of two frames' packed levels (Q <= 8) + the mbarrier
 
 // schedule word of step group g of row j.  The second pass re-reads the row's words through the `volatile` form: ptxas
 // otherwise keeps the first pass's 32 offsets alive (merging the loads) and spills them around the 32 c2v registers.
@@ -149,11 +149,12 @@ LDPC_DEVINL uint32_t x2_check_row(unsigned char *msgb, const int slot, const uin
 
 // Lean channel front ends of the min-sum family (fp32 conditioning): the sample source is a launch constant,
 // so each source gets its own straight-line code instead of raw_samples4's per-sample dispatch through doubles.
-enum { SRC_PHILOX = 0, SRC_PHILOX_FAST = 1, SRC_Q8 = 2, SRC_OTHER = 3, SRC_QP = 4 };
+enum { SRC_PHILOX = 0, SRC_PHILOX_FAST = 1, SRC_Q8 = 2, SRC_OTHER = 3, SRC_QP = 4, SRC_QP_STAGED = 5 };
 
+// `staged`: SRC_QP_STAGED only, the frame's packed words in shared memory
 template <int SRC, bool HASCW>
 LDPC_DEVINL void ms_cond4_f32(const FrameIO &io, const DecParams &p, const CodeDev &c, const long long f, const uint8_t *cw, const int b,
-                              const uint32_t qflags, const bool fcond, float (&vf)[4])
+                              const uint32_t qflags, const bool fcond, float (&vf)[4], const uint32_t *staged = nullptr)
 {
     const int i0 = 4 * b;
     if (SRC == SRC_PHILOX) {                                   // same values as raw_samples4 + condition_ms_f32, bit for bit
@@ -177,9 +178,9 @@ LDPC_DEVINL void ms_cond4_f32(const FrameIO &io, const DecParams &p, const CodeD
             const int k = (int)(signed char)((w >> (8 * q)) & 0xffu);
             vf[q] = (k >= 32) ? p.Ymax_f : (k <= -32) ? -p.Ymax_f : (float)__dmul_rn((double)k, p.ms_step);
         }
-    } else if (SRC == SRC_QP) {                                // bit-packed quantiser levels
+    } else if (SRC == SRC_QP || SRC == SRC_QP_STAGED) {        // bit-packed quantiser levels
         double y4[4];
-        packed_levels4(io, p, c.N, f, b, y4);
+        if (SRC == SRC_QP_STAGED) packed_levels4_at<true>(staged, p, b, y4); else packed_levels4(io, p, c.N, f, b, y4);
 #pragma unroll
         for (int q = 0; q < 4; q++) vf[q] = (float)y4[q];
     } else {
@@ -219,10 +220,16 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
     uint32_t *yq = S + N;                                                         // [N]
     uint32_t *dbits = yq + N;                                                     // [2][nwords]
     unsigned char *msgb = reinterpret_cast<unsigned char *>(msg);
+    unsigned char *stage = smem_raw + (((size_t)64 + 4 * ((size_t)DV * N + 2 * (size_t)N) + 8 * (size_t)nwords + 15) & ~(size_t)15);   // [2][frame bytes <= N]
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(stage + 2 * N);
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, M = c.M;
     const uint32_t qflags = p.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES);
     const bool fcond = !io.y || io.y_dtype != LDPC_GPU_DT_F64;
-    const int src = ms_sample_source(io, p, N);
+    int src = ms_sample_source(io, p, N);
+    // bit-packed levels are staged one pair ahead by the TMA unit when a frame is a whole number of 16-byte units
+    const uint32_t fbytes = (uint32_t)(((size_t)N * p.Q) >> 3);
+    if (src == SRC_QP && (fbytes & 15u) == 0 && ((size_t)io.y & 15) == 0 && fbytes <= (uint32_t)N) src = SRC_QP_STAGED;
+    uint32_t stage_phase = 0;
     const bool has_row = tid < M;
     const int slot = has_row ? (int)__ldg(&c.row_slot[tid]) : 0;
     const long long npairs = (io.n_frames + 1) / 2;
@@ -236,8 +243,8 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
         int unca = 0, uncb = 0;
         for (int b = tid; b < nblk; b += nt) {
             float va[4], vb[4];
-            ms_cond4_f32<SRC, HASCW>(io, p, c, fa, cwa, b, qflags, fcond, va);
-            ms_cond4_f32<SRC, HASCW>(io, p, c, fb, cwb, b, qflags, fcond, vb);
+            ms_cond4_f32<SRC, HASCW>(io, p, c, fa, cwa, b, qflags, fcond, va, reinterpret_cast<const uint32_t *>(stage));
+            ms_cond4_f32<SRC, HASCW>(io, p, c, fb, cwb, b, qflags, fcond, vb, reinterpret_cast<const uint32_t *>(stage + fbytes));
             const uint2 cc = __ldg(reinterpret_cast<const uint2 *>(c.col_of_var) + b);
             uint32_t niba = 0, nibb = 0;
 #pragma unroll
@@ -271,6 +278,17 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
         if (lane == 0) { if (unca) atomicAdd(&fs[0].uncoded, unca); if (uncb) atomicAdd(&fs[1].uncoded, uncb); }
     };
 
+    auto stage_pair = [&](const long long pr) {                                    // one thread: both frames of pair pr -> stage[]
+        const long long fa = 2 * pr, fb = (2 * pr + 1 < io.n_frames) ? 2 * pr + 1 : 2 * pr;
+        mbar_expect_tx(mbar, 2u * fbytes);
+        tma_load_1d(stage, reinterpret_cast<const unsigned char *>(io.y) + (size_t)fa * fbytes, fbytes, mbar);
+        tma_load_1d(stage + fbytes, reinterpret_cast<const unsigned char *>(io.y) + (size_t)fb * fbytes, fbytes, mbar);
+    };
+    if (src == SRC_QP_STAGED) {
+        if (tid == 0) mbar_init(mbar, 1);
+        __syncthreads();
+        if (tid == 0 && (long long)blockIdx.x < npairs) stage_pair(blockIdx.x);
+    }
     for (long long pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
         const long long fa = 2 * pr, fb = (2 * pr + 1 < io.n_frames) ? 2 * pr + 1 : 2 * pr;   // a dead lane replays frame fa, unreported
         const bool live_b = 2 * pr + 1 < io.n_frames;
@@ -279,12 +297,14 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
         if (tid < 8) st[tid] = 0;
         if (p.T == 0) for (int w = tid; w < 2 * nwords; w += nt) dbits[w] = 0u;
         __syncthreads();
+        if (src == SRC_QP_STAGED) { mbar_wait(mbar, stage_phase); stage_phase ^= 1u; }   // this pair's levels have landed
         if (cwa || cwb) {                                                         // launch constants: one straight-line front end per source
             switch (src) {
             case SRC_PHILOX:      gen_pair(std::integral_constant<int, SRC_PHILOX>(), std::true_type(), fa, fb, cwa, cwb); break;
             case SRC_PHILOX_FAST: gen_pair(std::integral_constant<int, SRC_PHILOX_FAST>(), std::true_type(), fa, fb, cwa, cwb); break;
             case SRC_Q8:          gen_pair(std::integral_constant<int, SRC_Q8>(), std::true_type(), fa, fb, cwa, cwb); break;
             case SRC_QP:          gen_pair(std::integral_constant<int, SRC_QP>(), std::true_type(), fa, fb, cwa, cwb); break;
+            case SRC_QP_STAGED:   gen_pair(std::integral_constant<int, SRC_QP_STAGED>(), std::true_type(), fa, fb, cwa, cwb); break;
             default:              gen_pair(std::integral_constant<int, SRC_OTHER>(), std::true_type(), fa, fb, cwa, cwb); break;
             }
         } else {
@@ -293,12 +313,15 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
             case SRC_PHILOX_FAST: gen_pair(std::integral_constant<int, SRC_PHILOX_FAST>(), std::false_type(), fa, fb, cwa, cwb); break;
             case SRC_Q8:          gen_pair(std::integral_constant<int, SRC_Q8>(), std::false_type(), fa, fb, cwa, cwb); break;
             case SRC_QP:          gen_pair(std::integral_constant<int, SRC_QP>(), std::false_type(), fa, fb, cwa, cwb); break;
+            case SRC_QP_STAGED:   gen_pair(std::integral_constant<int, SRC_QP_STAGED>(), std::false_type(), fa, fb, cwa, cwb); break;
             default:              gen_pair(std::integral_constant<int, SRC_OTHER>(), std::false_type(), fa, fb, cwa, cwb); break;
             }
         }
 #pragma unroll
         for (int e = 0; e < DC; e++) v[e] = 0u;                                   // c2v = 0, S = y: the first v2c is the channel value (:364-370)
         __syncthreads();
+        // everybody has read the staged levels: the next pair's can land while this one iterates
+        if (src == SRC_QP_STAGED && tid == 0 && pr + gridDim.x < npairs) stage_pair(pr + gridDim.x);
 
         // certificate state of the two frames: every thread runs the same few-instruction state machine on the same shared
         // flag words, so no thread has to publish a decision and no barrier is added.  Flag words are double-buffered by
