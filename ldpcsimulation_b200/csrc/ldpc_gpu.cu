@@ -1574,7 +1574,7 @@ extern "C" int ldpc_gpu_nb_decoder_create(const ldpc_gpu_nb_code *c, int num_ite
         (rc = up(c->inv.data(), c->inv.size(), (const void **)&v.inv))) { ldpc_gpu_nb_decoder_destroy(d); return rc; }
     int n_sm = 0; cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
     d->grid = 2 * n_sm;
-    d->ws_stride = ((2 * (size_t)M * dcm + (size_t)N) * c->q + ((size_t)N + 7) / 8 + 31) & ~(size_t)31;        // doubles
+    d->ws_stride = ((4 * (size_t)M * dcm + (size_t)N) * c->q + ((size_t)N + 7) / 8 + 31) & ~(size_t)31;        // doubles
     if (cudaMalloc(&d->d_ws, d->ws_stride * sizeof(double) * d->grid) != cudaSuccess || cudaMalloc(&d->d_counters, sizeof(unsigned long long) * CNT_N) != cudaSuccess ||
         cudaStreamCreateWithFlags(&d->st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&d->k0) != cudaSuccess || cudaEventCreate(&d->k1) != cudaSuccess) {
         ldpc_gpu_nb_decoder_destroy(d); return set_err(LDPC_GPU_ERR_NOMEM, "non-binary decoder: allocation failed");
