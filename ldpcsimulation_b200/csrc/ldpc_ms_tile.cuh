@@ -112,12 +112,29 @@ __global__ void __launch_bounds__(NT_MAX, 1) ms_tile_kernel(const CodeDev c, con
             const bool last = (it == p.T - 1);
             if (last) for (int w = tid; w < FI * nwords; w += nt) dbits[w] = 0u;
             // ---- check-node phase: (row, group of FPT frame lanes) per thread ----------------------------
+            // fp32: the row's weight and index words are fetched one trip ahead: cn_deg -> index words -> gather is otherwise a chain
+            // of two L2 latencies in front of every DRAM gather, with every warp waiting in long_scoreboard (r1j capture).  (The fp64
+            // instantiation has no registers to spare for it: it spilled and lost 14 %.)
+            constexpr bool AHEAD = sizeof(Real) == 4;
+            int deg_n = 0; uint4 w_n[NG];
+            if (AHEAD && tid < M * LPN) {
+                const int j0 = tid / LPN;
+                deg_n = c.cn_deg[j0];
+#pragma unroll
+                for (int g = 0; g < NG; g++) if (g * VPL < deg_n) w_n[g] = __ldg(&cnv[(size_t)g * M + j0]);
+            }
             for (int t = tid; t < M * LPN; t += nt) {
                 const int j = t / LPN, fl = (t % LPN) * FPT;
-                const int deg = c.cn_deg[j];
+                const int deg = AHEAD ? deg_n : (int)c.cn_deg[j];
                 uint4 w[NG];
 #pragma unroll
-                for (int g = 0; g < NG; g++) if (g * VPL < deg) w[g] = __ldg(&cnv[(size_t)g * M + j]);
+                for (int g = 0; g < NG; g++) { if (AHEAD) w[g] = w_n[g]; else if (g * VPL < deg) w[g] = __ldg(&cnv[(size_t)g * M + j]); }
+                if (AHEAD && t + nt < M * LPN) {
+                    const int jn = (t + nt) / LPN;
+                    deg_n = c.cn_deg[jn];
+#pragma unroll
+                    for (int g = 0; g < NG; g++) if (g * VPL < deg_n) w_n[g] = __ldg(&cnv[(size_t)g * M + jn]);
+                }
                 PK v[DCMAX];
 #pragma unroll
                 for (int k = 0; k < DCMAX; k++) if (k < deg) v[k] = *reinterpret_cast<const PK *>(&msg[(size_t)IdxVec<IdxT>::get(w[k / VPL], k % VPL) * FI + fl]);
@@ -153,9 +170,11 @@ __global__ void __launch_bounds__(NT_MAX, 1) ms_tile_kernel(const CodeDev c, con
             __syncthreads();
             // ---- variable-node phase: (variable, group of FPT frame lanes) per thread ---------------------
             // (two variables per trip was measured slower: 128 registers are not enough for both, 6.3 vs 7.1 Gbit/s)
+            int vdeg_n = (AHEAD && tid < N * LPN) ? (int)c.vn_deg[tid / LPN] : 0;     // one trip ahead, as above
             for (int t = tid; t < N * LPN; t += nt) {
                 const int i = t / LPN, fl = (t % LPN) * FPT;
-                const int deg = c.vn_deg[i];
+                const int deg = AHEAD ? vdeg_n : (int)c.vn_deg[i];
+                if (AHEAD && t + nt < N * LPN) vdeg_n = c.vn_deg[(t + nt) / LPN];
                 PK cm[DVMAX];
                 PK sum = *reinterpret_cast<const PK *>(&yq[(size_t)i * FI + fl]);
 #pragma unroll
