@@ -2,7 +2,7 @@
 // E=226799: 3.9 MB of fp32 message traffic per frame-iteration).  This path is HBM-bound, so the
 // layout is chosen for the memory system rather than for shared memory:
 //
-//   one CTA owns a TILE of FI frames (FI * sizeof(Real) = 32 bytes, one DRAM sector) and keeps
+//   one CTA owns a TILE of FI frames (FI * sizeof(Real) = LDPC_TILE_BYTES, one 128-byte line) and keeps
 //       msg[(s*N + i) * FI + fl]     yq[i * FI + fl]          fl = frame lane inside the tile
 //   in its slice of an HBM workspace.  A thread is (node, fl); a warp is 32/FI consecutive nodes x FI
 //   frames.  A variable warp therefore touches 128 contiguous bytes per slot, and a check warp's
@@ -20,11 +20,12 @@
 namespace ldpc {
 
 // Bytes of one (edge, tile) entry = FI * sizeof(Real), and bytes one thread moves per access (FPT frames).
-// 64-byte entries moved as 16-byte vectors: a warp's gather is 8 rows x 64 B = 512 B per instruction, as
-// in a streaming copy.  Measured on DVB-S2 fp32 (profiles/r1_summary.md): 32-byte entries, 4-byte accesses
-// 52 % of the HBM copy peak (all warps in long_scoreboard, 32 KB in flight per SM); 64-byte entries alone +3 %.
+// 128-byte entries (one full line: 32 fp32 / 16 fp64 frames per tile) moved as 16-byte vectors.  Measured on DVB-S2 fp32: 32-byte
+// entries with 4-byte accesses 52 % of the HBM copy peak (all warps in long_scoreboard, 32 KB in flight per SM); 64-byte entries and
+// 16-byte accesses 67 % (profiles/r1_summary.md); row weight / index words fetched one trip ahead 70 %; 128-byte entries 72 % (7.7 Gbit/s;
+// needs the tile's decision words in the workspace instead of shared memory: FI x N bits; profiles/r2_summary.md).
 #ifndef LDPC_TILE_BYTES
-#define LDPC_TILE_BYTES 64
+#define LDPC_TILE_BYTES 128
 #endif
 template <typename Real> struct TileFI { enum { value = LDPC_TILE_BYTES / sizeof(Real) }; };
 template <typename Real, int W> struct alignas(sizeof(Real) * W) TilePack { Real x[W]; };
@@ -32,13 +33,14 @@ template <typename Real, int W> struct alignas(sizeof(Real) * W) TilePack { Real
 template <typename Real>
 static inline size_t ms_tile_state_bytes(const CodeDev &c)
 {
-    return (((size_t)c.dvN + c.N) * sizeof(Real) * TileFI<Real>::value + 255) & ~(size_t)255;
+    const size_t FI = TileFI<Real>::value;
+    return (((size_t)c.dvN + c.N) * sizeof(Real) * FI + 4 * FI * (size_t)((c.N + 31) / 32) + 255) & ~(size_t)255;   // messages, samples, decisions
 }
 template <typename Real>
 static inline size_t ms_tile_smem_bytes(const CodeDev &c)
 {
     const size_t FI = TileFI<Real>::value;
-    return ((16 * FI + 4 * FI * (size_t)((c.N + 31) / 32)) + 15) & ~(size_t)15;
+    return (16 * FI + 4 * (size_t)((c.N + 31) / 32) + 15) & ~(size_t)15;   // frame scratch + ONE frame's decision words (staging for finish_frame)
 }
 
 // DCMAX / DVMAX: compile-time bounds of the row / column weights (register arrays).
@@ -52,9 +54,11 @@ __global__ void __launch_bounds__(NT_MAX, 1) ms_tile_kernel(const CodeDev c, con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrameScratch *fs = reinterpret_cast<FrameScratch *>(smem_raw);                       // [FI]
     const int N = c.N, M = c.M, nwords = (N + 31) >> 5, nblk = (N + 3) >> 2;
-    uint32_t *dbits = reinterpret_cast<uint32_t *>(smem_raw + 16 * FI);                // [FI][nwords]
     Real *msg = reinterpret_cast<Real *>(io.workspace + (size_t)blockIdx.x * io.ws_stride);
     Real *yq = msg + (size_t)c.dvN * FI;
+    // [FI][nwords] hard decisions: in the workspace too (written in the last iteration only; FI x N bits of shared memory would cap FI)
+    uint32_t *dbits = reinterpret_cast<uint32_t *>(yq + (size_t)c.N * FI);
+    uint32_t *dstage = reinterpret_cast<uint32_t *>(smem_raw + 16 * FI);                 // [nwords]
     const int tid = threadIdx.x, nt = blockDim.x;
     const uint4 *cnv = reinterpret_cast<const uint4 *>(c.cn_pos);
     const Real INF = real_inf<Real>();
@@ -207,7 +211,9 @@ __global__ void __launch_bounds__(NT_MAX, 1) ms_tile_kernel(const CodeDev c, con
         for (int fl = 0; fl < FI; fl++) {
             if (f0 + fl >= io.n_frames) break;                       // uniform: dead lanes are not reported
             const uint8_t *cw = codeword_row(io, c, f0 + fl);
-            finish_frame(c, p, io, f0 + fl, cw, dbits + fl * nwords, &fs[fl], p.T, -1, 0, 0, 1, -1, tot);
+            for (int w = tid; w < nwords; w += nt) dstage[w] = __ldcg(&dbits[fl * nwords + w]);   // (set by L2 atomics: read at L2)
+            __syncthreads();
+            finish_frame(c, p, io, f0 + fl, cw, dstage, &fs[fl], p.T, -1, 0, 0, 1, -1, tot);
         }
     }
     if (tid == 0) tot.flush(io.counters);
