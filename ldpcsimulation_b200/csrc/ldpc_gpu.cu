@@ -626,9 +626,11 @@ geometry:
     if (d->gstate) {
         // HBM-resident state: enough CTAs to fill the SMs, bounded so the workspace stays modest
         d->ws_stride = (d->ws_stride + 255) & ~(size_t)255;
-        const size_t budget = (size_t)8 << 30;
+        const size_t budget = (size_t)12 << 30;
         while (d->grid_full > d->n_sm && (size_t)d->grid_full * d->ws_stride > budget) d->grid_full -= d->n_sm;
-        CU_TRY(cudaMalloc(&d->d_ws, (size_t)d->grid_full * d->ws_stride));
+        // two workspaces: the host pipeline keeps one launch per slot in flight, and CTA b of the second may start while CTA b of
+        // the first is still running
+        CU_TRY(cudaMalloc(&d->d_ws, 2 * (size_t)d->grid_full * d->ws_stride));
     }
     return LDPC_GPU_OK;
 }
@@ -840,7 +842,8 @@ static int launch(ldpc_gpu_decoder *d, const DecParams &p, const FrameIO &io, cu
 {
     const long long want = std::min<long long>((io.n_frames + d->frames_per_cta - 1) / d->frames_per_cta, d->grid_full);
     if (want <= 0) return LDPC_GPU_OK;
-    FrameIO io2 = io; io2.workspace = d->d_ws; io2.ws_stride = d->ws_stride;
+    FrameIO io2 = io; io2.ws_stride = d->ws_stride;
+    io2.workspace = d->d_ws ? d->d_ws + ((st == d->slot[1].st) ? (size_t)d->grid_full * d->ws_stride : 0) : nullptr;
     if (d->x2) {
         if ((size_t)io.n_frames > d->redo_cap) {          // grows only (streams of this decoder may still read the old list: drain them)
             for (Slot &s : d->slot) if (s.st) CU_TRY(cudaStreamSynchronize(s.st));
