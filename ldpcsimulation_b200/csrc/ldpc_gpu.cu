@@ -285,6 +285,7 @@ struct ldpc_gpu_decoder {
     CodeDev dev;                 // device pointers owned below
     std::vector<void *> owned;
     KernelFn fn = nullptr;
+    KernelFn fn_staged = nullptr;   // exact-lattice kernel, bit-packed levels staged by the TMA unit (ldpc_ms_x2.cuh); same geometry as fn
     int block = 0, smem = 0, ctas_per_sm = 0, grid_full = 0;
     bool gstate = false; size_t ws_stride = 0; unsigned char *d_ws = nullptr;   // HBM-resident frame state
     int frames_per_cta = 1;                                                      // > 1: frame-interleaved tile kernel
@@ -496,6 +497,7 @@ static int pick_kernel(ldpc_gpu_decoder *d)
                     const int variant = xv ? atoi(xv) : 1;
                     d->fn = variant == 0 ? (KernelFn)ms_x2_kernel<32, 6, 2048, 384, 2, true>
                           : variant == 2 ? (KernelFn)ms_x2_kernel<32, 6, 2048, 384, 3, false> : (KernelFn)ms_x2_kernel<32, 6, 2048, 384, 2, false>;
+                    if (variant == 1 && !getenv("LDPC_GPU_NO_TMA")) d->fn_staged = (KernelFn)ms_x2_kernel<32, 6, 2048, 384, 2, false, true>;
                     smem = ms_x2_smem_bytes(v);
                 }
             }
@@ -611,6 +613,7 @@ geometry:
     if ((d->cfg.flags & LDPC_GPU_F_CERT_STOP) && !d->x2)
         return set_err(LDPC_GPU_ERR_UNSUPPORTED, "LDPC_GPU_F_CERT_STOP needs LDPC_GPU_PREC_F16X2 on an exact lattice (plain / offset min-sum, dyadic quantiser step, the 802.3an H)");
     CU_TRY(cudaFuncSetAttribute((const void *)d->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (d->fn_staged) CU_TRY(cudaFuncSetAttribute((const void *)d->fn_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes fa;
     CU_TRY(cudaFuncGetAttributes(&fa, (const void *)d->fn));
     const int by_regs = (65536 / std::max(1, fa.numRegs)) & ~31;      // one CTA must fit the register file
@@ -859,7 +862,10 @@ static int launch(ldpc_gpu_decoder *d, const DecParams &p, const FrameIO &io, cu
         io2.redo_total = d->d_redo_total;
         CU_TRY(cudaMemsetAsync(io2.redo_count, 0, sizeof(unsigned int), st));
     }
-    d->fn<<<(unsigned)want, d->block, d->smem, st>>>(d->dev, p, io2);
+    KernelFn fn = d->fn;
+    if (d->fn_staged && io2.y && io2.y_dtype == LDPC_GPU_DT_QP && ((size_t)io2.y & 15) == 0 && ((((size_t)d->N * d->cfg.Q) >> 3) & 15) == 0 &&
+        (((size_t)d->N * d->cfg.Q) >> 3) <= (size_t)d->N) fn = d->fn_staged;
+    fn<<<(unsigned)want, d->block, d->smem, st>>>(d->dev, p, io2);
     CU_TRY(cudaGetLastError());
     d->last_launches++;
     if (d->x2) {                                          // how many frames the packed kernel could not certify: read by redo_after_sync

@@ -207,7 +207,10 @@ LDPC_DEVINL int ms_sample_source(const FrameIO &io, const DecParams &p, const in
     return SRC_OTHER;
 }
 
-template <int DC, int DV, int NFIX, int NT_MAX, int MINB, bool KEEP>
+// STAGED: the launch's samples are bit-packed levels whose frames are whole numbers of 16-byte units (checked by the host): they are
+// staged one frame pair ahead by the TMA unit.  A separate instantiation, so that the staging state costs the other sources no registers
+// (as a run-time branch of one kernel it pushed the register allocation into spills: 4.13 -> 4.26 ms per 65 536 frames on the Philox source).
+template <int DC, int DV, int NFIX, int NT_MAX, int MINB, bool KEEP, bool STAGED = false>
 __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, const DecParams p, const FrameIO io)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -225,10 +228,8 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, M = c.M;
     const uint32_t qflags = p.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES);
     const bool fcond = !io.y || io.y_dtype != LDPC_GPU_DT_F64;
-    int src = ms_sample_source(io, p, N);
-    // bit-packed levels are staged one pair ahead by the TMA unit when a frame is a whole number of 16-byte units
-    const uint32_t fbytes = (uint32_t)(((size_t)N * p.Q) >> 3);
-    if (src == SRC_QP && (fbytes & 15u) == 0 && ((size_t)io.y & 15) == 0 && fbytes <= (uint32_t)N) src = SRC_QP_STAGED;
+    const int src = STAGED ? (int)SRC_QP_STAGED : ms_sample_source(io, p, N);
+    const uint32_t fbytes = (uint32_t)(((size_t)N * p.Q) >> 3);                    // STAGED: bytes of one frame's packed levels
     uint32_t stage_phase = 0;
     const bool has_row = tid < M;
     const int slot = has_row ? (int)__ldg(&c.row_slot[tid]) : 0;
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
         tma_load_1d(stage, reinterpret_cast<const unsigned char *>(io.y) + (size_t)fa * fbytes, fbytes, mbar);
         tma_load_1d(stage + fbytes, reinterpret_cast<const unsigned char *>(io.y) + (size_t)fb * fbytes, fbytes, mbar);
     };
-    if (src == SRC_QP_STAGED) {
+    if (STAGED) {
         if (tid == 0) mbar_init(mbar, 1);
         __syncthreads();
         if (tid == 0 && (long long)blockIdx.x < npairs) stage_pair(blockIdx.x);
@@ -297,14 +298,16 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
         if (tid < 8) st[tid] = 0;
         if (p.T == 0) for (int w = tid; w < 2 * nwords; w += nt) dbits[w] = 0u;
         __syncthreads();
-        if (src == SRC_QP_STAGED) { mbar_wait(mbar, stage_phase); stage_phase ^= 1u; }   // this pair's levels have landed
-        if (cwa || cwb) {                                                         // launch constants: one straight-line front end per source
+        if (STAGED) { mbar_wait(mbar, stage_phase); stage_phase ^= 1u; }          // this pair's levels have landed
+        if (STAGED) {
+            if (cwa || cwb) gen_pair(std::integral_constant<int, SRC_QP_STAGED>(), std::true_type(), fa, fb, cwa, cwb);
+            else gen_pair(std::integral_constant<int, SRC_QP_STAGED>(), std::false_type(), fa, fb, cwa, cwb);
+        } else if (cwa || cwb) {                                                  // launch constants: one straight-line front end per source
             switch (src) {
             case SRC_PHILOX:      gen_pair(std::integral_constant<int, SRC_PHILOX>(), std::true_type(), fa, fb, cwa, cwb); break;
             case SRC_PHILOX_FAST: gen_pair(std::integral_constant<int, SRC_PHILOX_FAST>(), std::true_type(), fa, fb, cwa, cwb); break;
             case SRC_Q8:          gen_pair(std::integral_constant<int, SRC_Q8>(), std::true_type(), fa, fb, cwa, cwb); break;
             case SRC_QP:          gen_pair(std::integral_constant<int, SRC_QP>(), std::true_type(), fa, fb, cwa, cwb); break;
-            case SRC_QP_STAGED:   gen_pair(std::integral_constant<int, SRC_QP_STAGED>(), std::true_type(), fa, fb, cwa, cwb); break;
             default:              gen_pair(std::integral_constant<int, SRC_OTHER>(), std::true_type(), fa, fb, cwa, cwb); break;
             }
         } else {
@@ -313,7 +316,6 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
             case SRC_PHILOX_FAST: gen_pair(std::integral_constant<int, SRC_PHILOX_FAST>(), std::false_type(), fa, fb, cwa, cwb); break;
             case SRC_Q8:          gen_pair(std::integral_constant<int, SRC_Q8>(), std::false_type(), fa, fb, cwa, cwb); break;
             case SRC_QP:          gen_pair(std::integral_constant<int, SRC_QP>(), std::false_type(), fa, fb, cwa, cwb); break;
-            case SRC_QP_STAGED:   gen_pair(std::integral_constant<int, SRC_QP_STAGED>(), std::false_type(), fa, fb, cwa, cwb); break;
             default:              gen_pair(std::integral_constant<int, SRC_OTHER>(), std::false_type(), fa, fb, cwa, cwb); break;
             }
         }
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
         for (int e = 0; e < DC; e++) v[e] = 0u;                                   // c2v = 0, S = y: the first v2c is the channel value (:364-370)
         __syncthreads();
         // everybody has read the staged levels: the next pair's can land while this one iterates
-        if (src == SRC_QP_STAGED && tid == 0 && pr + gridDim.x < npairs) stage_pair(pr + gridDim.x);
+        if (STAGED && tid == 0 && pr + gridDim.x < npairs) stage_pair(pr + gridDim.x);
 
         // certificate state of the two frames: every thread runs the same few-instruction state machine on the same shared
         // flag words, so no thread has to publish a decision and no barrier is added.  Flag words are double-buffered by
