@@ -184,19 +184,12 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_quad_kernel(const CodeDev c, 
             }
             __syncthreads();
             // ---- variable-node phase: src/decodeMinSum.cpp:452-476, one storage column x four frames per thread ----
-            for (int col = tid; col < N; col += nt) {
-                int i = 0;
-                if (!REGV || last) i = (int)__ldg(&c.quad_var_of_col[col]);
-                const int dv = REGV ? DV : (int)c.vn_deg[i];
-                float4 sum = y4[col];
-                const float4 *mp = msg4 + col;
-#pragma unroll
-                for (int s = 0; s < DV; s++) if (REGV || s < dv) {                   // nlist order
-                    const float4 m = mp[s * N];
-                    sum = make_float4(sum.x + m.x, sum.y + m.y, sum.z + m.z, sum.w + m.w);
-                }
+            // two columns per trip with all loads issued before the first add: the phase is bound by the latency of its dependent
+            // LDS.128 (r2 capture: 42 % short_scoreboard), not by their number
+            auto vn_finish = [&](const int col, const float4 sum) {
                 S4[col] = sum;
                 if (last) {
+                    const int i = (int)__ldg(&c.quad_var_of_col[col]);
 #pragma unroll
                     for (int q = 0; q < FI; q++) {
                         const float x = q4_get(sum, q);
@@ -207,6 +200,27 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_quad_kernel(const CodeDev c, 
                         }
                     }
                 }
+            };
+            for (int col = tid; col < N; col += 2 * nt) {
+                const int col1 = col + nt;
+                const bool two = col1 < N;
+                const int cb = two ? col1 : col;                                     // (a lone last column is simply read twice)
+                int dv0 = DV, dv1 = DV;
+                if (!REGV) { dv0 = (int)c.vn_deg[__ldg(&c.quad_var_of_col[col])]; dv1 = (int)c.vn_deg[__ldg(&c.quad_var_of_col[cb])]; }
+                float4 m0[DV], m1v[DV];
+                float4 s0 = y4[col], s1 = y4[cb];
+#pragma unroll
+                for (int s = 0; s < DV; s++) {
+                    if (REGV || s < dv0) m0[s] = msg4[s * N + col];
+                    if (REGV || s < dv1) m1v[s] = msg4[s * N + cb];
+                }
+#pragma unroll
+                for (int s = 0; s < DV; s++) {                                       // nlist order
+                    if (REGV || s < dv0) s0 = make_float4(s0.x + m0[s].x, s0.y + m0[s].y, s0.z + m0[s].z, s0.w + m0[s].w);
+                    if (REGV || s < dv1) s1 = make_float4(s1.x + m1v[s].x, s1.y + m1v[s].y, s1.z + m1v[s].z, s1.w + m1v[s].w);
+                }
+                vn_finish(col, s0);
+                if (two) vn_finish(col1, s1);
             }
             __syncthreads();
         }
