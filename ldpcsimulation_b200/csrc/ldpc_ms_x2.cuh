@@ -375,13 +375,20 @@ __global__ void __launch_bounds__(NT_MAX, MINB) ms_x2_kernel(const CodeDev c, co
                 const int cp = tid + rr * NT_MAX;
                 if (cp >= N / 2) break;
                 const int col = 2 * cp;
-                const uint2 y2 = *reinterpret_cast<const uint2 *>(&yq[col]);
-                __half2 s0 = h2_from(y2.x), s1 = h2_from(y2.y);
+                // S = y + sum_s c2v as a balanced tree: on the lattice the additions are exact, so their order is free, and the tree has
+                // depth 3 instead of 7
+                __half2 a0[DV + 1], a1[DV + 1];
+                { const uint2 y2 = *reinterpret_cast<const uint2 *>(&yq[col]); a0[0] = h2_from(y2.x); a1[0] = h2_from(y2.y); }
 #pragma unroll
                 for (int s = 0; s < DV; s++) {
                     const uint2 cm = *reinterpret_cast<const uint2 *>(&msg[s * N + col]);
-                    s0 = __hadd2(s0, h2_from(cm.x)); s1 = __hadd2(s1, h2_from(cm.y));
+                    a0[s + 1] = h2_from(cm.x); a1[s + 1] = h2_from(cm.y);
                 }
+#pragma unroll
+                for (int w = 1; w < DV + 1; w *= 2)
+#pragma unroll
+                    for (int s = 0; s + w < DV + 1; s += 2 * w) { a0[s] = __hadd2(a0[s], a0[s + w]); a1[s] = __hadd2(a1[s], a1[s + w]); }
+                const __half2 s0 = a0[0], s1 = a1[0];
                 *reinterpret_cast<uint2 *>(&S[col]) = make_uint2(h2_bits(s0), h2_bits(s1));
                 if (last) {
                     const unsigned vv = __ldg(reinterpret_cast<const unsigned *>(c.var_of_col) + cp);
