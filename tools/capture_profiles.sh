@@ -1,3 +1,5 @@
+# The GPU-box recipe behind profiles/r2_*: every capture only after the same command ran clean without ncu; .ncu-rep files are
+# exported to CSV on the box (gpurun returns at most 64 MiB).  Usage: gpurun --timeout 2400 -- 'bash tools/capture_profiles.sh'
 set -x
 cap() { # name regex cmd...
   name=$1; rx=$2; shift 2
