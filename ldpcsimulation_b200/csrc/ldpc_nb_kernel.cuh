@@ -16,7 +16,7 @@
 // the test oracle, which this kernel equals bit for bit.
 //
 // One CTA per frame; messages live in an HBM / L2 workspace slice per CTA (E q doubles each way), one thread per check in the
-// check phase, one per variable in the variable phase.  The check update keeps its three q-vectors (the two operands and the result
+// check phase, q lanes per variable in the variable phase.  The check update keeps its three q-vectors (the two operands and the result
 // of one (min, max)-convolution) in registers with compile-time indices -- the first cut indexed A / F / B[8][q] dynamically, i.e.
 // in local memory: 0.27 Gbit/s on the GF(16) code -- and stores only the forward / backward vectors the outputs need
 // (F_1 .. F_(dc-2), B_(dc-2) .. B_1: 3 (dc - 2) convolutions per check instead of 3 dc - 4; the skipped ones feed no output).
@@ -160,30 +160,36 @@ __global__ void __launch_bounds__(256, 2) nb_minmax_kernel(const NbCodeDev c, co
                     nb_conv<Q>(U, V, W);
                     emit(k, W);
                 }
+                // (a single call site for the convolution -- one loop over the three kinds of step -- cuts the 14.5 k instructions of this
+                // phase to a third, but ptxas then keeps the q-vectors in local memory: 1.8 x slower, measured)
             }
             __syncthreads();
             // ---- variable phase -----------------------------------------------------------------------------
-            for (int i = tid; i < N; i += nt) {
-                const int deg = c.vn_deg[i];
-                double post[Q];
-                for (int a = 0; a < Q; a++) post[a] = gamma[(size_t)i * Q + a];
-                for (int s = 0; s < deg; s++) {
-                    const int e = c.vn_edge[(size_t)i * c.dv_max + s];
-                    for (int a = 0; a < Q; a++) post[a] += beta[(size_t)e * Q + a];
+            // Q lanes per variable (lane a owns symbol value a): the q-vectors of an edge are read and written as one coalesced line,
+            // the minimum / first argmin over a are shuffle reductions inside the group of Q lanes (exact: min, and ties -> lowest a)
+            for (int base = 0; base < N * Q; base += nt) {
+                const int t = base + tid;
+                const bool valid = t < N * Q;
+                const int i = valid ? t / Q : 0, a = t % Q;
+                const int deg = valid ? (int)c.vn_deg[i] : 0;
+                const double g = gamma[(size_t)i * Q + a];
+                double post = g;
+                for (int s = 0; s < deg; s++) post += beta[(size_t)c.vn_edge[(size_t)i * c.dv_max + s] * Q + a];
+                double bv = post; int bi = a;
+#pragma unroll
+                for (int o = Q / 2; o; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
                 }
-                int best = 0;
-                for (int a = 1; a < Q; a++) if (post[a] < post[best]) best = a;
-                dsym[i] = (uint8_t)best;
-                for (int s = 0; s < deg; s++) {
-                    const int e = c.vn_edge[(size_t)i * c.dv_max + s];
-                    double mn = 0.0;
-                    for (int a = 0; a < Q; a++) {
-                        double v = gamma[(size_t)i * Q + a];
-                        for (int s2 = 0; s2 < deg; s2++) if (s2 != s) v += beta[(size_t)c.vn_edge[(size_t)i * c.dv_max + s2] * Q + a];
-                        alpha[(size_t)e * Q + a] = v;
-                        mn = (a == 0) ? v : fmin(mn, v);
-                    }
-                    for (int a = 0; a < Q; a++) alpha[(size_t)e * Q + a] -= mn;
+                if (valid && a == 0) dsym[i] = (uint8_t)bi;
+                for (int s = 0; s < c.dv_max; s++) {                                 // (uniform trip count: the shuffles below need every lane)
+                    const bool on = s < deg;
+                    double v = g;
+                    for (int s2 = 0; s2 < deg; s2++) if (s2 != s && on) v += beta[(size_t)c.vn_edge[(size_t)i * c.dv_max + s2] * Q + a];
+                    double mn = v;
+#pragma unroll
+                    for (int o = Q / 2; o; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                    if (on) alpha[(size_t)c.vn_edge[(size_t)i * c.dv_max + s] * Q + a] = v - mn;
                 }
             }
             it++;
