@@ -52,6 +52,10 @@ WORKLOADS = {
                        text="BASELINE configs[0]: PEGReg504x1008.alist, float min-sum (decodeMinSum), T=50, Eb/N0=2.0 dB, R=0.5"),
     "ms_dvbs2": dict(code="dvbs2", variant="decodeMinSum", flags=[], cfg=dict(), T=10, snr_db=3.0, R=0.5, precision="f32", q8=None,
                      text="BASELINE configs[3]: dvbs2_1_2.alist (N=64800, E=226799), min-sum T=10, Eb/N0=3.0 dB: messages in HBM"),
+    "oms_dvbs2": dict(code="dvbs2", variant="decodeOffsetMinSum", flags=["quantizeSamples", "offsetMS"],
+                      cfg=dict(Ymax=1.9375, Q=5, delta=0.125), T=10, snr_db=3.0, R=0.5, precision="x2", q8=(1.9375, 5),
+                      text="BASELINE configs[3]: dvbs2_1_2.alist (N=64800, E=226799), offset min-sum (decodeOffsetMinSum: Ymax=1.9375 Q=5 delta=0.125) "
+                           "T=10, Eb/N0=3.0 dB: binary16 message tiles in HBM on the exact lattice, bit-identical to the fp64 instantiation (tests/test_gpu_tileh.py)"),
     "ngdbfhw_8023": dict(code="802_3_H", variant="NGDBFhw", flags=[], cfg=dict(), T=600, snr_db=4.5, R=R8023, precision="f64", q8=None,
                          text="BASELINE configs[2]: 802_3_H.alist, NGDBFhw (integer), T<=600 with early stop, Eb/N0=4.5 dB"),
     "smngdbf_8023": dict(code="802_3_H", variant="decodeSMNGDBF", flags=None, cfg=dict(num_iterations=100, alpha=0.3, theta=-0.525, windowsize=64),
@@ -509,12 +513,19 @@ def main():
         out, _ = short_value(wl, precision, 1 << 19, channel=abi.CHANNEL_FAST)
         extras["fast_channel"] = dict(out, note="LDPC_GPU_CHANNEL_FAST: SFU Box-Muller (lg2/sqrt/sin/cos.approx) instead of the CPU-reproducible polynomials")
     if not args.no_extras:
-        for name, frames in (("nms_8023", 1 << 19), ("oms_8023", 1 << 19), ("bp_8023", 1 << 17), ("ms_peg_t50", 1 << 18), ("ms_dvbs2", 1 << 13),
+        for name, frames in (("nms_8023", 1 << 19), ("oms_8023", 1 << 19), ("bp_8023", 1 << 17), ("ms_peg_t50", 1 << 18), ("ms_dvbs2", 1 << 13), ("oms_dvbs2", 18944),
                              ("ngdbfhw_8023", 1 << 18), ("smngdbf_8023", 1 << 16)):
             if name == wl:
                 continue
-            out, _ = short_value(name, WORKLOADS[name]["precision"], frames)
+            out, d3 = short_value(name, WORKLOADS[name]["precision"], frames)
             out["workload"] = WORKLOADS[name]["text"]
+            if WORKLOADS[name]["code"] == "dvbs2":           # HBM-bound: algorithmic bytes T (4E + N) b per frame against the measured copy peak
+                c3 = code_of("dvbs2")
+                bm = {"x2": 2, "f32": 4, "f64": 8}[WORKLOADS[name]["precision"]]
+                gbs = frames * WORKLOADS[name]["T"] * (4 * c3.E + c3.N) * bm / (out["kernel_ms_per_step"] * 1e-3) / 1e9
+                out["hbm"] = {"achieved_gbs": gbs, "peak_gbs": measured_peak()[0], "frac": gbs / measured_peak()[0], "message_bytes": bm}
+                if WORKLOADS[name]["precision"] == "x2":
+                    out["exact_lattice_kernel"], out["redo_frames"] = d3.stats()
             others[name] = out
     if not args.no_extras:                                   # BASELINE configs[4]: non-binary GF(16) min-max, frames sharded like everything else
         nbc = capi.NbCode(os.path.join(ROOT, "codes", "NB", "gf16.reg.1536.768.alist"))

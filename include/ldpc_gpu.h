@@ -89,9 +89,12 @@ extern "C" {
 /* ---- arithmetic of the message / metric path --------------------------- */
 #define LDPC_GPU_PREC_F64   0   /* parity instantiation: IEEE double, the reference's operation order */
 #define LDPC_GPU_PREC_F32   1   /* throughput instantiation: fp32 messages, same dataflow */
-#define LDPC_GPU_PREC_F16X2 2   /* min-sum family on regular scheduled codes only: two frames per thread in one
-                                   binary16 pair, v2c clamped to +-512.  NOT the reference's arithmetic: decisions
-                                   match on converging frames, BER/FER within confidence intervals */
+#define LDPC_GPU_PREC_F16X2 2   /* min-sum family, binary16 messages.  On an exact lattice (plain / offset min-sum, quantised samples with a
+                                   power-of-two quantiser unit) the results are the reference's bit for bit: two frames per lane on the 802.3an
+                                   H (csrc/ldpc_ms_x2.cuh), 64-frame binary16 message tiles in HBM for codes beyond one SM with dc, dv <= 8
+                                   (csrc/ldpc_ms_tileh.cuh, DVB-S2); frames that leave the exactly representable range are re-decoded by the
+                                   fp64 instantiation (ldpc_gpu_decoder_stats).  Off the lattice (802.3an H only): v2c clamped to +-512, NOT the
+                                   reference's arithmetic: decisions match on converging frames, BER/FER within confidence intervals */
 
 #define LDPC_GPU_DT_QP   4   /* the same quantiser levels, bit-packed: Q bits per sample (Q = cfg.Q, 2 <= Q <= 8), sample i of a frame in bits
                               * [iQ, (i+1)Q) of the frame's N*Q/8 bytes (little-endian bit order; N*Q must be a multiple of 32).  Code =
@@ -290,9 +293,9 @@ int  ldpc_gpu_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t 
 /* Timing of the last decode/simulate call on this decoder: kernel time from
  * CUDA events on the launching stream, and the number of kernel launches. */
 int  ldpc_gpu_last_timing(const ldpc_gpu_decoder *dec, double *kernel_ms, int64_t *launches);
-/* LDPC_GPU_PREC_F16X2 on an exact lattice (csrc/ldpc_ms_x2.cuh): *exact_lattice = 1 when the decoder runs the certified
- * two-frames-per-lane kernel, and *redo_frames = frames (since creation) it could not certify and handed to the fp64
- * instantiation.  Both optional. */
+/* LDPC_GPU_PREC_F16X2 on an exact lattice (csrc/ldpc_ms_x2.cuh, csrc/ldpc_ms_tileh.cuh): *exact_lattice = 1 when the decoder runs
+ * one of the binary16 kernels whose results are the reference's bit for bit, and *redo_frames = frames (since creation) it could
+ * not vouch for and handed to the fp64 instantiation.  Both optional. */
 int  ldpc_gpu_decoder_stats(const ldpc_gpu_decoder *dec, int64_t *redo_frames, int32_t *exact_lattice);
 /* Launch geometry the library chose (for DESIGN/roofline reporting). */
 int  ldpc_gpu_decoder_geometry(const ldpc_gpu_decoder *dec, int *grid, int *block, int *smem_bytes,

@@ -28,6 +28,7 @@
 #include "ldpc_ms_h2.cuh"
 #include "ldpc_ms_h2rc.cuh"
 #include "ldpc_ms_x2.cuh"
+#include "ldpc_ms_tileh.cuh"
 #include "ldpc_bf_kernels.cuh"
 #include "ldpc_sc_kernel.cuh"
 #include "ldpc_nb_kernel.cuh"
@@ -297,6 +298,7 @@ struct ldpc_gpu_decoder {
     int N = 0, M = 0;
     // exact-lattice packed kernel (ldpc_ms_x2.cuh): frames it cannot certify are decoded by an fp64 decoder on the same stream
     bool x2 = false; float x2_cap = 0, x2_m0 = 0;
+    bool x2_tile = false;        // ... its HBM-bound form (ldpc_ms_tileh.cuh): same redo protocol, no certificate
     ldpc_gpu_decoder *redo = nullptr;
     long long *d_redo_list = nullptr; size_t redo_cap = 0;
     unsigned int *d_redo_count = nullptr; unsigned long long *d_redo_total = nullptr;
@@ -321,6 +323,24 @@ static bool x2_lattice(const ldpc_gpu_decoder_cfg &c, int dv_min, int dv_max, fl
     const double m0_u = ceil((Yu + (dv_min - 1) * du) / (dv_min - 2));
     if ((dv_min - 1) * cap_u - Yu < m0_u || cap_u < m0_u) return false;
     *cap = (float)(cap_u * u); *m0 = (float)(m0_u * u);
+    return true;
+}
+
+// The HBM-bound form (ldpc_ms_tileh.cuh) runs T fixed iterations and needs the lattice and the cap only: every value stays an
+// integer multiple of u below 2^11 u while |c2v| <= C, Ymax + dv_max C <= 2047 u.
+static bool tile_lattice(const ldpc_gpu_decoder_cfg &c, int dv_max, float *cap)
+{
+    if (c.kind != LDPC_GPU_KIND_MINSUM || !(c.flags & LDPC_GPU_F_QUANTIZE_SAMPLES) || (c.flags & LDPC_GPU_F_NORMALIZED_MS)) return false;
+    if (c.Q < 2 || c.Q > 8 || !(c.Ymax > 0) || dv_max < 1) return false;
+    const double Yu = pow(2.0, c.Q) - 1.0, u = c.Ymax / Yu;
+    int ex;
+    if (frexp(u, &ex) != 0.5 || ex - 1 < -14 || ex - 1 > 4) return false;
+    const double du = (c.flags & LDPC_GPU_F_OFFSET_MS) ? c.delta / u : 0.0;
+    if (du < 0 || du != floor(du) || du > 64) return false;
+    double cap_u = floor((2047.0 - Yu) / dv_max);
+    if (const char *e = getenv("LDPC_GPU_X2_CAP_UNITS")) cap_u = std::min(cap_u, (double)atoi(e));   // test hook: a low cap exercises the redo path
+    if (cap_u < 1) return false;
+    *cap = (float)(cap_u * u);
     return true;
 }
 
@@ -481,6 +501,16 @@ static int pick_kernel(ldpc_gpu_decoder *d)
     if (kind == LDPC_GPU_KIND_MINSUM || kind == LDPC_GPU_KIND_BP || kind == LDPC_GPU_KIND_DDBMP) {
         if (v.dc_max > 64) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "message-passing kernels hold a row's signs in 64 bits: dc_max > 64");
         const int algo = kind == LDPC_GPU_KIND_MINSUM ? ALGO_MS : kind == LDPC_GPU_KIND_BP ? ALGO_BP : ALGO_DDBMP;
+        if (d->cfg.precision == LDPC_GPU_PREC_F16X2 && algo == ALGO_MS && v.dv_max <= 8 && v.dc_max <= 8 && tile_lattice(d->cfg, v.dv_max, &d->x2_cap) &&
+            (mp_smem_bytes<float>(v, algo) > (size_t)max_optin || getenv("LDPC_GPU_FORCE_HBM_STATE"))) {
+            // exact lattice, messages in HBM (DVB-S2-class codes): binary16 tile kernel, fp64 redo of the frames it cannot vouch for
+            d->x2 = true; d->x2_tile = true; d->gstate = true;
+            d->fn = v.idx16 ? (KernelFn)ms_tileh_kernel<uint16_t, 8, 8, 512> : (KernelFn)ms_tileh_kernel<uint32_t, 8, 8, 512>;
+            block = 512; d->frames_per_cta = TILEH_FI;
+            d->ws_stride = ms_tileh_state_bytes(v);
+            smem = ms_tileh_smem_bytes(v);
+            goto geometry;
+        }
         if (d->cfg.precision == LDPC_GPU_PREC_F16X2) {
             if (!(v.sched && v.regular_dc == 32 && v.regular_dv == 6 && v.N == 2048 && v.M <= 384))
                 return set_err(LDPC_GPU_ERR_UNSUPPORTED, "LDPC_GPU_PREC_F16X2 is built for regular (6,32) codes of length 2048 with a conflict-free schedule (the 802.3an H)");
@@ -610,7 +640,7 @@ static int pick_kernel(ldpc_gpu_decoder *d)
 geometry:
     if (smem > (size_t)max_optin)
         return set_err(LDPC_GPU_ERR_UNSUPPORTED, "shared-memory scratch (" + std::to_string(smem) + " B) exceeds one SM");
-    if ((d->cfg.flags & LDPC_GPU_F_CERT_STOP) && !d->x2)
+    if ((d->cfg.flags & LDPC_GPU_F_CERT_STOP) && (!d->x2 || d->x2_tile))
         return set_err(LDPC_GPU_ERR_UNSUPPORTED, "LDPC_GPU_F_CERT_STOP needs LDPC_GPU_PREC_F16X2 on an exact lattice (plain / offset min-sum, dyadic quantiser step, the 802.3an H)");
     CU_TRY(cudaFuncSetAttribute((const void *)d->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (d->fn_staged) CU_TRY(cudaFuncSetAttribute((const void *)d->fn_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -875,6 +905,18 @@ static int launch(ldpc_gpu_decoder *d, const DecParams &p, const FrameIO &io, cu
     return LDPC_GPU_OK;
 }
 
+// launch of the fp64 redo decoder over n frames (its own workspace when its state lives in HBM)
+static int launch_redo(ldpc_gpu_decoder *d, const DecParams &p, FrameIO io, long long n, cudaStream_t st)
+{
+    ldpc_gpu_decoder *r = d->redo;
+    io.workspace = r->d_ws; io.ws_stride = r->ws_stride;
+    const long long want = std::min<long long>((n + r->frames_per_cta - 1) / r->frames_per_cta, r->grid_full);
+    r->fn<<<(unsigned)want, r->block, r->smem, st>>>(r->dev, p, io);
+    CU_TRY(cudaGetLastError());
+    d->last_launches++;
+    return LDPC_GPU_OK;
+}
+
 // Exact-lattice kernel: after the stream of a launch has been synchronised, decode the frames it could not certify (about 5 in
 // 10^6 at the operating point) with the fp64 parity instantiation, same FrameIO, same stream.  *ran tells the caller whether
 // outputs changed.  Nothing is launched in the common case.
@@ -887,10 +929,7 @@ static int redo_after_sync(ldpc_gpu_decoder *d, const DecParams &p, const FrameI
     if (n == 0) return LDPC_GPU_OK;
     FrameIO io3 = io; io3.workspace = nullptr; io3.ws_stride = 0;
     io3.frame_list = d->d_redo_list + (size_t)half * d->redo_cap; io3.n_frames_dev = d->d_redo_count + half;
-    ldpc_gpu_decoder *r = d->redo;
-    r->fn<<<(unsigned)std::min<long long>((long long)n, r->grid_full), r->block, r->smem, st>>>(r->dev, p, io3);
-    CU_TRY(cudaGetLastError());
-    d->last_launches++;
+    { const int rc = launch_redo(d, p, io3, (long long)n, st); if (rc) return rc; }
     CU_TRY(cudaStreamSynchronize(st));
     if (ran) *ran = true;
     return LDPC_GPU_OK;
@@ -1011,10 +1050,7 @@ extern "C" int ldpc_gpu_decode_batch(ldpc_gpu_decoder *d, const ldpc_gpu_channel
             if (b->out_soft)   { if ((r2 = s.soft.reserve(ssz * N * n))) return r2; ior.out_soft = s.soft.p; }
             if (b->out_errors) { if ((r2 = s.errs.reserve(4 * n))) return r2; ior.out_errors = (int *)s.errs.p; }
             if (b->out_flags)  { if ((r2 = s.flags.reserve(n))) return r2; ior.out_flags = (uint8_t *)s.flags.p; }
-            ldpc_gpu_decoder *r = d->redo;
-            r->fn<<<(unsigned)std::min<long long>((long long)n, r->grid_full), r->block, r->smem, s.st>>>(r->dev, p, ior);
-            CU_TRY(cudaGetLastError());
-            d->last_launches++;
+            if ((r2 = launch_redo(d, p, ior, (long long)n, s.st))) return r2;
             for (size_t k = 0; k < n; k++) {
                 const size_t f = (size_t)pending[k];
                 if (b->out_bits)   CU_TRY(cudaMemcpyAsync(b->out_bits + f * bpf, (char *)s.bits.p + k * bpf, bpf, cudaMemcpyDeviceToHost, s.st));

@@ -16,6 +16,7 @@
 // and a-posteriori sums are bit-identical to the single-frame kernels in both precisions.
 #pragma once
 #include "ldpc_ms_fast.cuh"
+#include "ldpc_ms_x2.cuh"
 
 namespace ldpc {
 
@@ -66,28 +67,35 @@ __global__ void __launch_bounds__(NT_MAX, 1) ms_tile_kernel(const CodeDev c, con
     const bool normalized = (p.flags & LDPC_GPU_F_NORMALIZED_MS) != 0, offset = (p.flags & LDPC_GPU_F_OFFSET_MS) != 0;
     const uint32_t qflags = p.flags & (LDPC_GPU_F_QUANTIZE_SAMPLES | LDPC_GPU_F_SATURATE_SAMPLES);
     const bool fcond = !io.y || io.y_dtype != LDPC_GPU_DT_F64;
-    const long long ntiles = (io.n_frames + FI - 1) / FI;
+    // redo launch of the exact-lattice kernel (ldpc_ms_tileh.cuh): frame q of the launch is frame frame_list[q] of the batch
+    const long long n_launch = io.n_frames_dev ? min((long long)*io.n_frames_dev, io.n_frames) : io.n_frames;
+    auto frame_of = [&](long long q) -> long long { return io.frame_list ? io.frame_list[q] : q; };
+    const long long ntiles = (n_launch + FI - 1) / FI;
     CtaTotals tot; tot.clear();
 
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long f0 = tile * FI;
-        if (tid < FI) { fs[tid].uncoded = 0; fs[tid].errors = 0; fs[tid].flag = 0; }
-        for (int w = tid; w < FI * nwords; w += nt) dbits[w] = 0u;
-        __syncthreads();
-        // ---- channel front end, (block of 4 samples, frame lane) per thread ---------------------
+    // SRC >= 0: the lean fp32 front ends of ldpc_ms_x2.cuh (same values as raw_samples4 + condition_ms_guarded, bit for bit; the
+    // generic per-sample dispatch costs 215 lane-instructions per sample, twice the lean Philox body); SRC = -1: double conditioning
+    const int src = ms_sample_source(io, p, N);
+    auto front = [&](auto src_c, const long long f0) {
+        constexpr int SRC = decltype(src_c)::value;
         for (int t = tid; t < nblk * FI; t += nt) {
             const int b = t / FI, fl = t % FI;
-            const long long f = (f0 + fl < io.n_frames) ? f0 + fl : io.n_frames - 1;     // dead lanes replay the last frame, unreported
+            const long long f = frame_of((f0 + fl < n_launch) ? f0 + fl : n_launch - 1);   // dead lanes replay the last frame, unreported
             const uint8_t *cw = codeword_row(io, c, f);
-            double y4[4];
-            raw_samples4(io, p, c, f, cw, b, y4);
+            double y4[4]; float vf4[4];
+            if (SRC >= 0) {
+                if (4 * b + 3 < N) ms_cond4_f32<(SRC >= 0 ? SRC : SRC_OTHER), true>(io, p, c, f, cw, b, qflags, fcond, vf4);
+                else ms_cond4_f32<SRC_OTHER, true>(io, p, c, f, cw, b, qflags, fcond, vf4);   // ragged last block: the bounds-checked reader
+            } else raw_samples4(io, p, c, f, cw, b, y4);
             uint32_t nib = 0; int unc = 0;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int i = 4 * b + q;
                 if (i >= N) break;
                 Real vr; bool rneg;
-                if (sizeof(Real) == 4 && fcond) {
+                if (SRC >= 0) {
+                    vr = (Real)vf4[q]; rneg = !(vf4[q] > 0.0f);
+                } else if (sizeof(Real) == 4 && fcond) {
                     const float vf = condition_ms_guarded(y4[q], p, qflags);
                     vr = (Real)vf; rneg = !(vf > 0.0f);
                 } else {
@@ -102,7 +110,7 @@ __global__ void __launch_bounds__(NT_MAX, 1) ms_tile_kernel(const CodeDev c, con
                 nib |= (uint32_t)rneg << q;
                 const int deg = c.vn_deg[i];
                 for (int s = 0; s < deg; s++) msg[((size_t)s * N + i) * FI + fl] = vr;
-                if (io.out_soft && p.T == 0 && f0 + fl < io.n_frames) {
+                if (io.out_soft && p.T == 0 && f0 + fl < n_launch) {
                     if (io.y_dtype == LDPC_GPU_DT_F64) ((double *)io.out_soft)[(size_t)f * N + i] = (double)vr;
                     else ((float *)io.out_soft)[(size_t)f * N + i] = (float)vr;
                 }
@@ -110,6 +118,16 @@ __global__ void __launch_bounds__(NT_MAX, 1) ms_tile_kernel(const CodeDev c, con
             if (nib) atomicOr(&dbits[fl * nwords + ((4 * b) >> 5)], nib << ((4 * b) & 31));
             if (unc) atomicAdd(&fs[fl].uncoded, unc);
         }
+    };
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long f0 = tile * FI;
+        if (tid < FI) { fs[tid].uncoded = 0; fs[tid].errors = 0; fs[tid].flag = 0; }
+        for (int w = tid; w < FI * nwords; w += nt) dbits[w] = 0u;
+        __syncthreads();
+        // ---- channel front end, (block of 4 samples, frame lane) per thread ---------------------
+        if (sizeof(Real) == 4 && fcond && src == SRC_PHILOX) front(std::integral_constant<int, SRC_PHILOX>(), f0);   // the throughput entry's source
+        else front(std::integral_constant<int, -1>(), f0);
         __syncthreads();
 
         for (int it = 0; it < p.T; it++) {
@@ -199,9 +217,10 @@ __global__ void __launch_bounds__(NT_MAX, 1) ms_tile_kernel(const CodeDev c, con
 #pragma unroll
                     for (int q = 0; q < FPT; q++) {
                         if (!(sum.x[q] > 0)) atomicOr(&dbits[(fl + q) * nwords + (i >> 5)], 1u << (i & 31));
-                        if (io.out_soft && f0 + fl + q < io.n_frames) {
-                            if (io.y_dtype == LDPC_GPU_DT_F64) ((double *)io.out_soft)[(size_t)(f0 + fl + q) * N + i] = (double)sum.x[q];
-                            else ((float *)io.out_soft)[(size_t)(f0 + fl + q) * N + i] = (float)sum.x[q];
+                        if (io.out_soft && f0 + fl + q < n_launch) {
+                            const size_t fo = (size_t)frame_of(f0 + fl + q);
+                            if (io.y_dtype == LDPC_GPU_DT_F64) ((double *)io.out_soft)[fo * N + i] = (double)sum.x[q];
+                            else ((float *)io.out_soft)[fo * N + i] = (float)sum.x[q];
                         }
                     }
                 }
@@ -209,11 +228,12 @@ __global__ void __launch_bounds__(NT_MAX, 1) ms_tile_kernel(const CodeDev c, con
             __syncthreads();
         }
         for (int fl = 0; fl < FI; fl++) {
-            if (f0 + fl >= io.n_frames) break;                       // uniform: dead lanes are not reported
-            const uint8_t *cw = codeword_row(io, c, f0 + fl);
+            if (f0 + fl >= n_launch) break;                          // uniform: dead lanes are not reported
+            const long long f = frame_of(f0 + fl);
+            const uint8_t *cw = codeword_row(io, c, f);
             for (int w = tid; w < nwords; w += nt) dstage[w] = __ldcg(&dbits[fl * nwords + w]);   // (set by L2 atomics: read at L2)
             __syncthreads();
-            finish_frame(c, p, io, f0 + fl, cw, dstage, &fs[fl], p.T, -1, 0, 0, 1, -1, tot);
+            finish_frame(c, p, io, f, cw, dstage, &fs[fl], p.T, -1, 0, 0, 1, -1, tot);
         }
     }
     if (tid == 0) tot.flush(io.counters);
