@@ -497,10 +497,12 @@ __global__ void gdbf_par_kernel(const CodeDev c, const DecParams p, const FrameI
 static inline size_t hw_smem_bytes(const CodeDev &c)
 {
     const size_t nwords = (size_t)(c.N + 31) / 32, mwords = (size_t)(c.M + 31) / 32;
-    size_t n = 16 + 4 * (3 * nwords + 2 * mwords) + 2 * (size_t)c.dv_max * c.N + (size_t)c.N + LDPC_GPU_HW_QBUF + 64;
+    size_t n = 16 + 4 * (3 * nwords + 3 * mwords) + 32 * mwords + 2 * (size_t)c.dv_max * c.N + (size_t)c.N + LDPC_GPU_HW_QBUF + 64;
     return (n + 15) & ~(size_t)15;
 }
 
+// DV > 0: every variable has exactly DV checks (the slot loop unrolls); DV = 0: per-variable weights.
+template <int DV>
 __global__ void __launch_bounds__(384, 3) hw_kernel(const CodeDev c, const DecParams p, const FrameIO io)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -511,13 +513,13 @@ __global__ void __launch_bounds__(384, 3) hw_kernel(const CodeDev c, const DecPa
     uint32_t *rbits = dbits + nwords;                                   // received hard decisions
     uint32_t *cbits = rbits + nwords;                                   // codeword bits
     uint32_t *syn = cbits + nwords;                                     // syndrome bits, 1 <-> unsatisfied
-    uint32_t *tog = syn + mwords;                                       // toggles of the running iteration
-    uint16_t *chk = reinterpret_cast<uint16_t *>(tog + mwords);         // [dv_max][N] check of slot s of variable i
+    uint32_t *tog = syn + mwords;                                       // [2][mwords] toggles of the running iteration, by iteration parity
+    uint8_t *synb = reinterpret_cast<uint8_t *>(tog + 2 * mwords);      // [32 mwords] the syndrome bits again, one byte each: the flip metric's operand
+    uint16_t *chk = reinterpret_cast<uint16_t *>(synb + 32 * mwords);   // [dv_max][N] check of slot s of variable i
     signed char *yval = reinterpret_cast<signed char *>(chk + (size_t)dvm * N);   // unpack(y')   in [-31, 31], odd
     signed char *qval = yval + N;                                       // unpack(q')
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const int maxPhases = p.maxphase > 0 ? p.maxphase : 1;
-    const int reg_dv = c.regular_dv;                                    // regular codes: no per-variable weight load
     CtaTotals tot; tot.clear();
 
     for (int e = tid; e < dvm * N; e += nt) chk[e] = (uint16_t)c.vn_chk[e];      // once per CTA: the graph, variable side
@@ -576,38 +578,46 @@ __global__ void __launch_bounds__(384, 3) hw_kernel(const CodeDev c, const DecPa
         int leastIterations = T, leastErrors = N, satisfied = 1, it = 0;
         for (int phase = 0; phase < maxPhases; phase++) {             // :280-373
             for (int w = tid; w < nwords; w += nt) dbits[w] = rbits[w];
-            for (int w = tid; w < mwords; w += nt) tog[w] = 0u;
+            for (int w = tid; w < 2 * mwords; w += nt) tog[w] = 0u;
             __syncthreads();
             // full syndrome of the starting decisions (checkNodeUpdates, :546-563), once per phase
+            unsigned mine = 0;
             for (int j0 = tid; j0 < (mwords << 5); j0 += nt) {
                 unsigned par = 0;
                 if (j0 < M) {
                     const int deg = c.cn_deg[j0];
                     for (int k = 0; k < deg; k++) { const uint32_t i = c.cn_var[(size_t)k * M + j0]; par ^= dbits[i >> 5] >> (i & 31); }
                 }
-                const unsigned bal = __ballot_sync(0xffffffffu, (par & 1u) != 0);
+                par &= 1u; mine |= par;
+                synb[j0] = (uint8_t)par;
+                const unsigned bal = __ballot_sync(0xffffffffu, par != 0);
                 if (lane == 0) syn[j0 >> 5] = bal;
             }
-            __syncthreads();
+            int any = __syncthreads_or((int)mine);                    // some check unsatisfied (the same value in every thread)
             for (it = 0; it < T; it++) {
-                unsigned any = 0;
-                for (int w = 0; w < mwords; w++) any |= syn[w];
                 satisfied = (any == 0);
                 if (satisfied) break;                                 // :297-299
-                // symNodeUpdates :565-593, variables of a warp share one decision word
+                uint32_t *togw = tog + (it & 1) * mwords;
+                // symNodeUpdates :565-593, variables of a warp share one decision word.  Per variable: DV index loads, DV byte loads
+                // (the r2bh capture of the bit-packed form: 147 warp-instructions per variable-iteration, a quarter of them the per-slot
+                // shift / mask of the syndrome word and the runtime slot loop)
                 for (int i0 = tid; i0 < npad; i0 += nt) {
                     const bool valid = i0 < N;
                     const uint32_t dw = dbits[i0 >> 5];
                     bool nd = (dw >> lane) & 1u;
                     if (valid) {
-                        const int deg = reg_dv > 0 ? reg_dv : (int)c.vn_deg[i0];
+                        const int deg = DV > 0 ? DV : (int)c.vn_deg[i0];
                         const int d01 = (int)nd;
-                        int sat = 0;
-                        for (int sl = 0; sl < deg; sl++) { const int j = chk[sl * N + i0]; sat += 1 - (int)((syn[j >> 5] >> (j & 31)) & 1u); }
-                        const int E = (1 - 2 * d01) * (int)yval[i0] + sat * p.hw_Smult + (int)qval[i0 + qpointer];
+                        int unsat = 0;
+                        if (DV > 0) {
+#pragma unroll
+                            for (int sl = 0; sl < (DV > 0 ? DV : 1); sl++) unsat += (int)synb[chk[sl * N + i0]];
+                        } else
+                            for (int sl = 0; sl < deg; sl++) unsat += (int)synb[chk[sl * N + i0]];
+                        const int E = (1 - 2 * d01) * (int)yval[i0] + (deg - unsat) * p.hw_Smult + (int)qval[i0 + qpointer];
                         if (E <= p.hw_theta) {
                             nd = !nd;
-                            for (int sl = 0; sl < deg; sl++) { const int j = chk[sl * N + i0]; atomicXor(&tog[j >> 5], 1u << (j & 31)); }
+                            for (int sl = 0; sl < deg; sl++) { const int j = chk[sl * N + i0]; atomicXor(&togw[j >> 5], 1u << (j & 31)); }
                         }
                     }
                     const unsigned bal = __ballot_sync(0xffffffffu, valid && nd);
@@ -616,8 +626,14 @@ __global__ void __launch_bounds__(384, 3) hw_kernel(const CodeDev c, const DecPa
                 qpointer++;                                           // :356-358
                 if (qpointer >= QB - N) qpointer = 0;
                 __syncthreads();
-                for (int w = tid; w < mwords; w += nt) { syn[w] ^= tog[w]; tog[w] = 0u; }
-                __syncthreads();
+                // fold the iteration's toggles into both syndrome forms; the other parity's toggle words (consumed one iteration ago) are cleared
+                unsigned left = 0;
+                for (int j0 = tid; j0 < (mwords << 5); j0 += nt) {
+                    const unsigned b = (unsigned)synb[j0] ^ ((togw[j0 >> 5] >> (j0 & 31)) & 1u);
+                    synb[j0] = (uint8_t)b; left |= b;
+                }
+                for (int w = tid; w < mwords; w += nt) { syn[w] ^= togw[w]; tog[((it + 1) & 1) * mwords + w] = 0u; }
+                any = __syncthreads_or((int)left);
             }
             // countDecisionErrors against c in {0,1} (:362-372)
             int le = 0;

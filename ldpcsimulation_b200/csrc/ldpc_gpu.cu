@@ -629,7 +629,7 @@ static int pick_kernel(ldpc_gpu_decoder *d)
         if (v.M <= 512 && v.N <= 4096) block = 256;                           // measured on the 802.3an H: 256 > 384 > 512
     } else if (kind == LDPC_GPU_KIND_NGDBF_HW) {
         if (v.N >= LDPC_GPU_HW_QBUF) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "NGDBFhw's 2648-entry noise window needs N < 2648 (src/NGDBFhw.cpp:151)");
-        d->fn = (KernelFn)hw_kernel;
+        d->fn = v.regular_dv == 6 ? (KernelFn)hw_kernel<6> : (KernelFn)hw_kernel<0>;
         smem = hw_smem_bytes(v);
         block = std::min(384, std::max(128, round32(v.M)));                 // measured: one check per thread, 3 CTAs/SM (launch bounds 384 x 3)
     } else if (kind == LDPC_GPU_KIND_NGDBF_SC) {

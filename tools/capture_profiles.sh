@@ -12,6 +12,7 @@ python tools/prof_one.py x2 65536 > gpurun_out/r2at_plain_x2.log 2>&1 && cap x2 
 python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/r2at_plain_bench.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2at_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/r2at_ncu_bench.log 2>&1
 python tools/time_code.py decodeMinSum dvbs2 10 9472 f32 3.0 > gpurun_out/r2at_plain_tile.log 2>&1 && cap tile ms_tile python tools/time_code.py decodeMinSum dvbs2 10 4736 f32 3.0 1
+python tools/time_code.py decodeOffsetMinSum dvbs2 10 18944 f16x2 3.0 > gpurun_out/r2at_plain_tileh.log 2>&1 && cap tileh ms_tileh python tools/time_code.py decodeOffsetMinSum dvbs2 10 9472 f16x2 3.0 1
 python tools/time_code.py decodeMinSum PEG 50 262144 f32 2.0 > gpurun_out/r2at_plain_quad.log 2>&1 && cap quad ms_quad python tools/time_code.py decodeMinSum PEG 50 65536 f32 2.0 1
 python tools/time_code.py decodeBP 802_3_H 10 131072 f32 4.0 > gpurun_out/r2at_plain_bp.log 2>&1 && cap bp ms_rc_kernel python tools/time_code.py decodeBP 802_3_H 10 65536 f32 4.0 1
 ( time python bench.py > gpurun_out/r2at_bench.json 2> gpurun_out/r2at_bench.err ) 2> gpurun_out/r2at_bench.time
