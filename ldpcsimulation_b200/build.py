@@ -33,14 +33,16 @@ def sources():
 
 def build_library(force=False, verbose=False):
     os.makedirs(OUT, exist_ok=True)
-    if not force and _newer(LIB, sources()):
-        return LIB
     out = os.environ.get("LDPC_GPU_LIB_OUT", LIB)
     flags = list(NVCC_FLAGS)
     if os.environ.get("LDPC_FAST_BUILD"):
         # development only: ptxas on all cores (80 s instead of 3 min).  NOT for measurements: split compilation changes the register
         # allocation (the headline kernels pick up 100 - 500 bytes of spills; sum-product 7.0 -> 6.0 Gbit/s, DVB-S2 8.2 -> 7.7)
         flags += ["-split-compile", "0"]
+    stamp = os.path.join(OUT, "flags.txt")                     # a development build is never mistaken for the measured one
+    same_flags = os.path.exists(stamp) and open(stamp).read() == " ".join(flags)
+    if not force and same_flags and _newer(LIB, sources()):
+        return LIB
     cmd = [NVCC] + flags + [os.path.join(CSRC, "ldpc_gpu.cu"), "-o", out, "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     with open(os.path.join(OUT, "ptxas.log"), "w") as f:
@@ -48,6 +50,8 @@ def build_library(force=False, verbose=False):
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed")
+    with open(stamp, "w") as f:
+        f.write(" ".join(flags))
     if verbose:
         print(r.stderr)
     return LIB
