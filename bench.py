@@ -331,7 +331,7 @@ def main():
     dec = capi.Decoder(code, cfg, device=local)
     geo = dec.geometry()
     snr, R = W["snr_db"], W["R"]
-    F = args.frames or {"dvbs2": 1 << 14, "PEG": 1 << 19}.get(W["code"], 1 << 20)
+    F = args.frames or {"dvbs2": 18944, "PEG": 1 << 19}.get(W["code"], 1 << 20)
 
     # the path's one collective: library-owned NCCL communicator, id distributed over torch.distributed
     if world > 1:

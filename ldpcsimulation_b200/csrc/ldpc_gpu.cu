@@ -631,7 +631,9 @@ static int pick_kernel(ldpc_gpu_decoder *d)
         if (v.N >= LDPC_GPU_HW_QBUF) return set_err(LDPC_GPU_ERR_UNSUPPORTED, "NGDBFhw's 2648-entry noise window needs N < 2648 (src/NGDBFhw.cpp:151)");
         d->fn = v.regular_dv == 6 ? (KernelFn)hw_kernel<6> : (KernelFn)hw_kernel<0>;
         smem = hw_smem_bytes(v);
-        block = std::min(384, std::max(128, round32(v.M)));                 // measured: one check per thread, 3 CTAs/SM (launch bounds 384 x 3)
+        // measured on the 802.3an H (524 288 frames at 4.5 dB): 384 threads x 3 CTAs/SM 18.3 Gbit/s, 256 x 4 19.2, 192 x 6 19.3, 128 x 7 19.6: the two
+        // barriers of an iteration stall a whole CTA, so many small CTAs (independent frames) hide them better than few large ones
+        block = 128;
     } else if (kind == LDPC_GPU_KIND_NGDBF_SC) {
         d->fn = (KernelFn)sc_kernel;
         smem = sc_smem_bytes(v, d->cfg.num_iterations, d->cfg.Q);

@@ -18,7 +18,8 @@
 // interface stays untouched:
 //   LDPC_SEED       Philox seed (default time(0), like ran_seed(time(0)), src/decodeMinSum.cpp:187)
 //   LDPC_FRAMES     fixed frame count instead of the stop rule
-//   LDPC_PRECISION  f64 (default: the reference's arithmetic) | f32
+//   LDPC_PRECISION  f64 (default: the reference's arithmetic) | f32 | f16x2 (min-sum family: binary16 messages; results identical to
+//                   f64 when the macro set is an exact lattice -- stderr says which kernel runs, include/ldpc_gpu.h LDPC_GPU_PREC_F16X2)
 //   LDPC_DEVICES    comma list of CUDA ordinals; frames are sharded by frame-id range, one host
 //                   thread per GPU (default "0")
 //   LDPC_POLL       frames per launch between stop-rule polls
@@ -247,7 +248,7 @@ int main(int argc, char *argv[])
     ldpc_gpu_decoder_cfg_default(v->kind, &cfg);
     cfg.flags = f;
     const char *pe = getenv("LDPC_PRECISION");
-    cfg.precision = (pe && string(pe) == "f32") ? LDPC_GPU_PREC_F32 : LDPC_GPU_PREC_F64;
+    cfg.precision = (pe && string(pe) == "f32") ? LDPC_GPU_PREC_F32 : (pe && string(pe) == "f16x2") ? LDPC_GPU_PREC_F16X2 : LDPC_GPU_PREC_F64;
 
     // ---- parse, echoing like the reference --------------------------------------------------
     int idx = 1;
@@ -324,6 +325,10 @@ int main(int argc, char *argv[])
     for (size_t g = 0; g < devs.size(); g++) {
         sh[g].device = devs[g];
         if (ldpc_gpu_decoder_create(code, &cfg, devs[g], &sh[g].dec)) { cerr << "decoder: " << ldpc_gpu_last_error() << endl; return 1; }
+        if (g == 0 && cfg.precision == LDPC_GPU_PREC_F16X2) {
+            int32_t exact = 0; ldpc_gpu_decoder_stats(sh[g].dec, nullptr, &exact);
+            cerr << (exact ? "f16x2: exact lattice, results identical to LDPC_PRECISION=f64" : "f16x2: NOT an exact lattice, binary16 messages clamped (labelled throughput arithmetic)") << endl;
+        }
         if (n_cw) ldpc_gpu_decoder_set_codewords(sh[g].dec, cw.data(), n_cw);
         sh[g].ew.assign(N, 0); sh[g].ith.assign(ith_len, 0); sh[g].ph.assign(cfg.maxphase > 0 ? cfg.maxphase : 1, 0);
     }

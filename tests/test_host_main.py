@@ -126,6 +126,24 @@ def test_tsv_line_layout_and_values(variant, tmp_path):
 
 @needs_bin
 @pytest.mark.gpu
+def test_f16x2_host_main_writes_the_f64_line(tmp_path):
+    """LDPC_PRECISION=f16x2 on decodeOffsetMinSum's exact-lattice macro set (the headline kernel behind the reference's CLI):
+    the TSV line is the one LDPC_PRECISION=f64 writes, character for character."""
+    alist = code_path("802_3_H")
+    lines = {}
+    for prec in ("f64", "f16x2"):
+        log = str(tmp_path / (prec + ".tsv"))
+        env = dict(os.environ, LDPC_SEED="5", LDPC_FRAMES="3000", LDPC_POLL="3000", LDPC_PRECISION=prec)
+        r = subprocess.run(exe("decodeOffsetMinSum") + [alist, "0.8413", "3.6", "10", "1.9375", "5", "0.125", log], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr
+        if prec == "f16x2":
+            assert "exact lattice" in r.stderr and "NOT" not in r.stderr
+        lines[prec] = open(log).read()
+    assert lines["f64"] == lines["f16x2"] and float(lines["f64"].split("\t")[3]) > 0      # word errors were part of the comparison
+
+
+@needs_bin
+@pytest.mark.gpu
 def test_ngdbfhw_main(tmp_path):
     alist = code_path("802_3_H")
     log = str(tmp_path / "hw.tsv")
