@@ -412,7 +412,8 @@ def main():
         return out, d2
 
     # ---- e2e: reference-facing call with host buffers -------------------------------------------
-    Fe = args.e2e_frames if W["code"] != "dvbs2" else 1 << 11
+    # DVB-S2: two launches of 148 tiles of 64 frames (a 2048-frame batch would occupy 32 of the 148 SMs); the side formats stay at 2048 frames
+    Fe = args.e2e_frames if W["code"] != "dvbs2" else (18944 if W["q8"] else 1 << 11)
     if not W["q8"]:
         Fe = min(Fe, 1 << 17)                            # no packed-level headline format: everything runs at the side formats' batch
     sigma = float(np.sqrt(10 ** (-snr / 10) / R / 2))
@@ -426,7 +427,7 @@ def main():
         hw_noise = torch.empty((Fe, abi.HW_QBUF), dtype=torch.float64, pin_memory=True)
         hw_noise.copy_(torch.randn((Fe, abi.HW_QBUF), generator=gen, device="cuda", dtype=torch.float64))
 
-    Fs = min(Fe, 1 << 17)                                # batch of the side formats (fp64 samples of 2^19 frames would pin 8.6 GB per rank)
+    Fs = min(Fe, 1 << 17 if W["code"] != "dvbs2" else 1 << 11)   # batch of the side formats (fp64 samples of 2^19 frames would pin 8.6 GB per rank)
 
     def run_e2e(decoder, torch_dtype, abi_dtype, steps=e2e_steps, frames=None):
         Fe = frames or Fs                                 # (shadows the headline batch size: everything below is per call)
@@ -513,8 +514,8 @@ def main():
         out, _ = short_value(wl, precision, 1 << 19, channel=abi.CHANNEL_FAST)
         extras["fast_channel"] = dict(out, note="LDPC_GPU_CHANNEL_FAST: SFU Box-Muller (lg2/sqrt/sin/cos.approx) instead of the CPU-reproducible polynomials")
     if not args.no_extras:
-        for name, frames in (("nms_8023", 1 << 19), ("oms_8023", 1 << 19), ("bp_8023", 1 << 17), ("ms_peg_t50", 1 << 18), ("ms_dvbs2", 1 << 13), ("oms_dvbs2", 18944),
-                             ("ngdbfhw_8023", 1 << 18), ("smngdbf_8023", 1 << 16)):
+        for name, frames in (("nms_8023", 1 << 19), ("oms_8023", 1 << 19), ("bp_8023", 1 << 17), ("ms_peg_t50", 1 << 18), ("ms_dvbs2", 9472), ("oms_dvbs2", 18944),
+                             ("ngdbfhw_8023", 1 << 19), ("smngdbf_8023", 1 << 18)):
             if name == wl:
                 continue
             out, d3 = short_value(name, WORKLOADS[name]["precision"], frames)
