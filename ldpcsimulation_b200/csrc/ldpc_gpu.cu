@@ -508,7 +508,7 @@ static int pick_kernel(ldpc_gpu_decoder *d)
             d->fn = v.idx16 ? (KernelFn)ms_tileh_kernel<uint16_t, 8, 8, 512> : (KernelFn)ms_tileh_kernel<uint32_t, 8, 8, 512>;
             block = 512; d->frames_per_cta = TILEH_FI;
             d->ws_stride = ms_tileh_state_bytes(v);
-            smem = ms_tileh_smem_bytes(v);
+            smem = ms_tileh_smem_bytes(v) + ms_tileh_pipe_bytes(512, 8);
             goto geometry;
         }
         if (d->cfg.precision == LDPC_GPU_PREC_F16X2) {
