@@ -45,7 +45,6 @@ LDPC_DEVINL uint32_t tileh_decision_byte(const uint32_t (&s)[4])
     return b;
 }
 
-LDPC_DEVINL void tileh_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 LDPC_DEVINL void tileh_cp_async16(void *smem, const void *g)
 {
     const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
@@ -54,19 +53,16 @@ LDPC_DEVINL void tileh_cp_async16(void *smem, const void *g)
 LDPC_DEVINL void tileh_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int NPEND> LDPC_DEVINL void tileh_cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(NPEND) : "memory"); }
 
-// PIPE: shared-memory bytes of the two staging buffers ((1 + DVMAX) 16-byte entries per thread and stage)
+// shared-memory bytes of the two staging buffers ((1 + DVMAX) 16-byte entries per thread and stage)
 static inline size_t ms_tileh_pipe_bytes(int nt, int dvmax) { return (size_t)2 * (1 + dvmax) * nt * 16; }
 
-// PF: the entries of the thread's NEXT trip are requested into L2 while the current trip's loads are outstanding: the kernel is
-// bound by DRAM latency at 16 warps per SM (128 registers per thread hold one row's 8 x 16 bytes; a second row in registers would
-// spill), and a prefetch keeps a second row in flight without a destination register (measured 14.15 -> 14.59 Gbit/s on DVB-S2).
-//
-// PIPE: instead, the NEXT trip's entries are copied asynchronously (cp.async, 16 bytes per thread and entry, L2 -> shared memory, no
+// The NEXT trip's entries of a thread are copied asynchronously (cp.async, 16 bytes per thread and entry, L2 -> shared memory, no
 // destination registers) into the thread's own slots of a two-stage shared-memory buffer while the current trip is computed from the
 // other stage: twice the bytes in flight per SM, and the row is re-read from shared memory for the second pass instead of living in 32
-// registers.  Every thread reads only the slots it filled itself, so cp.async.wait_group is the only synchronisation.
-// (PIPE = false, PF = true is the register-staged form the pipelined one was measured against: 7.25 vs 6.58 ms per iteration of 18 944 frames.)
-template <typename IdxT, int DCMAX, int DVMAX, int NT_MAX, bool PF = false, bool PIPE = true>
+// registers.  Every thread reads only the slots it filled itself, so cp.async.wait_group is the only synchronisation.  Measured against
+// the register-staged form (one row of 8 x 16 bytes in registers, 124 registers, `prefetch.global.L2` of the next trip): 6.58 instead of
+// 7.25 ms per iteration of 18 944 DVB-S2 frames (profiles/r2_summary.md section 7).
+template <typename IdxT, int DCMAX, int DVMAX, int NT_MAX>
 __global__ void __launch_bounds__(NT_MAX, 1) ms_tileh_kernel(const CodeDev c, const DecParams p, const FrameIO io)
 {
     constexpr int FI = TILEH_FI, LPN = TILEH_LPN;
@@ -76,7 +72,7 @@ __global__ void __launch_bounds__(NT_MAX, 1) ms_tileh_kernel(const CodeDev c, co
     uint32_t *capf = reinterpret_cast<uint32_t *>(smem_raw + 16 * FI);                   // [2]: bit fl = some |c2v| of frame lane fl exceeded the cap
     uint32_t *dstage = capf + 4;                                                         // [nwords]
     static_assert(DCMAX <= 1 + DVMAX, "the staging slots are sized for the variable phase");
-    uint4 *sbuf = reinterpret_cast<uint4 *>(smem_raw + ((16 * (size_t)TILEH_FI + 16 + 4 * (size_t)((c.N + 31) / 32) + 15) & ~(size_t)15));   // PIPE: [2][1 + DVMAX][nt] staging slots, behind ms_tileh_smem_bytes()
+    uint4 *sbuf = reinterpret_cast<uint4 *>(smem_raw + ((16 * (size_t)TILEH_FI + 16 + 4 * (size_t)((c.N + 31) / 32) + 15) & ~(size_t)15));   // [2][1 + DVMAX][nt] staging slots, behind ms_tileh_smem_bytes()
     const int N = c.N, M = c.M, nwords = (N + 31) >> 5, nblk = (N + 3) >> 2;
     __half *msg = reinterpret_cast<__half *>(io.workspace + (size_t)blockIdx.x * io.ws_stride);
     __half *yq = msg + (size_t)c.dvN * FI;
@@ -165,108 +161,41 @@ __global__ void __launch_bounds__(NT_MAX, 1) ms_tileh_kernel(const CodeDev c, co
         for (int it = 0; it < p.T; it++) {
             const bool last = (it == p.T - 1);
             // ---- check-node phase: (row, lane group) per thread; weight and index words one trip ahead (ldpc_ms_tile.cuh) ----
-            if (PIPE) {
-                const int lim = M * LPN;
-                auto slot = [&](const int st, const int k) -> uint4 * { return sbuf + ((size_t)(st * (1 + DVMAX) + k) * nt + tid); };
-                auto load_idx = [&](const int t, int &deg, uint4 (&w)[NG]) {
-                    const int j = t / LPN;
-                    deg = c.cn_deg[j];
+            {
+            const int lim = M * LPN;
+            auto slot = [&](const int st, const int k) -> uint4 * { return sbuf + ((size_t)(st * (1 + DVMAX) + k) * nt + tid); };
+            auto load_idx = [&](const int t, int &deg, uint4 (&w)[NG]) {
+                const int j = t / LPN;
+                deg = c.cn_deg[j];
 #pragma unroll
-                    for (int g = 0; g < NG; g++) if (g * VPL < deg) w[g] = __ldg(&cnv[(size_t)g * M + j]);
-                };
-                auto issue = [&](const int st, const int deg, const uint4 (&w)[NG]) {
+                for (int g = 0; g < NG; g++) if (g * VPL < deg) w[g] = __ldg(&cnv[(size_t)g * M + j]);
+            };
+            auto issue = [&](const int st, const int deg, const uint4 (&w)[NG]) {
 #pragma unroll
-                    for (int k = 0; k < DCMAX; k++) if (k < deg) tileh_cp_async16(slot(st, k), &msgv[(size_t)IdxVec<IdxT>::get(w[k / VPL], k % VPL) * 8 + lgc]);
-                };
-                int deg_c = 0, deg_n = 0; uint4 w_c[NG], w_n[NG];
-                if (tid < lim) { load_idx(tid, deg_c, w_c); issue(0, deg_c, w_c); }
+                for (int k = 0; k < DCMAX; k++) if (k < deg) tileh_cp_async16(slot(st, k), &msgv[(size_t)IdxVec<IdxT>::get(w[k / VPL], k % VPL) * 8 + lgc]);
+            };
+            int deg_c = 0, deg_n = 0; uint4 w_c[NG], w_n[NG];
+            if (tid < lim) { load_idx(tid, deg_c, w_c); issue(0, deg_c, w_c); }
+            tileh_cp_async_commit();
+            if (tid + nt < lim) load_idx(tid + nt, deg_n, w_n);
+            int st = 0;
+            for (int t = tid; t < lim; t += nt, st ^= 1) {
+                if (t + nt < lim) issue(st ^ 1, deg_n, w_n);
                 tileh_cp_async_commit();
-                if (tid + nt < lim) load_idx(tid + nt, deg_n, w_n);
-                int st = 0;
-                for (int t = tid; t < lim; t += nt, st ^= 1) {
-                    if (t + nt < lim) issue(st ^ 1, deg_n, w_n);
-                    tileh_cp_async_commit();
-                    int deg_nn = 0; uint4 w_nn[NG];
-                    if (t + 2 * nt < lim) load_idx(t + 2 * nt, deg_nn, w_nn);
-                    tileh_cp_async_wait<1>();                                            // this trip's entries have landed
-                    const int deg = deg_c;
-                    uint32_t m1[4] = { INF2, INF2, INF2, INF2 }, m2[4] = { INF2, INF2, INF2, INF2 };
-#pragma unroll
-                    for (int k = 0; k < DCMAX; k++) if (k < deg) {
-                        const uint4 x = *slot(st, k);
-                        const uint32_t xv[4] = { x.x, x.y, x.z, x.w };
-#pragma unroll
-                        for (int h = 0; h < 4; h++) {
-                            const __half2 hi = __hmax2(__habs2(h2_from(m1[h])), __habs2(h2_from(xv[h])));
-                            m2[h] = h2_bits(__hmin2(h2_from(m2[h]), hi));
-                            m1[h] = h2_min_xorsign_abs(m1[h], xv[h]);
-                        }
-                    }
-                    uint32_t m1a[4], s1[4]; __half2 ds[4];
-#pragma unroll
-                    for (int h = 0; h < 4; h++) {
-                        const uint32_t sg = m1[h] & 0x80008000u;
-                        m1a[h] = m1[h] & 0x7fff7fffu;
-                        const __half2 t1 = __hmax2(__hsub2(h2_from(m1a[h]), delta2), zero2);
-                        const __half2 t2 = __hmax2(__hsub2(h2_from(m2[h]), delta2), zero2);
-                        cacc[h] |= __hgt2_mask(t2, cap2);
-                        s1[h] = h2_bits(t1) ^ sg;
-                        ds[h] = __hsub2(h2_from(h2_bits(t2) ^ sg), h2_from(s1[h]));
-                    }
-#pragma unroll
-                    for (int k = 0; k < DCMAX; k++) if (k < deg) {
-                        const uint4 x = *slot(st, k);
-                        const uint32_t xv[4] = { x.x, x.y, x.z, x.w };
-                        uint32_t oo[4];
-#pragma unroll
-                        for (int h = 0; h < 4; h++) {
-                            const __half2 eq = __heq2(__habs2(h2_from(xv[h])), h2_from(m1a[h]));
-                            oo[h] = x2_and_xor(xv[h], 0x80008000u, h2_bits(__hfma2(eq, ds[h], h2_from(s1[h]))));
-                        }
-                        msgv[(size_t)IdxVec<IdxT>::get(w_c[k / VPL], k % VPL) * 8 + lgc] = make_uint4(oo[0], oo[1], oo[2], oo[3]);
-                    }
-                    deg_c = deg_n; deg_n = deg_nn;
-#pragma unroll
-                    for (int g = 0; g < NG; g++) { w_c[g] = w_n[g]; w_n[g] = w_nn[g]; }
-                }
-                tileh_cp_async_wait<0>();
-            } else {
-            int deg_n = 0; uint4 w_n[NG];
-            if (tid < M * LPN) {
-                const int j0 = tid / LPN;
-                deg_n = c.cn_deg[j0];
-#pragma unroll
-                for (int g = 0; g < NG; g++) if (g * VPL < deg_n) w_n[g] = __ldg(&cnv[(size_t)g * M + j0]);
-            }
-            for (int t = tid; t < M * LPN; t += nt) {
-                const int deg = deg_n;
-                uint4 w[NG];
-#pragma unroll
-                for (int g = 0; g < NG; g++) w[g] = w_n[g];
-                if (t + nt < M * LPN) {
-                    const int jn = (t + nt) / LPN;
-                    deg_n = c.cn_deg[jn];
-#pragma unroll
-                    for (int g = 0; g < NG; g++) if (g * VPL < deg_n) w_n[g] = __ldg(&cnv[(size_t)g * M + jn]);
-                }
-                uint32_t v[DCMAX][4];
-                if (PF && t + nt < M * LPN) {
-#pragma unroll
-                    for (int k = 0; k < DCMAX; k++) if (k < deg_n) tileh_prefetch_l2(&msgv[(size_t)IdxVec<IdxT>::get(w_n[k / VPL], k % VPL) * 8 + lgc]);
-                }
-#pragma unroll
-                for (int k = 0; k < DCMAX; k++) if (k < deg) {
-                    const uint4 x = msgv[(size_t)IdxVec<IdxT>::get(w[k / VPL], k % VPL) * 8 + lgc];
-                    v[k][0] = x.x; v[k][1] = x.y; v[k][2] = x.z; v[k][3] = x.w;
-                }
+                int deg_nn = 0; uint4 w_nn[NG];
+                if (t + 2 * nt < lim) load_idx(t + 2 * nt, deg_nn, w_nn);
+                tileh_cp_async_wait<1>();                                            // this trip's entries have landed
+                const int deg = deg_c;
                 uint32_t m1[4] = { INF2, INF2, INF2, INF2 }, m2[4] = { INF2, INF2, INF2, INF2 };
 #pragma unroll
                 for (int k = 0; k < DCMAX; k++) if (k < deg) {
+                    const uint4 x = *slot(st, k);
+                    const uint32_t xv[4] = { x.x, x.y, x.z, x.w };
 #pragma unroll
                     for (int h = 0; h < 4; h++) {
-                        const __half2 hi = __hmax2(__habs2(h2_from(m1[h])), __habs2(h2_from(v[k][h])));
+                        const __half2 hi = __hmax2(__habs2(h2_from(m1[h])), __habs2(h2_from(xv[h])));
                         m2[h] = h2_bits(__hmin2(h2_from(m2[h]), hi));
-                        m1[h] = h2_min_xorsign_abs(m1[h], v[k][h]);                      // |.| = running minimum, sign = running sign product
+                        m1[h] = h2_min_xorsign_abs(m1[h], xv[h]);
                     }
                 }
                 uint32_t m1a[4], s1[4]; __half2 ds[4];
@@ -274,103 +203,72 @@ __global__ void __launch_bounds__(NT_MAX, 1) ms_tileh_kernel(const CodeDev c, co
                 for (int h = 0; h < 4; h++) {
                     const uint32_t sg = m1[h] & 0x80008000u;
                     m1a[h] = m1[h] & 0x7fff7fffu;
-                    // offset (:503-515; delta = 0 for plain min-sum), once per row
                     const __half2 t1 = __hmax2(__hsub2(h2_from(m1a[h]), delta2), zero2);
                     const __half2 t2 = __hmax2(__hsub2(h2_from(m2[h]), delta2), zero2);
-                    cacc[h] |= __hgt2_mask(t2, cap2);                                    // t2 >= t1
+                    cacc[h] |= __hgt2_mask(t2, cap2);
                     s1[h] = h2_bits(t1) ^ sg;
                     ds[h] = __hsub2(h2_from(h2_bits(t2) ^ sg), h2_from(s1[h]));
                 }
 #pragma unroll
                 for (int k = 0; k < DCMAX; k++) if (k < deg) {
-                    uint4 o;
+                    const uint4 x = *slot(st, k);
+                    const uint32_t xv[4] = { x.x, x.y, x.z, x.w };
                     uint32_t oo[4];
 #pragma unroll
                     for (int h = 0; h < 4; h++) {
-                        const __half2 eq = __heq2(__habs2(h2_from(v[k][h])), h2_from(m1a[h]));     // 1.0 where this edge attains the row minimum
-                        oo[h] = x2_and_xor(v[k][h], 0x80008000u, h2_bits(__hfma2(eq, ds[h], h2_from(s1[h]))));
+                        const __half2 eq = __heq2(__habs2(h2_from(xv[h])), h2_from(m1a[h]));
+                        oo[h] = x2_and_xor(xv[h], 0x80008000u, h2_bits(__hfma2(eq, ds[h], h2_from(s1[h]))));
                     }
-                    o.x = oo[0]; o.y = oo[1]; o.z = oo[2]; o.w = oo[3];
-                    msgv[(size_t)IdxVec<IdxT>::get(w[k / VPL], k % VPL) * 8 + lgc] = o;
+                    msgv[(size_t)IdxVec<IdxT>::get(w_c[k / VPL], k % VPL) * 8 + lgc] = make_uint4(oo[0], oo[1], oo[2], oo[3]);
                 }
+                deg_c = deg_n; deg_n = deg_nn;
+#pragma unroll
+                for (int g = 0; g < NG; g++) { w_c[g] = w_n[g]; w_n[g] = w_nn[g]; }
             }
+            tileh_cp_async_wait<0>();
             }
             __syncthreads();
             // ---- variable-node phase: (variable, lane group) per thread ------------------------------
-            if (PIPE) {
-                const int lim = N * LPN;
-                auto slot = [&](const int st, const int k) -> uint4 * { return sbuf + ((size_t)(st * (1 + DVMAX) + k) * nt + tid); };
-                auto issue = [&](const int st, const int t, const int deg) {
-                    const int i = t / LPN;
-                    tileh_cp_async16(slot(st, 0), &yqv[(size_t)i * 8 + lgc]);
-#pragma unroll
-                    for (int sl = 0; sl < DVMAX; sl++) if (sl < deg) tileh_cp_async16(slot(st, 1 + sl), &msgv[((size_t)sl * N + i) * 8 + lgc]);
-                };
-                int vdeg_c = (tid < lim) ? (int)c.vn_deg[tid / LPN] : 0;
-                if (tid < lim) issue(0, tid, vdeg_c);
-                tileh_cp_async_commit();
-                int vdeg_n = (tid + nt < lim) ? (int)c.vn_deg[(tid + nt) / LPN] : 0;
-                int st = 0;
-                for (int t = tid; t < lim; t += nt, st ^= 1) {
-                    if (t + nt < lim) issue(st ^ 1, t + nt, vdeg_n);
-                    tileh_cp_async_commit();
-                    const int vdeg_nn = (t + 2 * nt < lim) ? (int)c.vn_deg[(t + 2 * nt) / LPN] : 0;
-                    tileh_cp_async_wait<1>();
-                    const int i = t / LPN, deg = vdeg_c;
-                    const uint4 y = *slot(st, 0);
-                    uint32_t sum[4] = { y.x, y.y, y.z, y.w };
-#pragma unroll
-                    for (int sl = 0; sl < DVMAX; sl++) if (sl < deg) {                     // nlist order (exact here: any order gives the same sum)
-                        const uint4 x = *slot(st, 1 + sl);
-                        sum[0] = h2_bits(__hadd2(h2_from(sum[0]), h2_from(x.x))); sum[1] = h2_bits(__hadd2(h2_from(sum[1]), h2_from(x.y)));
-                        sum[2] = h2_bits(__hadd2(h2_from(sum[2]), h2_from(x.z))); sum[3] = h2_bits(__hadd2(h2_from(sum[3]), h2_from(x.w)));
-                    }
-#pragma unroll
-                    for (int sl = 0; sl < DVMAX; sl++) if (sl < deg) {
-                        const uint4 x = *slot(st, 1 + sl);
-                        uint4 o;
-                        o.x = h2_bits(__hsub2(h2_from(sum[0]), h2_from(x.x))); o.y = h2_bits(__hsub2(h2_from(sum[1]), h2_from(x.y)));
-                        o.z = h2_bits(__hsub2(h2_from(sum[2]), h2_from(x.z))); o.w = h2_bits(__hsub2(h2_from(sum[3]), h2_from(x.w)));
-                        msgv[((size_t)sl * N + i) * 8 + lgc] = o;
-                    }
-                    if (last) emit(i, lgc, sum, f0);
-                    vdeg_c = vdeg_n; vdeg_n = vdeg_nn;
-                }
-                tileh_cp_async_wait<0>();
-            } else {
-            int vdeg_n = (tid < N * LPN) ? (int)c.vn_deg[tid / LPN] : 0;
-            for (int t = tid; t < N * LPN; t += nt) {
+            {
+            const int lim = N * LPN;
+            auto slot = [&](const int st, const int k) -> uint4 * { return sbuf + ((size_t)(st * (1 + DVMAX) + k) * nt + tid); };
+            auto issue = [&](const int st, const int t, const int deg) {
                 const int i = t / LPN;
-                const int deg = vdeg_n;
-                if (t + nt < N * LPN) vdeg_n = c.vn_deg[(t + nt) / LPN];
-                uint32_t cm[DVMAX][4];
-                if (PF && t + nt < N * LPN) {
-                    const int in = (t + nt) / LPN;
-                    tileh_prefetch_l2(&yqv[(size_t)in * 8 + lgc]);
+                tileh_cp_async16(slot(st, 0), &yqv[(size_t)i * 8 + lgc]);
 #pragma unroll
-                    for (int s = 0; s < DVMAX; s++) if (s < vdeg_n) tileh_prefetch_l2(&msgv[((size_t)s * N + in) * 8 + lgc]);
-                }
-                const uint4 y = yqv[(size_t)i * 8 + lgc];
+                for (int sl = 0; sl < DVMAX; sl++) if (sl < deg) tileh_cp_async16(slot(st, 1 + sl), &msgv[((size_t)sl * N + i) * 8 + lgc]);
+            };
+            int vdeg_c = (tid < lim) ? (int)c.vn_deg[tid / LPN] : 0;
+            if (tid < lim) issue(0, tid, vdeg_c);
+            tileh_cp_async_commit();
+            int vdeg_n = (tid + nt < lim) ? (int)c.vn_deg[(tid + nt) / LPN] : 0;
+            int st = 0;
+            for (int t = tid; t < lim; t += nt, st ^= 1) {
+                if (t + nt < lim) issue(st ^ 1, t + nt, vdeg_n);
+                tileh_cp_async_commit();
+                const int vdeg_nn = (t + 2 * nt < lim) ? (int)c.vn_deg[(t + 2 * nt) / LPN] : 0;
+                tileh_cp_async_wait<1>();
+                const int i = t / LPN, deg = vdeg_c;
+                const uint4 y = *slot(st, 0);
                 uint32_t sum[4] = { y.x, y.y, y.z, y.w };
 #pragma unroll
-                for (int s = 0; s < DVMAX; s++) if (s < deg) {
-                    const uint4 x = msgv[((size_t)s * N + i) * 8 + lgc];
-                    cm[s][0] = x.x; cm[s][1] = x.y; cm[s][2] = x.z; cm[s][3] = x.w;
+                for (int sl = 0; sl < DVMAX; sl++) if (sl < deg) {                     // nlist order (exact here: any order gives the same sum)
+                    const uint4 x = *slot(st, 1 + sl);
+                    sum[0] = h2_bits(__hadd2(h2_from(sum[0]), h2_from(x.x))); sum[1] = h2_bits(__hadd2(h2_from(sum[1]), h2_from(x.y)));
+                    sum[2] = h2_bits(__hadd2(h2_from(sum[2]), h2_from(x.z))); sum[3] = h2_bits(__hadd2(h2_from(sum[3]), h2_from(x.w)));
                 }
 #pragma unroll
-                for (int s = 0; s < DVMAX; s++) if (s < deg) {                             // nlist order (exact here: any order gives the same sum)
-#pragma unroll
-                    for (int h = 0; h < 4; h++) sum[h] = h2_bits(__hadd2(h2_from(sum[h]), h2_from(cm[s][h])));
-                }
-#pragma unroll
-                for (int s = 0; s < DVMAX; s++) if (s < deg) {
+                for (int sl = 0; sl < DVMAX; sl++) if (sl < deg) {
+                    const uint4 x = *slot(st, 1 + sl);
                     uint4 o;
-                    o.x = h2_bits(__hsub2(h2_from(sum[0]), h2_from(cm[s][0]))); o.y = h2_bits(__hsub2(h2_from(sum[1]), h2_from(cm[s][1])));
-                    o.z = h2_bits(__hsub2(h2_from(sum[2]), h2_from(cm[s][2]))); o.w = h2_bits(__hsub2(h2_from(sum[3]), h2_from(cm[s][3])));
-                    msgv[((size_t)s * N + i) * 8 + lgc] = o;
+                    o.x = h2_bits(__hsub2(h2_from(sum[0]), h2_from(x.x))); o.y = h2_bits(__hsub2(h2_from(sum[1]), h2_from(x.y)));
+                    o.z = h2_bits(__hsub2(h2_from(sum[2]), h2_from(x.z))); o.w = h2_bits(__hsub2(h2_from(sum[3]), h2_from(x.w)));
+                    msgv[((size_t)sl * N + i) * 8 + lgc] = o;
                 }
                 if (last) emit(i, lgc, sum, f0);
+                vdeg_c = vdeg_n; vdeg_n = vdeg_nn;
             }
+            tileh_cp_async_wait<0>();
             }
             __syncthreads();
         }

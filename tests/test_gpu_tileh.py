@@ -27,7 +27,7 @@ def _same(a, b, soft=True):
 def _tile_decoder(name, kw):
     d = capi.Decoder(capi.Code(code_path(name)), abi.default_cfg(abi.KIND_MINSUM, precision=abi.PREC_F16X2, **kw))
     assert d.stats()[0], "the exact-lattice kernel was not selected"
-    assert d.geometry()["smem_bytes"] < 160 * 1024         # only the cp.async staging slots are in shared memory, not the messages (DVB-S2: 37.8 MB per tile)
+    assert d.geometry()["smem_bytes"] < 227 * 1024         # only the cp.async staging slots are in shared memory, not the messages (DVB-S2: 37.8 MB per tile)
     return d
 
 
