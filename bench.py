@@ -98,6 +98,11 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            # nvidia-smi attaches to every GPU of the box while it starts (a few hundred ms of driver work that can stall CUDA calls of
+            # all ranks): wait for its first row, so that only the periodic queries fall into the timed region
+            t_end = time.time() + 3.0
+            while not self.rows and time.time() < t_end and self.proc.poll() is None:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
 
